@@ -1,0 +1,160 @@
+/*
+ * prs_cabi.h — C-ABI of libparticlebot_b200.so (hand-written sm_100a CUDA behind plain pointers).
+ *
+ * Part 1 re-declares, name for name and argument for argument, the `extern "C"` launch wrappers
+ * the reference's host class binds (declared particlebot.cuh:15-121, defined
+ * particlebot_cuda.cu:26-384).  A maintainer of the reference links particlebot.cpp against this
+ * library INSTEAD of particlebot_cuda.o and nothing else changes.  Conventions
+ * kept from the reference: every pointer is a DEVICE pointer owned by the caller unless it says
+ * host; pos/vel arrays are float2-per-robot, rad/phase/absForce are float-per-robot, all in
+ * ORIGINAL robot order; no return codes — a CUDA error prints to stderr and exit(EXIT_FAILURE)s
+ * (include/helper_cuda.h:999-1031); work is issued on one stream (default: the legacy default
+ * stream) and nothing synchronises the host except threadSync/copyArrayFromDevice/copyArrayToDevice.
+ *
+ * Part 2 is what the reference does not have: stream selection, a parametric world wall, the
+ * fused whole-step path, device-side light-distance reduction, and the simulation-object API
+ * (the C++ class Particlebot of include/prs_particlebot.hpp wrapped for C/ctypes callers).
+ */
+#ifndef PRS_CABI_H
+#define PRS_CABI_H
+
+#include <stddef.h>
+#include "prs_simparams.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct cudaGraphicsResource;
+struct curandStateXORWOW; /* 48-byte generator state of the toolkit's device API */
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1 — the reference's entry points
+ * ------------------------------------------------------------------------------------------ */
+void cudaInit(int argc, char **argv);                 /* particlebot_cuda.cu:29  (-device=N honoured) */
+void cudaGLInit(int argc, char **argv);               /* :43 headless: same as cudaInit */
+void allocateArray(void **devPtr, size_t size);       /* :49 */
+void freeArray(void *devPtr);                         /* :54 */
+void threadSync(void);                                /* :59 */
+void copyArrayToDevice(void *device, const void *host, int offset, int size);  /* :64 */
+/* :95 — a non-null resource means "map the GL buffer first" in the reference; headless builds
+ * have no GL buffers, so a non-null resource is an error (exit), never silently ignored. */
+void copyArrayFromDevice(void *host, const void *device, struct cudaGraphicsResource **res, int size);
+/* GL interop (:69-93): present so that the reference host code links; they abort when called
+ * because this library is built without OpenGL (rendering is optional, north_star (5)). */
+void registerGLBufferObject(unsigned vbo, struct cudaGraphicsResource **res);
+void unregisterGLBufferObject(struct cudaGraphicsResource *res);
+void *mapGLBufferObject(struct cudaGraphicsResource **res);
+void unmapGLBufferObject(struct cudaGraphicsResource *res);
+
+void setParameters(SimParams *hostParams);            /* :111 params + 7 obstacle arrays -> constant memory */
+
+unsigned iDivUp(unsigned a, unsigned b);              /* :126 */
+
+void integrateSystem(float *pos, float *vel, float *rad, float deltaTime, unsigned nCells,
+                     float time);                     /* :145 + kernel_impl.cuh:53-103 */
+void calcHash(unsigned *gridParticlebotHash, unsigned *gridParticlebotIndex, float *pos,
+              int nCells);                            /* :162 + kernel_impl.cuh:446-465 */
+void sortParticlebots(unsigned *dGridParticlebotHash, unsigned *dGridParticlebotIndex,
+                      unsigned nCells);               /* :377 stable sort by key, in place */
+void reorderDataAndFindCellStart(unsigned *cellStart, unsigned *cellEnd, float *sortedPos,
+                                 float *sortedVel, float *sortedRad, unsigned *gridParticlebotHash,
+                                 unsigned *gridParticlebotIndex, float *oldPos, float *oldVel,
+                                 float *oldRad, unsigned nCells, unsigned numCells); /* :284 */
+void collide(float *newVel, float *absForce_a, float *absForce_r, float *sortedPos,
+             float *sortedVel, float *sortedRad, unsigned *gridParticlebotIndex,
+             unsigned *cellStart, unsigned *cellEnd, unsigned nCells, unsigned numCells,
+             float deltaTime);                        /* :331 + kernel_impl.cuh:541-831 */
+void updateRad_light_wave(float *pos, float *absForce_a, float *absForce_r, float *rad,
+                          float *phase, float time, float deltaTime, int *dead, int nCells); /* :180 */
+void updatePhase(float *pos, float *phase, float spacing, float max_d, float min_d, int nCells); /* :210 */
+void curand_setup(struct curandStateXORWOW *state, int N);                      /* :198 */
+void add_normal_noise(struct curandStateXORWOW *state, float *val, float std, int N); /* :204 */
+/* :241 centroid of pos[0..n) scaled by 1/n, y tagged +2000, stored at pos[n + ((int)(time/hist_int))%hist_steps]
+ * (the render trail).  temppos/temppos1 are scratch of >= n float2 as in the reference. */
+void calcCOG(float *pos, float *temppos, float *temppos1, int nCells, float time, int hist_steps,
+             float hist_int);
+/* :227 colours for the point-sprite renderer */
+void updateCol(float *rad, float *col, int nCells, float *pos, float *phase, int *dead);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2 — B200 additions
+ * ------------------------------------------------------------------------------------------ */
+const char *prs_version(void);
+void prs_set_stream(void *cuda_stream);   /* all later launches/copies go to this cudaStream_t */
+void *prs_get_stream(void);
+/* wall position of integrate; the reference hard-codes 64 (kernel_impl.cuh:75-97) */
+void prs_set_world_half_extent(float half);
+float prs_get_world_half_extent(void);
+/* collide arithmetic: 0 = "exact" (operation order of the reference, IEEE div/sqrt),
+ * 1 = "fast" (one reciprocal per pair, shared-memory tiles); both are parity-tested */
+void prs_set_collide_mode(int mode);
+int prs_get_collide_mode(void);
+/* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
+unsigned long long prs_launch_count(int reset);
+
+/* device-side replacement of the host loop particlebot.cpp:214-228: d_min_d[0] = min_i |light-p_i| */
+void prs_min_light_distance(const float *pos, int n, float *d_min_d);
+/* updatePhase reading min_d from device memory (no host round trip) */
+void prs_update_phase_dev(const float *pos, float *phase, float spacing, const float *d_min_d, int n);
+/* swarm centroid sum_i pos_i / n into d_out[0..1] (observable; deterministic two-stage tree) */
+void prs_centroid(const float *pos, int n, float *d_scratch, float *d_out);
+
+/* sort with caller-visible key width: keys must be < 2^key_bits; out-of-place when out_* != in_* */
+void prs_sort_pairs(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys,
+                    unsigned *out_vals, unsigned n, int key_bits);
+
+/* Fused whole step on the reference's buffers (same observable results as the call sequence
+ * updateRad_light_wave -> integrateSystem -> [calcHash, sortParticlebots] ->
+ * reorderDataAndFindCellStart -> collide of particlebot.cpp:238-296):
+ *   do_sort != 0 on steps where the sort gate fires. */
+typedef struct {
+  float *pos, *vel, *rad, *phase, *absForce_a, *absForce_r; int *dead;   /* original order */
+  unsigned *hash, *index, *cellStart, *cellEnd;                          /* grid tables */
+  float *sortedPos, *sortedVel, *sortedRad;                              /* sorted copies */
+  unsigned nCells, numCells;
+} prs_step_buffers;
+void prs_fused_step(const prs_step_buffers *b, float time, float deltaTime, int do_sort);
+
+/* ---- simulation object (class Particlebot, include/prs_particlebot.hpp) for C callers ---- */
+typedef struct prs_sim prs_sim;
+/* fills *p with the defaults of main.cpp:833-911 and the derived grid of :932-939; extras receive
+ * timestep, sort_interval, dump_interval (floats).  Obstacle arrays are owned by the library. */
+typedef struct {
+  float timestep, sort_interval, dump_interval;
+  float camera_x, camera_y, light_radius;
+  int display_interval, video_interval;
+  char csv_filename[300], video_filename[300];
+} prs_run_options;
+void prs_params_defaults(SimParams *p, prs_run_options *opt);
+/* parses a .cfg file with the reference's grammar and quirks (main.cpp:594-816, 913-928) on top
+ * of *p / *opt, then derives cellSize/gridSize/numCells/worldOrigin.  Returns 0, or -1 if the
+ * file cannot be opened (the reference silently runs with defaults then). */
+int prs_params_load_cfg(const char *path, SimParams *p, prs_run_options *opt);
+void prs_params_derive_grid(SimParams *p);
+/* synthetic worlds of SURVEY.md §8d: grid_dim cells per axis (power of two), world half extent */
+void prs_params_set_world(SimParams *p, unsigned grid_dim, float world_half);
+
+/* backend: 0 = fused native path, 1 = native per-call path (the reference's call sequence on this
+ * library's entry points), 2 = per-call path on an external library with the reference's ABI
+ * (path given; used to drive oracle/_ref/libprs_refcuda.so from tests and bench.py) */
+prs_sim *prs_sim_create(const SimParams *p, float world_half, int backend, const char *ext_lib);
+void prs_sim_destroy(prs_sim *s);
+void prs_sim_srand(prs_sim *s, unsigned seed);            /* main.cpp:929 */
+void prs_sim_reset(prs_sim *s);                           /* Particlebot::reset */
+void prs_sim_init_hex(prs_sim *s, unsigned nx, unsigned ny, float pitch, float jitter, unsigned seed); /* synthetic swarms */
+int prs_sim_update(prs_sim *s, float dt, float sort_interval); /* Particlebot::update; returns 1 when time > max_time */
+float prs_sim_time(const prs_sim *s);
+void prs_sim_sync(prs_sim *s);
+/* which: ParticlebotArray values, plus 100 absForce_a, 101 absForce_r, 102 hash, 103 index,
+ * 104 cellStart, 105 cellEnd, 106 sortedPos, 107 sortedVel, 108 sortedRad, 109 rng state */
+void *prs_sim_device_ptr(prs_sim *s, int which);
+void prs_sim_get(prs_sim *s, int which, void *host, size_t bytes);
+void prs_sim_set(prs_sim *s, int which, const void *host, size_t offset_bytes, size_t bytes);
+/* dumpParticlebot (particlebot.cpp:303-367): CSV row when the dump gate fires */
+void prs_sim_dump(prs_sim *s, void *FILE_ptr, float dump_interval, unsigned testing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRS_CABI_H */

@@ -1,0 +1,216 @@
+"""particlerobotsimulations_b200 — ctypes view of libparticlebot_b200.so.
+
+The product is the C++/CUDA library (csrc/, include/): hand-written sm_100a kernels behind the
+reference's own `extern "C"` entry points plus the headless `Particlebot` class.  This module
+only loads it for tests, bench.py and Python users; there is NO CPU fallback — if the library is
+missing or no CUDA device is present, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libparticlebot_b200.so")
+
+# array selectors of prs_sim_get/set/device_ptr (ParticlebotArray + additions, prs_cabi.h)
+POSITION, VELOCITY, RADII, PHASE, FREQUENCY, DEAD = range(6)
+ABSFORCE_A, ABSFORCE_R, HASH, INDEX, CELLSTART, CELLEND, SORTEDPOS, SORTEDVEL, SORTEDRAD, RNGSTATE = range(100, 110)
+BACKEND_FUSED, BACKEND_PERCALL, BACKEND_EXTERNAL = 0, 1, 2
+
+
+class _U2(C.Structure):
+    _fields_ = [("x", C.c_uint), ("y", C.c_uint)]
+
+
+class _F2(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+
+class SimParams(C.Structure):
+    """Mirror of include/prs_simparams.h (reference particlebot_kernel.cuh:58-120), 256 bytes."""
+
+    _fields_ = [
+        ("gridSize", _U2), ("numCells", C.c_uint), ("_pad0", C.c_uint),
+        ("worldOrigin", _F2), ("cellSize", _F2),
+        ("nCells", C.c_uint), ("nDead", C.c_int), ("maxParticlebotsPerCell", C.c_uint),
+        ("gravity", C.c_float), ("spring", C.c_float), ("damping", C.c_float), ("shear", C.c_float),
+        ("attraction", C.c_float), ("boundaryDamping", C.c_float), ("friction", C.c_float),
+        ("massFactor", C.c_float), ("frictionFactor", C.c_float), ("radFactor", C.c_float),
+        ("attractionFactor", C.c_float), ("constraint", C.c_float), ("constraint_contraction", C.c_float),
+        ("centroid_steps", C.c_int), ("centroid_int", C.c_float), ("centroid_radius", C.c_float),
+        ("light_x", C.c_float), ("light_y", C.c_float), ("phase_update_interval", C.c_float),
+        ("control", C.c_int), ("config", C.c_int),
+        ("min_radius", C.c_float), ("max_radius", C.c_float), ("rise_period", C.c_float), ("freq", C.c_float),
+        ("nobstacles", C.c_int),
+        ("x1obs", C.POINTER(C.c_float)), ("x2obs", C.POINTER(C.c_float)),
+        ("y1obs", C.POINTER(C.c_float)), ("y2obs", C.POINTER(C.c_float)),
+        ("n_cir_obstacles", C.c_int),
+        ("x_cir_obs", C.POINTER(C.c_float)), ("y_cir_obs", C.POINTER(C.c_float)), ("r_cir_obs", C.POINTER(C.c_float)),
+        ("Nx", C.c_int), ("phase_std", C.c_float), ("seed", C.c_uint),
+        ("light_shadow", C.c_uint), ("testing", C.c_uint), ("constrained_contraction", C.c_uint),
+        ("display_shadow", C.c_uint), ("time_to_dead", C.c_float), ("max_time", C.c_float),
+    ]
+
+
+assert C.sizeof(SimParams) == 256, C.sizeof(SimParams)
+
+
+class RunOptions(C.Structure):
+    _fields_ = [
+        ("timestep", C.c_float), ("sort_interval", C.c_float), ("dump_interval", C.c_float),
+        ("camera_x", C.c_float), ("camera_y", C.c_float), ("light_radius", C.c_float),
+        ("display_interval", C.c_int), ("video_interval", C.c_int),
+        ("csv_filename", C.c_char * 300), ("video_filename", C.c_char * 300),
+    ]
+
+
+class StepBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "pos", "vel", "rad", "phase", "absForce_a", "absForce_r", "dead", "hash", "index", "cellStart", "cellEnd",
+        "sortedPos", "sortedVel", "sortedRad")] + [("nCells", C.c_uint), ("numCells", C.c_uint)]
+
+
+_lib = None
+
+# name -> (restype, argtypes); the reference's entry points first (include/prs_cabi.h part 1)
+_VP, _F, _I, _U = C.c_void_p, C.c_float, C.c_int, C.c_uint
+SIGNATURES = {
+    "cudaInit": (None, [_I, _VP]), "cudaGLInit": (None, [_I, _VP]),
+    "allocateArray": (None, [C.POINTER(_VP), C.c_size_t]), "freeArray": (None, [_VP]), "threadSync": (None, []),
+    "copyArrayToDevice": (None, [_VP, _VP, _I, _I]), "copyArrayFromDevice": (None, [_VP, _VP, _VP, _I]),
+    "registerGLBufferObject": (None, [_U, _VP]), "unregisterGLBufferObject": (None, [_VP]),
+    "mapGLBufferObject": (_VP, [_VP]), "unmapGLBufferObject": (None, [_VP]),
+    "setParameters": (None, [C.POINTER(SimParams)]), "iDivUp": (_U, [_U, _U]),
+    "integrateSystem": (None, [_VP, _VP, _VP, _F, _U, _F]),
+    "calcHash": (None, [_VP, _VP, _VP, _I]),
+    "sortParticlebots": (None, [_VP, _VP, _U]),
+    "reorderDataAndFindCellStart": (None, [_VP] * 10 + [_U, _U]),
+    "collide": (None, [_VP] * 9 + [_U, _U, _F]),
+    "updateRad_light_wave": (None, [_VP, _VP, _VP, _VP, _VP, _F, _F, _VP, _I]),
+    "updatePhase": (None, [_VP, _VP, _F, _F, _F, _I]),
+    "curand_setup": (None, [_VP, _I]), "add_normal_noise": (None, [_VP, _VP, _F, _I]),
+    "calcCOG": (None, [_VP, _VP, _VP, _I, _F, _I, _F]),
+    "updateCol": (None, [_VP, _VP, _I, _VP, _VP, _VP]),
+    # part 2
+    "prs_version": (C.c_char_p, []), "prs_set_stream": (None, [_VP]), "prs_get_stream": (_VP, []),
+    "prs_set_world_half_extent": (None, [_F]), "prs_get_world_half_extent": (_F, []),
+    "prs_set_collide_mode": (None, [_I]), "prs_get_collide_mode": (_I, []),
+    "prs_launch_count": (C.c_ulonglong, [_I]),
+    "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),
+    "prs_centroid": (None, [_VP, _I, _VP, _VP]),
+    "prs_sort_pairs": (None, [_VP, _VP, _VP, _VP, _U, _I]),
+    "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
+    "prs_params_defaults": (None, [C.POINTER(SimParams), C.POINTER(RunOptions)]),
+    "prs_params_load_cfg": (_I, [C.c_char_p, C.POINTER(SimParams), C.POINTER(RunOptions)]),
+    "prs_params_derive_grid": (None, [C.POINTER(SimParams)]),
+    "prs_params_set_world": (None, [C.POINTER(SimParams), _U, _F]),
+    "prs_sim_create": (_VP, [C.POINTER(SimParams), _F, _I, C.c_char_p]), "prs_sim_destroy": (None, [_VP]),
+    "prs_sim_srand": (None, [_VP, _U]), "prs_sim_reset": (None, [_VP]),
+    "prs_sim_init_hex": (None, [_VP, _U, _U, _F, _F, _U]),
+    "prs_sim_update": (_I, [_VP, _F, _F]), "prs_sim_time": (_F, [_VP]), "prs_sim_sync": (None, [_VP]),
+    "prs_sim_device_ptr": (_VP, [_VP, _I]), "prs_sim_get": (None, [_VP, _I, _VP, C.c_size_t]),
+    "prs_sim_set": (None, [_VP, _I, _VP, C.c_size_t, C.c_size_t]),
+    "prs_sim_dump": (None, [_VP, _VP, _F, _U]),
+}
+
+
+def bind_signatures(lib, names=None):
+    for name, (res, args) in SIGNATURES.items():
+        if names is not None and name not in names:
+            continue
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def lib():
+    """The product library.  Raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python particlerobotsimulations_b200/build.py` "
+                "(nvcc, sm_100a).  There is no CPU or PyTorch fallback.")
+        _lib = bind_signatures(C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW))
+    return _lib
+
+
+def default_params():
+    p, o = SimParams(), RunOptions()
+    lib().prs_params_defaults(C.byref(p), C.byref(o))
+    return p, o
+
+
+def load_cfg(path):
+    """Defaults (main.cpp:833-911) + .cfg file (main.cpp:594-816, 913-928) + derived grid (:932-939)."""
+    p, o = default_params()
+    rc = lib().prs_params_load_cfg(os.fsencode(path), C.byref(p), C.byref(o))
+    if rc != 0:
+        raise FileNotFoundError(path)
+    return p, o
+
+
+_DTYPES = {POSITION: (np.float32, 2), VELOCITY: (np.float32, 2), RADII: (np.float32, 1), PHASE: (np.float32, 1),
+           FREQUENCY: (np.float32, 1), DEAD: (np.int32, 1), ABSFORCE_A: (np.float32, 1), ABSFORCE_R: (np.float32, 1),
+           HASH: (np.uint32, 1), INDEX: (np.uint32, 1), SORTEDPOS: (np.float32, 2), SORTEDVEL: (np.float32, 2),
+           SORTEDRAD: (np.float32, 1)}
+
+
+class Simulation:
+    """`class Particlebot` (include/prs_particlebot.hpp) through its C wrappers."""
+
+    def __init__(self, params, world_half=64.0, backend=BACKEND_FUSED, external_library=None):
+        self._lib = lib()
+        self.params = params
+        self.n = int(params.nCells)
+        ext = os.fsencode(external_library) if external_library else None
+        self._h = self._lib.prs_sim_create(C.byref(params), world_half, backend, ext)
+
+    def close(self):
+        if self._h:
+            self._lib.prs_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def srand(self, seed):
+        self._lib.prs_sim_srand(self._h, seed)
+
+    def reset(self):
+        self._lib.prs_sim_reset(self._h)
+
+    def init_hex(self, nx, ny, pitch, jitter, seed):
+        self._lib.prs_sim_init_hex(self._h, nx, ny, pitch, jitter, seed)
+
+    def update(self, dt, sort_interval):
+        return bool(self._lib.prs_sim_update(self._h, dt, sort_interval))
+
+    def sync(self):
+        self._lib.prs_sim_sync(self._h)
+
+    @property
+    def time(self):
+        return float(self._lib.prs_sim_time(self._h))
+
+    def device_ptr(self, which):
+        return self._lib.prs_sim_device_ptr(self._h, which)
+
+    def get(self, which):
+        if which in (CELLSTART, CELLEND):
+            out = np.empty(int(self.params.numCells), np.uint32)
+        else:
+            dt, w = _DTYPES[which]
+            out = np.empty((self.n, w) if w > 1 else (self.n,), dt)
+        self._lib.prs_sim_get(self._h, which, out.ctypes.data, out.nbytes)
+        return out
+
+    def set(self, which, arr, offset_items=0):
+        dt, w = _DTYPES[which]
+        a = np.ascontiguousarray(arr, dt)
+        self._lib.prs_sim_set(self._h, which, a.ctypes.data, offset_items * a.itemsize * w, a.nbytes)

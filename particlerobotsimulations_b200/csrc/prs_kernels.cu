@@ -1,0 +1,675 @@
+/*
+ * prs_kernels.cu — hand-written sm_100a kernels of the per-timestep particle-robot update and the
+ * C-ABI launch wrappers that carry the reference's names (include/prs_cabi.h part 1).
+ *
+ * Every kernel cites the reference code whose RESULT it reproduces; the implementation is new:
+ *   - one constant block instead of eight symbols, one stream, no per-call allocation, no host sync;
+ *   - calcHash / integrate / controller are streaming kernels (and exist fused, k_control_integrate_hash);
+ *   - sort is the onesweep radix sort of prs_onesweep.cuh;
+ *   - collide exists in an "exact" variant (operation order of the reference) and a "fast" variant
+ *     (shared-memory row tiles, one reciprocal per pair) — prs_collide.cuh.
+ *
+ * Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo   (NO --use_fast_math: hashes
+ * need IEEE divides, the reference is built without it, Makefile:78-84).
+ */
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "prs_cabi.h"
+#include "prs_device.cuh"
+#include "prs_onesweep.cuh"
+#include "prs_host_state.h"
+
+#include "prs_collide.cuh"
+
+using namespace prs;
+
+/* ------------------------------------------------------------------------------------------
+ * host-side state of the library (one simulation context per process, like the reference's
+ * global __constant__ params)
+ * ------------------------------------------------------------------------------------------ */
+PrsHostState g_prs;
+
+void prs_fail(const char *what, cudaError_t e, const char *file, int line) {
+  /* error convention of the reference: message on stderr, exit(EXIT_FAILURE)
+   * (include/helper_cuda.h:999-1031) */
+  fprintf(stderr, "%s(%i) : CUDA error %d (%s) in %s\n", file, line, (int)e, cudaGetErrorString(e), what);
+  exit(EXIT_FAILURE);
+}
+
+#define PRS_LAUNCH(kernel, grid, block, smem, ...)                                   \
+  do {                                                                               \
+    kernel<<<(grid), (block), (smem), g_prs.stream>>>(__VA_ARGS__);                  \
+    g_prs.launches++;                                                                \
+    cudaError_t e_ = cudaGetLastError();                                             \
+    if (e_ != cudaSuccess) prs_fail(#kernel, e_, __FILE__, __LINE__);                \
+  } while (0)
+
+static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+/* ------------------------------------------------------------------------------------------
+ * kernels
+ * ------------------------------------------------------------------------------------------ */
+
+/* cell hash per robot + identity index  (result of calcHashD, kernel_impl.cuh:446-465) */
+__global__ void __launch_bounds__(256) k_calc_hash(uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
+                                                   const float2 *__restrict__ pos, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 p = pos[i];
+  const int2 g = cell_of(p.x, p.y);
+  hash[i] = cell_hash(g.x, g.y);
+  index[i] = i;
+}
+
+/* cell table + gather into sorted order (result of reorderDataAndFindCellStartD, :469-538).
+ * The previous key comes from a second (L1-resident) load instead of a shared-memory halo. */
+__global__ void __launch_bounds__(256)
+k_reorder(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, float2 *__restrict__ sortedPos,
+          float2 *__restrict__ sortedVel, float *__restrict__ sortedRad, const uint32_t *__restrict__ hash,
+          const uint32_t *__restrict__ index, const float2 *__restrict__ pos, const float2 *__restrict__ vel,
+          const float *__restrict__ rad, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t h = hash[k];
+  const uint32_t src = index[k];
+  const uint32_t hp = (k > 0) ? hash[k - 1] : 0u;
+  const float2 p = pos[src];
+  const float2 v = vel[src];
+  const float r = rad[src];
+  if (k == 0 || h != hp) {
+    cellStart[h] = k;
+    if (k > 0) cellEnd[hp] = k;
+  }
+  if (k == n - 1) cellEnd[h] = k + 1;
+  sortedRad[k] = r;
+  sortedPos[k] = p;
+  sortedVel[k] = v;
+}
+
+/* Euler step + wall bounce for one robot (result of integrate_functor, :53-103) */
+__device__ __forceinline__ void integrate_one(float2 &pos, float2 &vel, float rad, float dt) {
+  const float W = c_prm.world_half;
+  const float bd = c_prm.p.boundaryDamping;
+  pos.x += vel.x * dt;
+  pos.y += vel.y * dt;
+  if (pos.x > W - rad) { pos.x = W - rad; vel.x *= bd; }
+  if (pos.x < -W + rad) { pos.x = -W + rad; vel.x *= bd; }
+  if (pos.y > W - rad) { pos.y = W - rad; vel.y *= bd; }
+  if (pos.y < -W + rad) { pos.y = -W + rad; vel.y *= bd; }
+}
+
+__global__ void __launch_bounds__(256) k_integrate(float2 *__restrict__ pos, float2 *__restrict__ vel,
+                                                   const float *__restrict__ rad, float dt, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 p = pos[i], v = vel[i];
+  integrate_one(p, v, rad[i], dt);
+  pos[i] = p;
+  vel[i] = v;
+}
+
+/* radius-phase controller for one robot (result of updateRad_light_wave, :124-181); returns the
+ * new radius, or the old one when the robot holds its radius */
+template <bool CC>
+__device__ __forceinline__ float controller_one(float rad, float phase, float fr, float fa, float time, float dt) {
+  const SimParams &P = c_prm.p;
+  if (phase > 10000000.0f) return rad;
+  const float period = (P.Nx + 1) * P.rise_period;
+  float t1 = time + phase;
+  if (t1 < 0) t1 = t1 + 100 * (P.Nx + 1) * P.rise_period;
+  if (t1 >= period) t1 = t1 - period * floorf(t1 / period);
+  if (t1 >= 2 * P.rise_period) return rad;
+  float target;
+  if (t1 <= P.rise_period)
+    target = P.min_radius + (P.max_radius - P.min_radius) / P.rise_period * t1;
+  else
+    target = P.max_radius + (P.min_radius - P.max_radius) / P.rise_period * (t1 - P.rise_period);
+  const float dr1 = target - rad;
+  float dr = 0;
+  const float max_speed = 0.1f;
+  float torque = dr1 * P.constraint * rad / max_speed / P.max_radius / dt;
+  torque = fminf(torque, P.constraint);
+  if (dr1 > 0) {
+    if (torque / rad > fr) dr = max_speed * P.max_radius / P.constraint * (torque / rad - fr) * dt;
+  } else {
+    if (CC) {
+      if (-P.constraint_contraction * dr1 > fa * rad)
+        dr = (P.constraint_contraction * dr1 + fa * rad) / (P.constraint_contraction);
+      dr = fmaxf(dr, -P.max_radius * dt);
+    } else {
+      dr = dr1;
+    }
+  }
+  dr = rad + dr;
+  if (dr > P.max_radius) dr = P.max_radius;
+  if (dr < P.min_radius) dr = P.min_radius;
+  return dr;
+}
+
+__global__ void __launch_bounds__(256)
+k_update_rad(const float *__restrict__ fa, const float *__restrict__ fr, float *__restrict__ rad,
+             const float *__restrict__ phase, float time, float dt, const int *__restrict__ dead, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (dead[i]) return;
+  const float r = rad[i];
+  float rn;
+  if (c_prm.p.constrained_contraction) rn = controller_one<true>(r, phase[i], fr[i], fa[i], time, dt);
+  else rn = controller_one<false>(r, phase[i], fr[i], 0.0f, time, dt);
+  if (rn != r) rad[i] = rn;
+}
+
+/* Fused K1: controller -> integrate -> (hash) with one read and one write of each robot
+ * (north_star (4); SURVEY.md §8d K1: 60 B per robot on sort steps). */
+template <bool DO_SORT>
+__global__ void __launch_bounds__(256)
+k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, float *__restrict__ rad,
+                         const float *__restrict__ phase, const float *__restrict__ fa, const float *__restrict__ fr,
+                         const int *__restrict__ dead, uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
+                         float time, float dt, int run_controller, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 p = pos[i];
+  float2 v = vel[i];
+  float r = rad[i];
+  if (run_controller && !dead[i]) {
+    float rn;
+    if (c_prm.p.constrained_contraction) rn = controller_one<true>(r, phase[i], fr[i], fa[i], time, dt);
+    else rn = controller_one<false>(r, phase[i], fr[i], 0.0f, time, dt);
+    if (rn != r) { rad[i] = rn; r = rn; }
+  }
+  const float2 v0 = v;
+  integrate_one(p, v, r, dt);
+  pos[i] = p;
+  if (v.x != v0.x || v.y != v0.y) vel[i] = v;
+  if (DO_SORT) {
+    const int2 g = cell_of(p.x, p.y);
+    hash[i] = cell_hash(g.x, g.y);
+    index[i] = i;
+  }
+}
+
+/* ---- light shadow tests (results of checkIntersectionLine/Circle/checkIntersection, :184-262) ---- */
+__device__ int seg_hit(float x0, float y0, float x1, float y1, float x3, float y3, float x4, float y4) {
+  if (fabsf((x4 - x3) / (x1 - x0)) == fabsf((y4 - y3) / (y1 - y0))) return 0;
+  float t, t1;
+  if (fabsf(y4 - y3) > 0) {
+    t = (x3 - x0 - (y3 - y0) * (x3 - x4) / (y3 - y4)) * ((y3 - y4) / ((x1 - x0) * (y3 - y4) - (y1 - y0) * (x3 - x4)));
+    if (t <= 0 || t >= 1) return 0;
+    t1 = (y3 - y0 - t * (y1 - y0)) / (y3 - y4);
+    if (t1 <= 0 || t1 >= 1) return 0;
+  } else if (fabsf(x4 - x3) > 0) {
+    t = (y3 - y0 - (x3 - x0) * (y3 - y4) / (x3 - x4)) * ((x3 - x4) / ((y1 - y0) * (x3 - x4) - (x1 - x0) * (y3 - y4)));
+    if (t <= 0 || t >= 1) return 0;
+    t1 = (x3 - x0 - t * (x1 - x0)) / (x3 - x4);
+    if (t1 <= 0 || t1 >= 1) return 0;
+  } else {
+    return 0;
+  }
+  return 1;
+}
+__device__ int disc_hit(float lx, float ly, float px, float py, float ox, float oy, float orad) {
+  const float C1 = powf(lx, 2) + powf(ly, 2), C2 = powf(px, 2) + powf(py, 2), C3 = powf(ox, 2) + powf(oy, 2);
+  const float C4 = lx * px + ly * py, C5 = lx * ox + ly * oy, C6 = px * ox + py * oy;
+  const float A = C1 + C2 - 2 * C4;
+  const float B = -2 * C1 + 2 * C4 + 2 * C5 - 2 * C6;
+  const float C = C1 + C3 - 2 * C5 - powf(orad, 2);
+  const float D = powf(B, 2) - 4 * A * C;
+  if (D >= 0) {
+    const float R1 = (-B + powf(D, 0.5f)) / 2 / A, R2 = (-B - powf(D, 0.5f)) / 2 / A;
+    if (R1 > 0 && R1 < 1) return 1;
+    if (R2 > 0 && R2 < 1) return 1;
+  }
+  return 0;
+}
+__device__ int in_shadow(float px, float py) {
+  const float lx = c_prm.p.light_x, ly = c_prm.p.light_y;
+  for (int i = 0; i < c_prm.p.n_cir_obstacles; i++)
+    if (disc_hit(lx, ly, px, py, c_prm.x_cir[i], c_prm.y_cir[i], c_prm.r_cir[i])) return 1;
+  for (int i = 0; i < c_prm.p.nobstacles; i++) {
+    const float x1 = c_prm.x1obs[i], x2 = c_prm.x2obs[i], y1 = c_prm.y1obs[i], y2 = c_prm.y2obs[i];
+    if (seg_hit(lx, ly, px, py, x1, y1, x1, y2)) return 1;
+    if (seg_hit(lx, ly, px, py, x1, y2, x2, y2)) return 1;
+    if (seg_hit(lx, ly, px, py, x2, y2, x2, y1)) return 1;
+    if (seg_hit(lx, ly, px, py, x2, y1, x1, y1)) return 1;
+  }
+  return 0;
+}
+
+/* light-distance phase offsets (result of updatePhase, :264-290); min_d from a scalar or from
+ * device memory (d_min_d != nullptr) */
+__global__ void __launch_bounds__(256) k_update_phase(const float2 *__restrict__ pos, float *__restrict__ phase,
+                                                      float spacing, float min_d_host, const float *__restrict__ d_min_d,
+                                                      uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float min_d = d_min_d ? d_min_d[0] : min_d_host;
+  const float2 p = pos[i];
+  const float dist = norm2(mk(p.x, p.y) - mk(c_prm.p.light_x, c_prm.p.light_y));
+  int visible = 1;
+  if (c_prm.p.light_shadow) {
+    if (in_shadow(p.x, p.y)) visible = 0;
+  }
+  if (!visible) {
+    if (c_prm.p.light_shadow == 1) phase[i] = -(c_prm.p.Nx - 1) * c_prm.p.rise_period;
+    if (c_prm.p.light_shadow == 2) phase[i] = 9999999999.0f;
+  } else {
+    phase[i] = (min_d - dist) / (spacing)*c_prm.p.rise_period;
+  }
+}
+
+/* min_i |light - p_i| on the device.  The reference does this on the host with glibc powf
+ * (particlebot.cpp:214-228); the _rn intrinsics below evaluate the same correctly rounded
+ * square / sum / square root (no FMA), and positive floats order like their bit patterns. */
+__global__ void __launch_bounds__(256) k_min_light_distance(const float2 *__restrict__ pos, uint32_t n,
+                                                            uint32_t *__restrict__ out_bits) {
+  float m = __int_as_float(0x7f7f7f7f);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float2 p = pos[i];
+    const float dx = c_prm.p.light_x - p.x, dy = c_prm.p.light_y - p.y;
+    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    m = fminf(m, d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(out_bits, (uint32_t)__float_as_int(m));
+}
+
+/* XORWOW per robot, the toolkit's own device API so the stream is the reference's bit for bit
+ * (results of curand_setup_kernel / add_normal_noise_kernel, :36-51) */
+__global__ void __launch_bounds__(256) k_curand_setup(curandState *__restrict__ st, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) curand_init(c_prm.p.seed, i, 0, &st[i]);
+}
+__global__ void __launch_bounds__(256) k_add_normal_noise(curandState *__restrict__ st, float *__restrict__ val,
+                                                          float std, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float noise = std * curand_normal(st + i);
+  val[i] += noise;
+}
+
+/* one level of the reference's 64-wide centroid tree (calcCOG/calcCOG1, :295-349): block b sums
+ * in[b*64 .. b*64+63] pairwise (+32, +16, ... +1); the last level scales and tags y with +2000 */
+__global__ void __launch_bounds__(64) k_cog_level(const float2 *__restrict__ in, float2 *__restrict__ out, int n,
+                                                  int last, float mul) {
+  __shared__ float2 s[64];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * 64 + tid;
+  float2 a = make_float2(0.0f, 0.0f);
+  if (i < n) { const float2 t = in[i]; a.x += t.x; a.y += t.y; }
+  s[tid] = a;
+  __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) {
+    if (tid < o) {
+      const float2 b = s[tid + o];
+      s[tid].x += b.x;
+      s[tid].y += b.y;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float2 r = s[0];
+    if (last) { r.x *= mul; r.y *= mul; r.y = r.y + 2000.0f; }
+    out[blockIdx.x] = r;
+  }
+}
+
+/* swarm centroid as an observable: double accumulation, fixed two-stage shape (deterministic) */
+__global__ void __launch_bounds__(256) k_centroid_partial(const float2 *__restrict__ pos, uint32_t n, double2 *__restrict__ part) {
+  __shared__ double sx[256], sy[256];
+  double ax = 0, ay = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float2 p = pos[i];
+    ax += p.x; ay += p.y;
+  }
+  sx[threadIdx.x] = ax; sy[threadIdx.x] = ay;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sx[threadIdx.x] += sx[threadIdx.x + o]; sy[threadIdx.x] += sy[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = make_double2(sx[0], sy[0]);
+}
+__global__ void k_centroid_final(const double2 *__restrict__ part, int nb, uint32_t n, float *__restrict__ out) {
+  double ax = 0, ay = 0;
+  for (int b = 0; b < nb; b++) { ax += part[b].x; ay += part[b].y; }
+  out[0] = (float)(ax / (double)n);
+  out[1] = (float)(ay / (double)n);
+}
+
+/* radius -> colour for the optional renderer (result of updateCol_k, :401-443; the shadow
+ * darkening halves the HSL lightness) */
+__device__ float hue_channel(float p, float q, float t) {
+  if (t < 0) t += 1;
+  if (t > 1) t -= 1;
+  if (t < 1.0 / 6.0) return p + (q - p) * 6.0 * t;
+  if (t < 1.0 / 2.0) return q;
+  if (t < 2.0 / 3.0) return p + (q - p) * (2.0 / 3.0 - t) * 6.0;
+  return p;
+}
+__global__ void __launch_bounds__(256) k_update_col(const float *__restrict__ rad, float4 *__restrict__ col,
+                                                    const float2 *__restrict__ pos, const int *__restrict__ dead, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r = rad[i];
+  float4 cc = col[i];
+  if (dead[i]) {
+    cc.x = 0.0f; cc.y = 0.0f; cc.z = 0.0f;
+  } else {
+    const float lo = c_prm.p.min_radius, hi = c_prm.p.max_radius;
+    cc.x = 30.0f / 255.0f;
+    cc.y = (20.0f + (200.0f - 20.0f) * powf(hi - r, 2.0f) / powf(hi - lo, 2.0f)) / 255.0f;
+    cc.z = (30.0f + (210.0f - 30.0f) * powf(r - lo, 0.5f) / powf(hi - lo, 0.5f)) / 255.0f;
+    if (c_prm.p.display_shadow) {
+      const float2 p = pos[i];
+      if (in_shadow(p.x, p.y)) {
+        const float mx = fmaxf(fmaxf(cc.x, cc.y), cc.z), mn = fminf(fminf(cc.x, cc.y), cc.z);
+        float h, s, l = (mx + mn) / 2;
+        if (mx == mn) {
+          h = s = 0;
+        } else {
+          const float d = mx - mn;
+          s = l > 0.5 ? d / (2.0 - mx - mn) : d / (mx + mn);
+          if (mx == cc.x) h = (cc.y - cc.z) / d + (cc.y < cc.z ? 6.0 : 0.0);
+          else if (mx == cc.y) h = (cc.z - cc.x) / d + 2.0;
+          else h = (cc.x - cc.y) / d + 4.0;
+          h /= 6.0;
+        }
+        l = l / 2.0;
+        if (s == 0) {
+          cc.x = cc.y = cc.z = l;
+        } else {
+          const float q = l < 0.5 ? l * (1.0 + s) : l + s - l * s;
+          const float pp = 2.0 * l - q;
+          cc.x = hue_channel(pp, q, h + 1.0 / 3.0);
+          cc.y = hue_channel(pp, q, h);
+          cc.z = hue_channel(pp, q, h - 1.0 / 3.0);
+        }
+      }
+    }
+  }
+  col[i] = cc;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * sort driver
+ * ------------------------------------------------------------------------------------------ */
+static void ensure_sort_workspace(uint32_t n, int npass) {
+  prs_sort::Workspace &w = g_prs.sort_ws;
+  if (w.cap_pairs < n) {
+    for (int b = 0; b < 2; b++) {
+      if (w.keys[b]) PRS_CUDA(cudaFree(w.keys[b]));
+      if (w.vals[b]) PRS_CUDA(cudaFree(w.vals[b]));
+      PRS_CUDA(cudaMalloc(&w.keys[b], (size_t)n * 4));
+      PRS_CUDA(cudaMalloc(&w.vals[b], (size_t)n * 4));
+    }
+    w.cap_pairs = n;
+  }
+  const size_t need = prs_sort::meta_words(n, npass);
+  if (w.cap_meta < need) {
+    if (w.meta) PRS_CUDA(cudaFree(w.meta));
+    PRS_CUDA(cudaMalloc(&w.meta, need * 4));
+    w.cap_meta = need;
+  }
+}
+
+/* stable sort of n pairs by the low key_bits of the key; result in out_* (may alias in_*).
+ * vals_are_iota: in_vals[i] == i is known (skips reading them in the first pass). */
+static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out_k, uint32_t *out_v, uint32_t n,
+                       int key_bits, bool vals_are_iota) {
+  using namespace prs_sort;
+  if (n == 0) return;
+  if (key_bits < 1) key_bits = 1;
+  if (key_bits > 32) key_bits = 32;
+  const int npass = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
+  ensure_sort_workspace(n, npass);
+  Workspace &w = g_prs.sort_ws;
+  const uint32_t tiles = div_up(n, TILE);
+  uint32_t *ghist = w.meta;
+  uint32_t *counters = w.meta + MAX_PASSES * RADIX;
+  uint32_t *status = counters + MAX_PASSES;
+  PRS_CUDA(cudaMemsetAsync(w.meta, 0, meta_words(n, npass) * 4, g_prs.stream));
+  const unsigned hist_blocks = min(div_up(n, THREADS * 8), 148u * 8u);
+  PRS_LAUNCH(k_histogram, hist_blocks, THREADS, 0, in_k, n, ghist, npass);
+  const uint32_t *src_k = in_k, *src_v = vals_are_iota ? nullptr : in_v;
+  for (int p = 0; p < npass; p++) {
+    /* ping-pong through the two scratch pairs so that the LAST pass lands in out_* */
+    uint32_t *dst_k, *dst_v;
+    if (p == npass - 1) { dst_k = out_k; dst_v = out_v; }
+    else { dst_k = w.keys[p & 1]; dst_v = w.vals[p & 1]; }
+    PRS_LAUNCH(k_onesweep, tiles, THREADS, 0, src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
+               status + (size_t)p * tiles * RADIX, counters + p);
+    src_k = dst_k;
+    src_v = dst_v;
+  }
+}
+
+static int key_bits_of_grid() {
+  /* cell keys are < numCells (power of two); before setParameters assume full 32-bit keys */
+  if (!g_prs.params_set || g_prs.h_prm.p.numCells == 0) return 32;
+  int b = 0;
+  while ((1ull << b) < (unsigned long long)g_prs.h_prm.p.numCells) b++;
+  return b < 1 ? 1 : b;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * C-ABI part 1: the reference's entry points
+ * ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+void cudaInit(int argc, char **argv) {
+  /* -device=N picks the device (helper_cuda.h:1246-1283); otherwise the current device stays */
+  int dev = -1;
+  for (int i = 1; i < argc; i++) {
+    const char *a = argv[i];
+    while (*a == '-') a++;
+    if (strncmp(a, "device=", 7) == 0) dev = atoi(a + 7);
+  }
+  int count = 0;
+  PRS_CUDA(cudaGetDeviceCount(&count));
+  if (count == 0) { printf("No CUDA Capable devices found, exiting...\n"); exit(EXIT_SUCCESS); }
+  if (dev >= 0) PRS_CUDA(cudaSetDevice(dev));
+}
+void cudaGLInit(int argc, char **argv) { cudaInit(argc, argv); }
+
+void allocateArray(void **devPtr, size_t size) { PRS_CUDA(cudaMalloc(devPtr, size)); }
+void freeArray(void *devPtr) { PRS_CUDA(cudaFree(devPtr)); }
+void threadSync(void) { PRS_CUDA(cudaDeviceSynchronize()); }
+
+void copyArrayToDevice(void *device, const void *host, int offset, int size) {
+  PRS_CUDA(cudaMemcpyAsync((char *)device + offset, host, (size_t)size, cudaMemcpyHostToDevice, g_prs.stream));
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+}
+static void no_gl(const char *fn) {
+  fprintf(stderr, "%s: libparticlebot_b200 is built headless (no OpenGL interop); rendering is optional\n", fn);
+  exit(EXIT_FAILURE);
+}
+void copyArrayFromDevice(void *host, const void *device, struct cudaGraphicsResource **res, int size) {
+  if (res) no_gl("copyArrayFromDevice(mapped VBO)");
+  PRS_CUDA(cudaMemcpyAsync(host, device, (size_t)size, cudaMemcpyDeviceToHost, g_prs.stream));
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+}
+void registerGLBufferObject(unsigned, struct cudaGraphicsResource **) { no_gl("registerGLBufferObject"); }
+void unregisterGLBufferObject(struct cudaGraphicsResource *) { no_gl("unregisterGLBufferObject"); }
+void *mapGLBufferObject(struct cudaGraphicsResource **) { no_gl("mapGLBufferObject"); return nullptr; }
+void unmapGLBufferObject(struct cudaGraphicsResource *) { no_gl("unmapGLBufferObject"); }
+
+void setParameters(SimParams *hp) {
+  PrsDevParams &d = g_prs.h_prm;
+  memset(&d, 0, sizeof(d));
+  d.p = *hp;
+  if (hp->nobstacles > PRS_MAX_OBSTACLES || hp->n_cir_obstacles > PRS_MAX_OBSTACLES || hp->nobstacles < 0 ||
+      hp->n_cir_obstacles < 0) {
+    /* the reference overruns its 10-entry constant arrays here; refuse instead */
+    fprintf(stderr, "setParameters: more than %d obstacles of one kind\n", PRS_MAX_OBSTACLES);
+    exit(EXIT_FAILURE);
+  }
+  for (int i = 0; i < hp->nobstacles; i++) {
+    d.x1obs[i] = hp->x1obs[i]; d.x2obs[i] = hp->x2obs[i]; d.y1obs[i] = hp->y1obs[i]; d.y2obs[i] = hp->y2obs[i];
+  }
+  for (int i = 0; i < hp->n_cir_obstacles; i++) {
+    d.x_cir[i] = hp->x_cir_obs[i]; d.y_cir[i] = hp->y_cir_obs[i]; d.r_cir[i] = hp->r_cir_obs[i];
+  }
+  d.world_half = g_prs.world_half;
+  g_prs.params_set = true;
+  PRS_CUDA(cudaMemcpyToSymbolAsync(c_prm, &d, sizeof(d), 0, cudaMemcpyHostToDevice, g_prs.stream));
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+}
+
+unsigned iDivUp(unsigned a, unsigned b) { return (a % b != 0) ? (a / b + 1) : (a / b); }
+
+void integrateSystem(float *pos, float *vel, float *rad, float deltaTime, unsigned nCells, float /*time*/) {
+  if (!nCells) return;
+  PRS_LAUNCH(k_integrate, div_up(nCells, 256), 256, 0, (float2 *)pos, (float2 *)vel, rad, deltaTime, nCells);
+}
+
+void calcHash(unsigned *hash, unsigned *index, float *pos, int nCells) {
+  if (nCells <= 0) return;
+  PRS_LAUNCH(k_calc_hash, div_up(nCells, 256), 256, 0, hash, index, (const float2 *)pos, (uint32_t)nCells);
+}
+
+void sortParticlebots(unsigned *hash, unsigned *index, unsigned nCells) {
+  sort_pairs(hash, index, hash, index, nCells, key_bits_of_grid(), false);
+}
+
+void reorderDataAndFindCellStart(unsigned *cellStart, unsigned *cellEnd, float *sortedPos, float *sortedVel,
+                                 float *sortedRad, unsigned *hash, unsigned *index, float *oldPos, float *oldVel,
+                                 float *oldRad, unsigned nCells, unsigned numCells) {
+  PRS_CUDA(cudaMemsetAsync(cellStart, 0xff, (size_t)numCells * sizeof(unsigned), g_prs.stream));
+  if (!nCells) return;
+  PRS_LAUNCH(k_reorder, div_up(nCells, 256), 256, 0, cellStart, cellEnd, (float2 *)sortedPos, (float2 *)sortedVel,
+             sortedRad, hash, index, (const float2 *)oldPos, (const float2 *)oldVel, oldRad, nCells);
+}
+
+void collide(float *newVel, float *absForce_a, float *absForce_r, float *sortedPos, float *sortedVel,
+             float *sortedRad, unsigned *index, unsigned *cellStart, unsigned *cellEnd, unsigned nCells,
+             unsigned /*numCells*/, float deltaTime) {
+  if (!nCells) return;
+  prs_launch_collide((float2 *)newVel, absForce_a, absForce_r, (const float2 *)sortedPos, (const float2 *)sortedVel,
+                     sortedRad, index, cellStart, cellEnd, nCells, deltaTime);
+}
+
+void updateRad_light_wave(float * /*pos*/, float *absForce_a, float *absForce_r, float *rad, float *phase, float time,
+                          float deltaTime, int *dead, int nCells) {
+  if (nCells <= 0) return;
+  PRS_LAUNCH(k_update_rad, div_up(nCells, 256), 256, 0, absForce_a, absForce_r, rad, phase, time, deltaTime, dead,
+             (uint32_t)nCells);
+}
+
+void updatePhase(float *pos, float *phase, float spacing, float /*max_d*/, float min_d, int nCells) {
+  if (nCells <= 0) return;
+  PRS_LAUNCH(k_update_phase, div_up(nCells, 256), 256, 0, (const float2 *)pos, phase, spacing, min_d,
+             (const float *)nullptr, (uint32_t)nCells);
+}
+
+void curand_setup(struct curandStateXORWOW *state, int N) {
+  if (N <= 0) return;
+  PRS_LAUNCH(k_curand_setup, div_up(N, 256), 256, 0, (curandState *)state, (uint32_t)N);
+}
+void add_normal_noise(struct curandStateXORWOW *state, float *val, float std, int N) {
+  if (N <= 0) return;
+  PRS_LAUNCH(k_add_normal_noise, div_up(N, 256), 256, 0, (curandState *)state, val, std, (uint32_t)N);
+}
+
+void calcCOG(float *pos, float *temppos, float *temppos1, int nCells, float time, int hist_steps, float hist_int) {
+  if (nCells <= 0) return;
+  const int ind = ((int)(time / hist_int)) % hist_steps;
+  const float mul = 1.0f / float(nCells);
+  /* levels of 64: in -> a -> b -> a ... ; the last level writes the scaled, tagged centroid */
+  const float2 *in = (const float2 *)pos;
+  float2 *bufs[2] = {(float2 *)temppos, (float2 *)temppos1};
+  int n = nCells, which = 0;
+  while (true) {
+    const int nb = (n + 63) / 64;
+    const int last = (nb == 1);
+    float2 *out = last ? (float2 *)temppos1 : bufs[which];
+    if (last && in == (const float2 *)temppos1) {
+      /* never read and write temppos1 in the same level */
+      PRS_CUDA(cudaMemcpyAsync(temppos, temppos1, (size_t)n * sizeof(float2), cudaMemcpyDeviceToDevice, g_prs.stream));
+      in = (const float2 *)temppos;
+    }
+    PRS_LAUNCH(k_cog_level, nb, 64, 0, in, out, n, last, mul);
+    if (last) break;
+    in = out;
+    which ^= 1;
+    n = nb;
+  }
+  PRS_CUDA(cudaMemcpyAsync(pos + 2 * (size_t)(ind + nCells), temppos1, 2 * sizeof(float), cudaMemcpyDeviceToDevice,
+                           g_prs.stream));
+}
+
+void updateCol(float *rad, float *col, int nCells, float *pos, float * /*phase*/, int *dead) {
+  if (nCells <= 0) return;
+  PRS_LAUNCH(k_update_col, div_up(nCells, 256), 256, 0, rad, (float4 *)col, (const float2 *)pos, dead, (uint32_t)nCells);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * C-ABI part 2: additions
+ * ------------------------------------------------------------------------------------------ */
+const char *prs_version(void) { return "particlebot-b200 0.1 (sm_100a)"; }
+void prs_set_stream(void *s) { g_prs.stream = (cudaStream_t)s; }
+void *prs_get_stream(void) { return (void *)g_prs.stream; }
+
+void prs_set_world_half_extent(float half) {
+  g_prs.world_half = half;
+  g_prs.h_prm.world_half = half;
+  PRS_CUDA(cudaMemcpyToSymbolAsync(c_prm, &half, sizeof(float), offsetof(PrsDevParams, world_half),
+                                   cudaMemcpyHostToDevice, g_prs.stream));
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+}
+float prs_get_world_half_extent(void) { return g_prs.world_half; }
+void prs_set_collide_mode(int mode) { g_prs.collide_mode = mode; }
+int prs_get_collide_mode(void) { return g_prs.collide_mode; }
+unsigned long long prs_launch_count(int reset) {
+  const unsigned long long v = g_prs.launches;
+  if (reset) g_prs.launches = 0;
+  return v;
+}
+
+void prs_min_light_distance(const float *pos, int n, float *d_min_d) {
+  PRS_CUDA(cudaMemsetAsync(d_min_d, 0x7f, sizeof(float), g_prs.stream));
+  if (n <= 0) return;
+  const unsigned blocks = min(div_up((unsigned)n, 256 * 4), 148u * 8u);
+  PRS_LAUNCH(k_min_light_distance, blocks, 256, 0, (const float2 *)pos, (uint32_t)n, (uint32_t *)d_min_d);
+}
+void prs_update_phase_dev(const float *pos, float *phase, float spacing, const float *d_min_d, int n) {
+  if (n <= 0) return;
+  PRS_LAUNCH(k_update_phase, div_up(n, 256), 256, 0, (const float2 *)pos, phase, spacing, 0.0f, d_min_d, (uint32_t)n);
+}
+void prs_centroid(const float *pos, int n, float *d_scratch, float *d_out) {
+  if (n <= 0) return;
+  const int nb = (int)min(div_up((unsigned)n, 256 * 8), 256u);
+  PRS_LAUNCH(k_centroid_partial, nb, 256, 0, (const float2 *)pos, (uint32_t)n, (double2 *)d_scratch);
+  PRS_LAUNCH(k_centroid_final, 1, 1, 0, (const double2 *)d_scratch, nb, (uint32_t)n, d_out);
+}
+
+void prs_sort_pairs(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys, unsigned *out_vals,
+                    unsigned n, int key_bits) {
+  sort_pairs(in_keys, in_vals, out_keys, out_vals, n, key_bits, false);
+}
+
+void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort) {
+  const uint32_t n = b->nCells;
+  if (!n) return;
+  const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
+  if (do_sort) {
+    PRS_LAUNCH(k_control_integrate_hash<true>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
+               b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
+    sort_pairs(b->hash, b->index, b->hash, b->index, n, key_bits_of_grid(), true);
+  } else {
+    PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
+               b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
+  }
+  reorderDataAndFindCellStart(b->cellStart, b->cellEnd, b->sortedPos, b->sortedVel, b->sortedRad, b->hash, b->index,
+                              b->pos, b->vel, b->rad, n, b->numCells);
+  collide(b->vel, b->absForce_a, b->absForce_r, b->sortedPos, b->sortedVel, b->sortedRad, b->index, b->cellStart,
+          b->cellEnd, n, b->numCells, dt);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+/*
+ * prs_main.cpp — headless runner `ParticleBot <cfg> [--steps N] [--backend fused|percall|ext:<lib>]
+ * [--no-csv] [--quiet]`: the reference's main() (main.cpp:823-967) without GLUT/GL/OpenCV.  The
+ * GLUT display callback that drives the reference (dumpParticlebot, then update, main.cpp:360-361)
+ * becomes a plain loop; rendering and video are optional components that are not built here
+ * (north_star (5)).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+
+#include "prs_particlebot.hpp"
+
+int main(int argc, char **argv) {
+  SimParams params;
+  prs_run_options opt;
+  prs_params_defaults(&params, &opt);
+  const char *cfg = "example.cfg";
+  long max_steps = -1;
+  int backend = PRS_BACKEND_FUSED;
+  const char *ext = 0;
+  bool csv = true, quiet = false;
+  int positional = 0;
+  for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "--steps") && i + 1 < argc) max_steps = atol(argv[++i]);
+    else if (!strcmp(argv[i], "--backend") && i + 1 < argc) {
+      const char *b = argv[++i];
+      if (!strcmp(b, "fused")) backend = PRS_BACKEND_FUSED;
+      else if (!strcmp(b, "percall")) backend = PRS_BACKEND_PERCALL;
+      else if (!strncmp(b, "ext:", 4)) { backend = PRS_BACKEND_EXTERNAL; ext = b + 4; }
+      else { fprintf(stderr, "unknown backend %s\n", b); return 2; }
+    } else if (!strcmp(argv[i], "--no-csv")) csv = false;
+    else if (!strcmp(argv[i], "--quiet")) quiet = true;
+    else if (!strcmp(argv[i], "--headless")) { /* default */ }
+    else if (argv[i][0] != '-' && positional++ == 0) cfg = argv[i];
+  }
+  if (prs_params_load_cfg(cfg, &params, &opt) != 0)
+    fprintf(stderr, "warning: cannot open %s, running with defaults (as the reference does)\n", cfg);
+
+  cudaInit(argc, argv);
+  FILE *fp = csv ? fopen(opt.csv_filename, "w+") : fopen("/dev/null", "w");
+  if (!fp) { perror(opt.csv_filename); return 1; }
+  if (quiet) { if (!freopen("/dev/null", "w", stdout)) return 1; }
+
+  Particlebot bot(params, 64.0f, backend, ext);
+  bot.srand(params.seed); /* main.cpp:929 */
+  bot.reset();
+
+  const auto t0 = std::chrono::steady_clock::now();
+  long steps = 0;
+  while (max_steps < 0 || steps < max_steps) {
+    bot.dumpParticlebot(0, params.nCells, fp, opt.dump_interval, params.testing, params.light_x, params.light_y);
+    if (bot.update(opt.timestep, opt.sort_interval)) break; /* time > max_time: the reference exit(0)s */
+    steps++;
+  }
+  bot.sync();
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  fclose(fp);
+  fprintf(stderr, "ParticleBot: %ld steps, %u robots, %.3f s, %.1f steps/s, %.3e particle-steps/s\n", steps,
+          params.nCells, sec, steps / sec, (double)steps * params.nCells / sec);
+  return 0;
+}

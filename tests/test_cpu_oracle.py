@@ -1,0 +1,207 @@
+"""CPU-side tests (run with -m "not gpu"): the oracle against independent numpy restatements and
+against the golden vectors produced by the reference's own kernels; host logic; C-ABI exports."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import particlerobotsimulations_b200 as prs
+from oracle import binding as ob
+from tests import util
+
+
+def test_glibc_rand_restatement_matches_libc():
+    libc = C.CDLL("libc.so.6")
+    L = ob.lib()
+    for seed in (1, 5555, 6666, 7777, 8888, 9999, 0, 2**31 + 5):
+        libc.srand(C.c_uint(seed))
+        want = [libc.rand() for _ in range(2000)]
+        g = ob.GlibcRand()
+        L.prso_srand(C.byref(g), seed)
+        got = [L.prso_rand(C.byref(g)) for _ in range(2000)]
+        assert got == want
+
+
+def test_gate_cadence_matches_fp32_drift():
+    """with time accumulated in fp32 by 0.01f the gates fire at these steps."""
+    L = ob.lib()
+    t = np.float32(0.0)
+    dt = np.float32(0.01)
+    fired = {180.0: [], 12.0: [], 10.0: []}
+    for step in range(20000):
+        for T in fired:
+            if L.prso_gate(float(t), T, float(dt)):
+                fired[T].append(step)
+        t = np.float32(t + dt)
+    assert fired[180.0] == [0, 18002]
+    assert fired[12.0][:9] == [0, 1200, 2400, 3601, 4801, 6001, 7201, 8401, 9600]
+    assert fired[10.0][:5] == [0, 1000, 2000, 3000, 4001]
+
+
+def test_cfg_defaults_and_examples():
+    p, o = prs.default_params()
+    assert p.nCells == 501 and p.nDead == -1 and p.Nx == 5
+    assert np.float32(p.attraction) == np.float32(3.0) * np.float32(0.000015884)
+    assert np.float32(p.gravity) == np.float32(9.81 * float(np.float32(0.566)))
+    assert abs(p.phase_std - 0.6) < 1e-6 and o.sort_interval == 180.0 and abs(o.timestep - 0.01) < 1e-9
+    assert p.gridSize.x == 512 and p.numCells == 262144 and p.worldOrigin.x == -64.0
+    assert np.float32(p.cellSize.x) == np.float32(p.max_radius) * np.float32(2)
+    p, o = util.cfg("example")
+    assert (p.nCells, p.nDead, p.light_x, p.light_y, p.seed, p.max_time) == (300, 0, -2.0, 4.0, 5555, 7200.0)
+    assert o.csv_filename == b"example_data.csv"
+    p, o = util.cfg("example_gap")
+    assert p.nobstacles == 2 and [p.x1obs[i] for i in range(2)] == [np.float32(-1.2)] * 2
+    assert [p.y1obs[i] for i in range(2)] == [-8.0, 1.0] and [p.y2obs[i] for i in range(2)] == [-1.0, 8.0]
+    p, o = util.cfg("example_obstacle")
+    assert p.n_cir_obstacles == 3 and [p.r_cir_obs[i] for i in range(3)] == [np.float32(v) for v in (0.5, 0.3, 0.45)]
+    p, o = util.cfg("example_object_transport")
+    assert p.nCells == 201 and p.nDead == -1 and p.attractionFactor == 0.0
+
+
+def test_cfg_parser_quirks(tmp_path):
+    f = tmp_path / "q.cfg"
+    f.write_text("# comment\nNx\n9\nconstraint_contraction\n7.5\nconstrained_contraction\n1\ncentroid_int\n3.9\n"
+                 "phase_update_interval\n7.7\nconfig\nCONFIG_HEX\nunknown_key\n42\nnCells\n64\ntime_to_dead\n5\n"
+                 "time_to_dead_x\n9\n")
+    p, o = prs.load_cfg(str(f))
+    assert p.Nx == 5                       # 2-character names never reach the parser (main.cpp:924)
+    assert p.constraint == 7.5             # "constraint" prefix swallows constraint_contraction (:725)
+    assert p.constraint_contraction == 10.0
+    assert p.constrained_contraction == 1
+    assert p.centroid_int == 3.0 and p.phase_update_interval == 7.0   # strtol into floats (:684, :789)
+    assert p.config == 0                   # `config` is a no-op (:794-809)
+    assert p.nCells == 64                  # unknown_key consumed its value line and parsing went on
+    assert p.time_to_dead == 5.0           # exact-match key (:749); time_to_dead_x is not it
+
+
+def _np_hash(p, pos):
+    ox, oy = np.float32(p.worldOrigin.x), np.float32(p.worldOrigin.y)
+    cx, cy = np.float32(p.cellSize.x), np.float32(p.cellSize.y)
+    gx = np.floor((pos[:, 0] - ox) / cx).astype(np.int64) & (p.gridSize.x - 1)
+    gy = np.floor((pos[:, 1] - oy) / cy).astype(np.int64) & (p.gridSize.y - 1)
+    return (gy * p.gridSize.x + gx).astype(np.uint32)
+
+
+def test_oracle_hash_sort_celltable_against_numpy():
+    p, o = util.cfg("example")
+    rng = np.random.default_rng(1)
+    n = 5000
+    pos = (rng.random((n, 2), dtype=np.float32) * 140 - 70).astype(np.float32)  # includes wrap-around cells
+    L = ob.lib()
+    h = np.empty(n, np.uint32)
+    idx = np.empty(n, np.uint32)
+    L.prso_calc_hash(C.byref(p), pos.ctypes.data, h.ctypes.data, idx.ctypes.data, n)
+    assert np.array_equal(h, _np_hash(p, pos)) and np.array_equal(idx, np.arange(n, dtype=np.uint32))
+    order = np.argsort(h, kind="stable")
+    hs, is_ = h.copy(), idx.copy()
+    L.prso_sort_pairs(hs.ctypes.data, is_.ctypes.data, n)
+    assert np.array_equal(hs, h[order]) and np.array_equal(is_, order.astype(np.uint32))
+    vel = rng.random((n, 2), dtype=np.float32)
+    rad = rng.random(n, dtype=np.float32)
+    cs = np.zeros(p.numCells, np.uint32)
+    ce = np.full(p.numCells, 12345, np.uint32)
+    sp, sv, sr = np.empty((n, 2), np.float32), np.empty((n, 2), np.float32), np.empty(n, np.float32)
+    L.prso_reorder_find_cell_start(C.byref(p), cs.ctypes.data, ce.ctypes.data, sp.ctypes.data, sv.ctypes.data,
+                                   sr.ctypes.data, hs.ctypes.data, is_.ctypes.data, pos.ctypes.data, vel.ctypes.data,
+                                   rad.ctypes.data, n, p.numCells)
+    assert np.array_equal(sp, pos[order]) and np.array_equal(sv, vel[order]) and np.array_equal(sr, rad[order])
+    occupied = np.unique(hs)
+    assert np.all(cs[np.setdiff1d(np.arange(p.numCells), occupied)] == 0xFFFFFFFF)
+    assert np.all(ce[np.setdiff1d(np.arange(p.numCells), occupied)] == 12345)   # cellEnd is never cleared
+    first = np.searchsorted(hs, occupied, "left")
+    last = np.searchsorted(hs, occupied, "right")
+    assert np.array_equal(cs[occupied], first.astype(np.uint32)) and np.array_equal(ce[occupied], last.astype(np.uint32))
+
+
+@pytest.mark.parametrize("name", util.CFGS)
+def test_oracle_placement_properties(name):
+    p, o = util.cfg(name)
+    s = ob.OracleSim(p)
+    s.srand(p.seed)
+    s.reset()
+    pos, rad, dead = s.get("pos"), s.get("rad"), s.get("dead")
+    assert pos[0, 0] == 5.0 and pos[0, 1] == 0.0
+    assert np.all(np.isfinite(pos))
+    n = p.nCells
+    if p.nDead == -1:
+        assert dead[n - 1] == 1 and rad[n - 1] == np.float32(p.min_radius) * np.float32(p.radFactor)
+        assert pos[n - 1, 1] == 0.0 and pos[n - 1, 0] < pos[: n - 1, 0].min()
+    # aggregation: every disc from the 4th on touches (2*min_radius, within rounding) or clears its neighbours
+    d = np.linalg.norm(pos[None, 3:n - 1] - pos[3:n - 1, None], axis=-1) + np.eye(n - 4) * 10
+    assert d.min() > 2 * p.min_radius * (1 - 1e-5)
+
+
+def test_oracle_dead_draw_and_controller_skip():
+    p, o = util.cfg("example_dead_cells")
+    s = util.oracle_state_after(p, o, 50)
+    dead = s.get("dead")
+    assert dead.sum() == 20
+    assert np.all(s.get("rad")[dead == 1] == np.float32(p.min_radius))   # dead robots never oscillate
+    assert np.any(s.get("rad")[dead == 0] > np.float32(p.min_radius))
+
+
+def test_oracle_xorwow_matches_published_first_outputs():
+    """XORWOW with seed 0, subsequence 0 is Marsaglia's original generator: the first output of
+    the classic xorwow state (123456789, 362436069, 521288629, 88675123, 5783321, d=6615241) is
+    246875399 + 6615241 + 362437 = 3495... computed below independently in Python."""
+    L = ob.lib()
+    st = (ob.RngState * 4)()
+    L.prso_curand_setup(st, 0, 4)
+    # curand salts the seed: s0 = 0 ^ 0xaad26b49 etc. (curand_kernel.h:_curand_init_inplace)
+    M = 0xFFFFFFFF
+    s0, s1 = 0xaad26b49, 0xf7dcefdd
+    t0, t1 = (1099087573 * s0) & M, (2591861531 * s1) & M
+    v = [(123456789 + t0) & M, 362436069 ^ t0, (521288629 + t1) & M, 88675123 ^ t1, (5783321 + t0) & M]
+    d = (6615241 + t1 + t0) & M
+    assert list(st[0].v) == v and st[0].d == d
+    # subsequences 1..3 differ from 0 and from each other (skip-ahead by 2^67 each)
+    states = {tuple(st[i].v) for i in range(4)}
+    assert len(states) == 4
+
+
+def test_oracle_noise_alternates_fresh_and_cached():
+    L = ob.lib()
+    n = 64
+    st = (ob.RngState * n)()
+    L.prso_curand_setup(st, 5555, n)
+    a = np.zeros(n, np.float32)
+    L.prso_add_normal_noise(st, a.ctypes.data, 1.0, n)
+    assert all(st[i].boxmuller_flag == 1 for i in range(n))          # second Box-Muller value cached (Q11)
+    b = np.zeros(n, np.float32)
+    L.prso_add_normal_noise(st, b.ctypes.data, 1.0, n)
+    assert all(st[i].boxmuller_flag == 0 for i in range(n))
+    z = np.concatenate([a, b])
+    assert abs(z.mean()) < 0.3 and 0.7 < z.std() < 1.3
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The library loads without a GPU and exports every function include/prs_cabi.h declares."""
+    L = prs.lib()
+    hdr = open(os.path.join(util.ROOT, "include", "prs_cabi.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", hdr))
+    names -= {"defined"}
+    assert {"collide", "calcHash", "sortParticlebots", "reorderDataAndFindCellStart", "integrateSystem",
+            "prs_fused_step", "prs_sim_update"} <= names
+    out = subprocess.check_output(["nm", "-D", "--defined-only", prs.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = sorted(names - exported)
+    assert not missing, missing
+    for n in names:
+        assert hasattr(L, n)
+    assert set(prs.SIGNATURES) <= names | {"cudaGLInit"}
+
+
+def test_product_never_links_the_oracle():
+    """No file of the product library refers to oracle/ (the oracle is a checker, not a code path)."""
+    for d in ("particlerobotsimulations_b200", "include"):
+        for root, _, files in os.walk(os.path.join(util.ROOT, d)):
+            for f in files:
+                if f.endswith((".cu", ".cuh", ".cpp", ".h", ".hpp", ".py")):
+                    txt = open(os.path.join(root, f)).read()
+                    assert "prs_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+    out = subprocess.check_output(["ldd", prs.LIB_PATH], text=True)
+    assert "oracle" not in out

@@ -1,0 +1,400 @@
+"""GPU parity tests (-m gpu): the hand-written CUDA path, called through the C-ABI, against
+(1) the CPU oracle and (2) the reference's own kernels compiled verbatim (oracle/_ref), on the
+same inputs.
+
+Bars (BASELINE.json north_star): cell hashes, sort order and cellStart/cellEnd bit-exact;
+fp32 positions/velocities within 1e-5 relative over a 100-step horizon.  "Relative" is
+elementwise |a-b| / max(|b|, floor) with floor = 1 world unit for positions (the swarm sits
+~5 units from the origin) and the largest |velocity| of the step for velocities.
+Against the CPU oracle the bar is looser (5e-4) because the device code contracts FMAs and uses
+the approximate __powf which IEEE host arithmetic cannot reproduce; the tight bar
+is applied against the reference kernels themselves.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import particlerobotsimulations_b200 as prs
+from oracle import binding as ob
+from tests import util
+from tests.util import Dev
+
+pytestmark = pytest.mark.gpu
+
+TOL_REF = 1e-5      # vs the reference's kernels (north_star)
+TOL_ORACLE = 5e-4   # vs the IEEE CPU restatement
+
+
+def _backends():
+    b = [("percall", prs.BACKEND_PERCALL, None), ("fused", prs.BACKEND_FUSED, None)]
+    return b
+
+
+def _random_swarm(p, n, rng, spread=20.0):
+    pos = ((rng.random((n, 2), dtype=np.float32) - 0.5) * spread).astype(np.float32)
+    vel = ((rng.random((n, 2), dtype=np.float32) - 0.5) * 0.2).astype(np.float32)
+    rad = (p.min_radius + rng.random(n, dtype=np.float32) * (p.max_radius - p.min_radius)).astype(np.float32)
+    return pos, vel, rad
+
+
+# --------------------------------------------------------------------------------------------
+# per-kernel parity
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 255, 300, 4097, 200_000])
+def test_calc_hash_bit_exact(n):
+    p, o = util.cfg("example")
+    L = prs.lib()
+    L.setParameters(C.byref(p))
+    rng = np.random.default_rng(n)
+    pos = ((rng.random((n, 2), dtype=np.float32) - 0.5) * 150).astype(np.float32)   # beyond the 120-unit grid: wraps
+    pos[0] = (-64.0, -64.0)
+    d_pos, d_h, d_i = Dev(pos), Dev(4 * n, np.uint32), Dev(4 * n, np.uint32)
+    L.calcHash(d_h.ptr, d_i.ptr, d_pos.ptr, n)
+    h, i = d_h.get(), d_i.get()
+    ho, io = np.empty(n, np.uint32), np.empty(n, np.uint32)
+    ob.lib().prso_calc_hash(C.byref(p), pos.ctypes.data, ho.ctypes.data, io.ctypes.data, n)
+    assert np.array_equal(h, ho) and np.array_equal(i, io)
+    if util.refcuda_available():
+        R = util.refcuda()
+        R.setParameters(C.byref(p))
+        r_h, r_i = Dev(4 * n, np.uint32), Dev(4 * n, np.uint32)
+        R.calcHash(r_h.ptr, r_i.ptr, d_pos.ptr, n)
+        assert np.array_equal(h, r_h.get()) and np.array_equal(i, r_i.get())
+
+
+@pytest.mark.parametrize("n,bits", [(1, 18), (31, 18), (4096, 18), (4097, 18), (300, 18), (100_003, 22), (1 << 20, 22),
+                                    (50_000, 32), (70_000, 7)])
+def test_sort_bit_exact_and_stable(n, bits):
+    L = prs.lib()
+    rng = np.random.default_rng(n + bits)
+    keys = (rng.integers(0, 2 ** bits, n, dtype=np.uint64)).astype(np.uint32)
+    if n > 1000:
+        keys[: n // 2] = keys[0]     # long runs of equal keys: stability matters
+    vals = rng.permutation(n).astype(np.uint32)
+    order = np.argsort(keys, kind="stable")
+    d_k, d_v = Dev(keys), Dev(vals)
+    o_k, o_v = Dev(4 * n, np.uint32), Dev(4 * n, np.uint32)
+    L.prs_sort_pairs(d_k.ptr, d_v.ptr, o_k.ptr, o_v.ptr, n, bits)
+    assert np.array_equal(o_k.get(), keys[order]) and np.array_equal(o_v.get(), vals[order])
+    assert np.array_equal(d_k.get(), keys)     # out-of-place call leaves the input alone
+    # in place through the reference's entry point (key width from setParameters: numCells = 2^18)
+    if bits <= 18:
+        p, _ = util.cfg("example")
+        L.setParameters(C.byref(p))
+        L.sortParticlebots(d_k.ptr, d_v.ptr, n)
+        assert np.array_equal(d_k.get(), keys[order]) and np.array_equal(d_v.get(), vals[order])
+        if util.refcuda_available():
+            R = util.refcuda()
+            r_k, r_v = Dev(keys), Dev(vals)
+            R.sortParticlebots(r_k.ptr, r_v.ptr, n)
+            R.threadSync()
+            assert np.array_equal(d_k.get(), r_k.get()) and np.array_equal(d_v.get(), r_v.get())
+
+
+def _grid_pipeline(L, p, pos, vel, rad):
+    n = len(rad)
+    d = dict(pos=Dev(pos), vel=Dev(vel), rad=Dev(rad), hash=Dev(4 * n, np.uint32), index=Dev(4 * n, np.uint32),
+             cs=Dev(np.zeros(p.numCells, np.uint32)), ce=Dev(np.full(p.numCells, 777, np.uint32)),
+             spos=Dev(8 * n, np.float32), svel=Dev(8 * n, np.float32), srad=Dev(4 * n, np.float32))
+    L.setParameters(C.byref(p))
+    L.calcHash(d["hash"].ptr, d["index"].ptr, d["pos"].ptr, n)
+    L.sortParticlebots(d["hash"].ptr, d["index"].ptr, n)
+    L.reorderDataAndFindCellStart(d["cs"].ptr, d["ce"].ptr, d["spos"].ptr, d["svel"].ptr, d["srad"].ptr,
+                                  d["hash"].ptr, d["index"].ptr, d["pos"].ptr, d["vel"].ptr, d["rad"].ptr, n, p.numCells)
+    return d
+
+
+@pytest.mark.parametrize("n", [1, 2, 300, 5000, 150_000])
+def test_reorder_and_cell_tables_bit_exact(n):
+    p, o = util.cfg("example")
+    rng = np.random.default_rng(n)
+    pos, vel, rad = _random_swarm(p, n, rng, spread=130.0 if n > 1000 else 8.0)
+    d = _grid_pipeline(prs.lib(), p, pos, vel, rad)
+    O = ob.lib()
+    h, i = np.empty(n, np.uint32), np.empty(n, np.uint32)
+    O.prso_calc_hash(C.byref(p), pos.ctypes.data, h.ctypes.data, i.ctypes.data, n)
+    O.prso_sort_pairs(h.ctypes.data, i.ctypes.data, n)
+    cs, ce = np.zeros(p.numCells, np.uint32), np.full(p.numCells, 777, np.uint32)
+    sp, sv, sr = np.empty((n, 2), np.float32), np.empty((n, 2), np.float32), np.empty(n, np.float32)
+    O.prso_reorder_find_cell_start(C.byref(p), cs.ctypes.data, ce.ctypes.data, sp.ctypes.data, sv.ctypes.data,
+                                   sr.ctypes.data, h.ctypes.data, i.ctypes.data, pos.ctypes.data, vel.ctypes.data,
+                                   rad.ctypes.data, n, p.numCells)
+    assert np.array_equal(d["hash"].get(), h) and np.array_equal(d["index"].get(), i)
+    assert np.array_equal(d["cs"].get(), cs) and np.array_equal(d["ce"].get(), ce)
+    assert np.array_equal(d["spos"].get(np.float32, (n, 2)), sp)
+    assert np.array_equal(d["svel"].get(np.float32, (n, 2)), sv) and np.array_equal(d["srad"].get(), sr)
+    if util.refcuda_available():
+        r = _grid_pipeline(util.refcuda(), p, pos, vel, rad)
+        for k in ("hash", "index", "cs", "ce", "spos", "svel", "srad"):
+            assert np.array_equal(d[k].get(), r[k].get()), k
+
+
+def _collide_inputs(name, steps):
+    """A physically meaningful state: the oracle's swarm after `steps` steps, radii mid-oscillation."""
+    p, o = util.cfg(name)
+    s = util.oracle_state_after(p, o, steps)
+    return p, o, s
+
+
+@pytest.mark.parametrize("name,steps", [("example", 0), ("example", 150), ("example_dead_cells", 120),
+                                        ("example_obstacle", 130), ("example_gap", 110),
+                                        ("example_object_transport", 140)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_collide_single_call(name, steps, mode):
+    p, o, s = _collide_inputs(name, steps)
+    n = p.nCells
+    dt = o.timestep
+    spos, svel, srad = s.get("sortedPos"), s.get("sortedVel"), s.get("sortedRad")
+    idx, cs, ce = s.get("index"), s.get("cellStart"), s.get("cellEnd")
+    if steps == 0:   # nothing sorted yet: build the tables from the initial placement
+        pos, vel, rad = s.get("pos"), s.get("vel"), s.get("rad")
+        O = ob.lib()
+        h = np.empty(n, np.uint32)
+        O.prso_calc_hash(C.byref(p), pos.ctypes.data, h.ctypes.data, idx.ctypes.data, n)
+        O.prso_sort_pairs(h.ctypes.data, idx.ctypes.data, n)
+        O.prso_reorder_find_cell_start(C.byref(p), cs.ctypes.data, ce.ctypes.data, spos.ctypes.data, svel.ctypes.data,
+                                       srad.ctypes.data, h.ctypes.data, idx.ctypes.data, pos.ctypes.data,
+                                       vel.ctypes.data, rad.ctypes.data, n, p.numCells)
+    fr0 = s.get("absForce_r")
+    # oracle
+    v_o, fa_o, fr_o = np.zeros((n, 2), np.float32), np.zeros(n, np.float32), fr0.copy()
+    ob.lib().prso_collide(C.byref(p), v_o.ctypes.data, fa_o.ctypes.data, fr_o.ctypes.data, spos.ctypes.data,
+                          svel.ctypes.data, srad.ctypes.data, idx.ctypes.data, cs.ctypes.data, ce.ctypes.data, n, dt)
+
+    def run(L):
+        L.setParameters(C.byref(p))
+        d = [Dev(np.zeros((n, 2), np.float32)), Dev(np.zeros(n, np.float32)), Dev(fr0), Dev(spos), Dev(svel), Dev(srad),
+             Dev(idx), Dev(cs), Dev(ce)]
+        L.collide(*[x.ptr for x in d], n, p.numCells, dt)
+        return d[0].get(), d[1].get(), d[2].get()
+
+    L = prs.lib()
+    L.prs_set_collide_mode(mode)
+    try:
+        v, fa, fr = run(L)
+    finally:
+        L.prs_set_collide_mode(0)
+    vs = max(float(np.abs(v_o).max()), 1e-3)
+    assert util.rel_err(v, v_o, vs) < TOL_ORACLE
+    assert util.rel_err(fr, fr_o, max(float(fr_o.max()), 1.0)) < TOL_ORACLE
+    assert util.rel_err(fa, fa_o, max(float(fa_o.max()), 1.0)) < TOL_ORACLE
+    if util.refcuda_available():
+        v_r, fa_r, fr_r = run(util.refcuda())
+        assert util.rel_err(v, v_r, vs) < TOL_REF
+        assert util.rel_err(fr, fr_r, max(float(fr_r.max()), 1.0)) < TOL_REF
+        assert util.rel_err(fa, fa_r, max(float(fa_r.max()), 1.0)) < TOL_REF
+        if mode == 0:   # the exact variant follows the reference's operation order: expect (near) bit equality
+            assert np.mean(v.view(np.uint32) == v_r.view(np.uint32)) > 0.99
+
+
+def test_collide_wraparound_stencil_uses_cell_path():
+    """Robots whose 5x5 stencil wraps around the grid edge take the per-cell path (Q9)."""
+    p, o = util.cfg("example")
+    n = 400
+    rng = np.random.default_rng(3)
+    pos = np.stack([-64.0 + rng.random(n, dtype=np.float32) * 0.6, -64.0 + rng.random(n, dtype=np.float32) * 0.6], 1)
+    pos = pos.astype(np.float32)
+    pos[n // 2:, 0] += np.float32(512 * 0.235 - 0.5)      # aliases onto the low side through the wrap
+    vel = np.zeros((n, 2), np.float32)
+    rad = np.full(n, p.min_radius, np.float32)
+    L, O = prs.lib(), ob.lib()
+    d = _grid_pipeline(L, p, pos, vel, rad)
+    out = [Dev(np.zeros((n, 2), np.float32)), Dev(np.zeros(n, np.float32)), Dev(np.zeros(n, np.float32))]
+    L.collide(out[0].ptr, out[1].ptr, out[2].ptr, d["spos"].ptr, d["svel"].ptr, d["srad"].ptr, d["index"].ptr,
+              d["cs"].ptr, d["ce"].ptr, n, p.numCells, o.timestep)
+    v_o, fa_o, fr_o = np.zeros((n, 2), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    spos, svel, srad = d["spos"].get(np.float32, (n, 2)), d["svel"].get(np.float32, (n, 2)), d["srad"].get()
+    idx, cs, ce = d["index"].get(), d["cs"].get(), d["ce"].get()
+    O.prso_collide(C.byref(p), v_o.ctypes.data, fa_o.ctypes.data, fr_o.ctypes.data, spos.ctypes.data, svel.ctypes.data,
+                   srad.ctypes.data, idx.ctypes.data, cs.ctypes.data, ce.ctypes.data, n, o.timestep)
+    assert np.all(np.isfinite(v_o))
+    assert util.rel_err(out[0].get(), v_o, max(float(np.abs(v_o).max()), 1e-3)) < TOL_ORACLE
+
+
+@pytest.mark.parametrize("name", ["example", "example_object_transport"])
+def test_integrate_controller_phase_noise(name):
+    p, o = util.cfg(name)
+    s = util.oracle_state_after(p, o, 37)
+    n = p.nCells
+    L, O = prs.lib(), ob.lib()
+    L.setParameters(C.byref(p))
+    L.prs_set_world_half_extent(64.0)
+    pos, vel, rad, phase = s.get("pos"), s.get("vel"), s.get("rad"), s.get("phase")
+    fa, fr, dead = s.get("absForce_a"), s.get("absForce_r"), s.get("dead")
+    pos[:4] = [[63.95, 0], [-63.95, 1], [2, 63.99], [3, -63.99]]     # wall bounces
+    vel[:4] = [[5, 0], [-5, 0], [0, 5], [0, -5]]
+    # integrate
+    d_pos, d_vel, d_rad = Dev(pos), Dev(vel), Dev(rad)
+    L.integrateSystem(d_pos.ptr, d_vel.ptr, d_rad.ptr, o.timestep, n, 0.0)
+    po, vo = pos.copy(), vel.copy()
+    O.prso_integrate(C.byref(p), po.ctypes.data, vo.ctypes.data, rad.ctypes.data, o.timestep, n, 64.0)
+    assert util.rel_err(d_pos.get(), po, 1.0) < 1e-6 and util.rel_err(d_vel.get(), vo, 1.0) < 1e-6
+    # controller at several times of the oscillation
+    for t in (0.0, 0.37, 1.5, 2.2, 3.9, 11.99, 100.25):
+        d_r = Dev(rad)
+        L.updateRad_light_wave(d_pos.ptr, Dev(fa).ptr, Dev(fr).ptr, d_r.ptr, Dev(phase).ptr, t, o.timestep, Dev(dead).ptr, n)
+        ro = rad.copy()
+        O.prso_update_rad(C.byref(p), fa.ctypes.data, fr.ctypes.data, ro.ctypes.data, phase.ctypes.data, t, o.timestep,
+                          dead.ctypes.data, n)
+        assert util.rel_err(d_r.get(), ro, 1e-3) < 2e-6, t
+    # phase offsets with the device-side light-distance reduction
+    d_min = Dev(np.zeros(16, np.float32))
+    L.prs_min_light_distance(d_pos.ptr, n, d_min.ptr)
+    pnow = d_pos.get()
+    min_o = O.prso_min_light_distance(C.byref(p), pnow.ctypes.data, n)
+    assert d_min.get()[0] == np.float32(min_o)
+    d_ph = Dev(np.zeros(n, np.float32))
+    L.prs_update_phase_dev(d_pos.ptr, d_ph.ptr, 2 * p.min_radius, d_min.ptr, n)
+    pho = np.zeros(n, np.float32)
+    O.prso_update_phase(C.byref(p), pnow.ctypes.data, pho.ctypes.data, 2 * p.min_radius, min_o, n)
+    assert util.rel_err(d_ph.get(), pho, 1.0) < 2e-6
+    # XORWOW: integer state bit-exact against the CPU restatement, normals to ~1e-6
+    st = Dev(48 * n, np.uint32)
+    L.curand_setup(st.ptr, n)
+    so = (ob.RngState * n)()
+    O.prso_curand_setup(so, p.seed, n)
+    words = st.get(np.uint32).reshape(n, 12)
+    want = np.frombuffer(bytes(so), np.uint32).reshape(n, 12)
+    assert np.array_equal(words[:, :6], want[:, :6])
+    for _ in range(3):
+        L.add_normal_noise(st.ptr, d_ph.ptr, p.phase_std, n)
+        O.prso_add_normal_noise(so, pho.ctypes.data, p.phase_std, n)
+        assert util.rel_err(d_ph.get(), pho, 1.0) < 5e-6
+    words = st.get(np.uint32).reshape(n, 12)
+    want = np.frombuffer(bytes(so), np.uint32).reshape(n, 12)
+    assert np.array_equal(words[:, :7], want[:, :7])
+
+
+def test_shadow_phase_modes():
+    for name, mode in (("example_obstacle", 1), ("example_obstacle", 2), ("example_gap", 1)):
+        p, o = util.cfg(name)
+        p.light_shadow = mode
+        s = util.oracle_state_after(p, o, 0)
+        n = p.nCells
+        pos = s.get("pos")
+        L, O = prs.lib(), ob.lib()
+        L.setParameters(C.byref(p))
+        min_o = O.prso_min_light_distance(C.byref(p), pos.ctypes.data, n)
+        d_ph = Dev(np.zeros(n, np.float32))
+        L.updatePhase(Dev(pos).ptr, d_ph.ptr, 2 * p.min_radius, 0.0, min_o, n)
+        pho = np.zeros(n, np.float32)
+        O.prso_update_phase(C.byref(p), pos.ctypes.data, pho.ctypes.data, 2 * p.min_radius, min_o, n)
+        got = d_ph.get()
+        shadow_val = -(p.Nx - 1) * p.rise_period if mode == 1 else np.float32(9999999999.0)
+        assert np.array_equal(got == shadow_val, pho == shadow_val)
+        assert (pho == shadow_val).sum() > 0
+        assert util.rel_err(got, pho, 1.0) < 2e-6
+
+
+# --------------------------------------------------------------------------------------------
+# trajectories
+# --------------------------------------------------------------------------------------------
+def _run(params, opt, backend, steps, ext=None, sort_interval=None, collide_mode=0, record_every=10):
+    L = prs.lib()
+    L.prs_set_collide_mode(collide_mode)
+    sim = prs.Simulation(params, 64.0, backend, ext)
+    sim.srand(params.seed)
+    sim.reset()
+    si = opt.sort_interval if sort_interval is None else sort_interval
+    snaps = []
+    for k in range(steps):
+        sim.update(opt.timestep, si)
+        if (k + 1) % record_every == 0 or k == 0:
+            snaps.append(dict(step=k + 1, pos=sim.get(prs.POSITION), vel=sim.get(prs.VELOCITY), rad=sim.get(prs.RADII),
+                              hash=sim.get(prs.HASH), index=sim.get(prs.INDEX), cs=sim.get(prs.CELLSTART),
+                              ce=sim.get(prs.CELLEND), dead=sim.get(prs.DEAD), phase=sim.get(prs.PHASE)))
+    sim.close()
+    L.prs_set_collide_mode(0)
+    return snaps
+
+
+def _compare(snaps, ref, tol, ints=True):
+    for a, b in zip(snaps, ref):
+        assert a["step"] == b["step"]
+        if ints:
+            for k in ("hash", "index", "cs", "ce", "dead"):
+                assert np.array_equal(a[k], b[k]), (k, a["step"])
+        vs = max(float(np.abs(b["vel"]).max()), 1e-3)
+        assert util.rel_err(a["pos"], b["pos"], 1.0) < tol, ("pos", a["step"])
+        assert util.rel_err(a["vel"], b["vel"], vs) < tol, ("vel", a["step"])
+        assert util.rel_err(a["rad"], b["rad"], 0.1) < tol, ("rad", a["step"])
+
+
+@pytest.mark.parametrize("name", util.CFGS)
+@pytest.mark.parametrize("sort_every_step", [False, True])
+def test_100_step_trajectory_vs_reference_kernels(name, sort_every_step):
+    """north_star: 1e-5 relative on pos/vel over 100 steps, integer tables bit-exact, against the
+    reference's own kernels driven by the same host logic (backend EXTERNAL)."""
+    if not util.refcuda_available():
+        pytest.skip("oracle/_ref/libprs_refcuda.so not built (needs /root/reference at build time)")
+    p, o = util.cfg(name)
+    si = o.timestep if sort_every_step else None
+    ref = _run(p, o, prs.BACKEND_EXTERNAL, 100, ob.REFCUDA_PATH, si)
+    for bname, kind, _ in _backends():
+        got = _run(p, o, kind, 100, None, si)
+        _compare(got, ref, TOL_REF)
+    fast = _run(p, o, prs.BACKEND_FUSED, 100, None, si, collide_mode=1)
+    _compare(fast, ref, TOL_REF)
+
+
+@pytest.mark.parametrize("name", util.CFGS)
+def test_100_step_trajectory_vs_oracle(name):
+    p, o = util.cfg(name)
+    s = ob.OracleSim(p)
+    s.srand(p.seed)
+    s.reset()
+    got = _run(p, o, prs.BACKEND_FUSED, 100, record_every=10)
+    k = 0
+    for snap in got:
+        while k < snap["step"]:
+            s.update(o.timestep, o.sort_interval)
+            k += 1
+        assert np.array_equal(snap["hash"], s.get("hash")) and np.array_equal(snap["index"], s.get("index"))
+        assert np.array_equal(snap["dead"], s.get("dead"))
+        vs = max(float(np.abs(s.get("vel")).max()), 1e-3)
+        assert util.rel_err(snap["pos"], s.get("pos"), 1.0) < TOL_ORACLE
+        assert util.rel_err(snap["vel"], s.get("vel"), vs) < 20 * TOL_ORACLE
+        assert util.rel_err(snap["rad"], s.get("rad"), 0.1) < TOL_ORACLE
+
+
+def test_fused_equals_percall_bitwise():
+    """The fused step is a re-scheduling of the same arithmetic: identical bits."""
+    p, o = util.cfg("example_obstacle")
+    a = _run(p, o, prs.BACKEND_PERCALL, 60, None, o.timestep)
+    b = _run(p, o, prs.BACKEND_FUSED, 60, None, o.timestep)
+    for x, y in zip(a, b):
+        for k in ("pos", "vel", "rad", "hash", "index", "cs", "ce", "phase"):
+            assert np.array_equal(x[k], y[k]), (k, x["step"])
+
+
+def test_synthetic_hex_swarm_properties():
+    """Size-independent checks at a size the oracle does not visit: sortedness, table consistency,
+    permutation, finite state, and parity of one collide call with the oracle on a 64k swarm."""
+    p, o = util.cfg("example")
+    nx = ny = 256
+    p.nCells = nx * ny
+    L = prs.lib()
+    L.prs_params_set_world(C.byref(p), 512, 64.0)
+    sim = prs.Simulation(p, 64.0, prs.BACKEND_FUSED)
+    sim.init_hex(nx, ny, 2 * p.min_radius, 0.01 * p.max_radius, 5555)
+    for _ in range(20):
+        sim.update(o.timestep, o.timestep)
+    h, idx, cs, ce = sim.get(prs.HASH), sim.get(prs.INDEX), sim.get(prs.CELLSTART), sim.get(prs.CELLEND)
+    n = p.nCells
+    assert np.all(h[1:] >= h[:-1])
+    assert np.array_equal(np.sort(idx), np.arange(n, dtype=np.uint32))
+    occ = np.unique(h)
+    assert np.array_equal(cs[occ], np.searchsorted(h, occ, "left").astype(np.uint32))
+    assert np.array_equal(ce[occ], np.searchsorted(h, occ, "right").astype(np.uint32))
+    pos, vel = sim.get(prs.POSITION), sim.get(prs.VELOCITY)
+    assert np.all(np.isfinite(pos)) and np.all(np.isfinite(vel))
+    spos, svel, srad = sim.get(prs.SORTEDPOS), sim.get(prs.SORTEDVEL), sim.get(prs.SORTEDRAD)
+    v_o, fa_o, fr_o = np.zeros((n, 2), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    ob.lib().prso_set_threads(ob.lib().prso_get_max_threads())
+    ob.lib().prso_collide(C.byref(p), v_o.ctypes.data, fa_o.ctypes.data, fr_o.ctypes.data, spos.ctypes.data,
+                          svel.ctypes.data, srad.ctypes.data, idx.ctypes.data, cs.ctypes.data, ce.ctypes.data, n,
+                          o.timestep)
+    ob.lib().prso_set_threads(1)
+    assert util.rel_err(vel, v_o, max(float(np.abs(v_o).max()), 1e-3)) < TOL_ORACLE
+    sim.close()
