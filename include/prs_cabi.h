@@ -93,6 +93,12 @@ int prs_get_collide_mode(void);
 /* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
 unsigned long long prs_launch_count(int reset);
 
+/* per-stage CUDA-event timing of prs_fused_step on the launching stream: stages are
+ * 0 controller+integrate(+hash), 1 sort, 2 reorder+cell table, 3 collide, 4 phase update.
+ * prs_stage_times synchronises, writes summed ms and span counts (5 entries each) and clears. */
+void prs_stage_timing(int enable);
+void prs_stage_times(float *ms, unsigned *counts);
+
 /* device-side replacement of the host loop particlebot.cpp:214-228: d_min_d[0] = min_i |light-p_i| */
 void prs_min_light_distance(const float *pos, int n, float *d_min_d);
 /* updatePhase reading min_d from device memory (no host round trip) */

@@ -148,7 +148,11 @@ extern "C" void prso_reorder_find_cell_start(const SimParams *, unsigned *cellSt
 static inline void pair_force(const SimParams *p, f2 pa, f2 pb, f2 va, f2 vb, float ra, float rb,
                               float attraction, f2 *force, float *forcea, float *forcer) {
   float rx = pb.x - pa.x, ry = pb.y - pa.y;
-  float dist = len2(rx, ry);
+  /* The ONE place where the oracle follows nvcc's FMA contraction (PTX of the reference build:
+   * mul ry*ry; fma rx*rx + that; sqrt.rn): the model is discontinuous at dist == ra+rb (contact
+   * spring ~0 vs attraction 2.5) and the aggregation placement puts pairs exactly at touching
+   * distance, so the regime decision must see the device's bits of `dist`. */
+  float dist = sqrtf(fmaf(rx, rx, ry * ry));
   float cd = ra + rb;
   float tx = 0.0f, ty = 0.0f;
   if (dist < cd) {

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include "prs_device.cuh"
 #include "prs_onesweep.cuh"
+#include <vector>
 
 struct PrsHostState {
   cudaStream_t stream = 0;            /* legacy default stream, like the reference */
@@ -16,7 +17,14 @@ struct PrsHostState {
   float world_half = 64.0f;           /* reference wall (kernel_impl.cuh:75-97) */
   int collide_mode = 0;               /* 0 exact, 1 fast */
   prs_sort::Workspace sort_ws;
+  /* optional per-stage CUDA-event timing of the fused step (bench.py's roofline numbers) */
+  bool stage_timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct StageSpan { int stage; cudaEvent_t a, b; };
+  std::vector<StageSpan> spans;
 };
+enum { PRS_STAGE_K1 = 0, PRS_STAGE_SORT = 1, PRS_STAGE_REORDER = 2, PRS_STAGE_COLLIDE = 3, PRS_STAGE_PHASE = 4, PRS_NUM_STAGES = 5 };
 extern PrsHostState g_prs;
 
 void prs_fail(const char *what, cudaError_t e, const char *file, int line);

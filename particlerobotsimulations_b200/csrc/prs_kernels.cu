@@ -51,6 +51,30 @@ void prs_fail(const char *what, cudaError_t e, const char *file, int line) {
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+/* stage timing: an event pair per stage and step on the launching stream, read after a sync */
+static cudaEvent_t next_event() {
+  if (g_prs.ev_used == g_prs.ev_pool.size()) {
+    cudaEvent_t e;
+    PRS_CUDA(cudaEventCreate(&e));
+    g_prs.ev_pool.push_back(e);
+  }
+  return g_prs.ev_pool[g_prs.ev_used++];
+}
+struct StageScope {
+  int stage;
+  cudaEvent_t a;
+  explicit StageScope(int s) : stage(s), a(0) {
+    if (g_prs.stage_timing) { a = next_event(); PRS_CUDA(cudaEventRecord(a, g_prs.stream)); }
+  }
+  ~StageScope() {
+    if (g_prs.stage_timing) {
+      cudaEvent_t b = next_event();
+      PRS_CUDA(cudaEventRecord(b, g_prs.stream));
+      g_prs.spans.push_back({stage, a, b});
+    }
+  }
+};
+
 /* ------------------------------------------------------------------------------------------
  * kernels
  * ------------------------------------------------------------------------------------------ */
@@ -659,17 +683,46 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
   if (!n) return;
   const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
   if (do_sort) {
-    PRS_LAUNCH(k_control_integrate_hash<true>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
-               b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
+    {
+      StageScope t(PRS_STAGE_K1);
+      PRS_LAUNCH(k_control_integrate_hash<true>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
+                 b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
+    }
+    StageScope t(PRS_STAGE_SORT);
     sort_pairs(b->hash, b->index, b->hash, b->index, n, key_bits_of_grid(), true);
   } else {
+    StageScope t(PRS_STAGE_K1);
     PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
   }
-  reorderDataAndFindCellStart(b->cellStart, b->cellEnd, b->sortedPos, b->sortedVel, b->sortedRad, b->hash, b->index,
-                              b->pos, b->vel, b->rad, n, b->numCells);
+  {
+    StageScope t(PRS_STAGE_REORDER);
+    reorderDataAndFindCellStart(b->cellStart, b->cellEnd, b->sortedPos, b->sortedVel, b->sortedRad, b->hash, b->index,
+                                b->pos, b->vel, b->rad, n, b->numCells);
+  }
+  StageScope t(PRS_STAGE_COLLIDE);
   collide(b->vel, b->absForce_a, b->absForce_r, b->sortedPos, b->sortedVel, b->sortedRad, b->index, b->cellStart,
           b->cellEnd, n, b->numCells, dt);
+}
+
+void prs_stage_timing(int enable) {
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+  g_prs.stage_timing = enable != 0;
+  g_prs.spans.clear();
+  g_prs.ev_used = 0;
+}
+/* sums the recorded spans per stage (ms) and their counts, then clears them */
+void prs_stage_times(float *ms, unsigned *counts) {
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+  for (int s = 0; s < PRS_NUM_STAGES; s++) { ms[s] = 0.0f; counts[s] = 0; }
+  for (const auto &sp : g_prs.spans) {
+    float t = 0.0f;
+    PRS_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+    ms[sp.stage] += t;
+    counts[sp.stage]++;
+  }
+  g_prs.spans.clear();
+  g_prs.ev_used = 0;
 }
 
 }  // extern "C"
