@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the per-timestep particle-robot update (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference|ref-cuda]
+                    [--robots-log2 L] [--sort-interval S] [--collide-mode 0|1]
+
+A "step" is one Particlebot::update() (controller -> integrate -> hash -> sort -> reorder ->
+collide) over the whole synthetic swarm.  Workloads:
+  N=1   S1: 2^20 robots on a 1024x1024 hex lattice (pitch 0.17 — 0.155 explodes under the reference's own
+        kernels, profiles/workload_stability_r1.txt — jitter 0.01*max_radius, seed 5555),
+        world half extent 128, 2048^2 cells of 0.235, light (-90,0), example.cfg physics,
+        sort EVERY step (sort_interval = timestep).
+  N>1   S2: 2^26 robots (8192x8192), world half extent 768, 8192^2 cells, slab-decomposed over the
+        ranks with halo exchange.
+Timing: W warm-up steps, then K steps each bracketed by CUDA events on the launching stream with
+an L2 flush (256 MiB write) between steps, outside the events; value = robots*K / sum(step times),
+max over ranks.  `back_to_back` is the same K steps without flushes (warm L2), for context.
+`e2e` runs the same steps through the C-ABI with HOST buffers: pinned-host -> device copies of
+pos/vel/rad before, device -> host copies of pos/vel/rad after every step, inside the timed region.
+`--impl reference` times the CPU oracle port (OpenMP, all host threads) — the reference ships no
+CPU path; `--impl ref-cuda` (extra) times the reference's OWN kernels compiled verbatim
+(oracle/_ref) on R1, the largest hex block its hard-coded +-64 world holds (640x640 robots);
+`--workload r1` runs this repo's path on the same swarm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PITCH = 0.17   # BASELINE.md S1 says 0.155 (= 2*min_radius): that crystal is numerically unstable in the reference's DEM model
+JITTER_FRAC = 0.01
+SEED = 5555
+STAGES = ["controller+integrate+hash", "sort", "reorder+celltable", "collide", "phase"]
+
+
+# ------------------------------------------------------------------------------------------------
+def swarm_config(prs, log2n, world64=False, nx=None, ny=None, pitch=None):
+    """SimParams + hex-block geometry of the synthetic swarm with 2^log2n robots (or nx*ny)."""
+    p, o = prs.load_cfg(os.path.join(ROOT, "examples", "example.cfg"))
+    pitch = PITCH if pitch is None else pitch
+    if nx is None:
+        nx = 1 << ((log2n + 1) // 2)
+        ny = 1 << (log2n // 2)
+    p.nCells = nx * ny
+    w, h = nx * pitch, ny * pitch * 0.8660254
+    if world64:
+        half, grid = 64.0, 512          # the reference's hard-coded world (kernel_impl.cuh:75-97, main.cpp:937)
+        light = (-60.0, 0.0)
+    else:
+        half = float(np.ceil(max(w, h) / 2 * 1.2 / 64.0) * 64.0)
+        grid = 1 << int(np.ceil(np.log2(2 * half / 0.235)))
+        light = {20: (-90.0, 0.0), 26: (-700.0, 0.0)}.get(log2n, (-0.7 * half, 0.0))
+    prs.lib().prs_params_set_world(C.byref(p), grid, half)
+    p.light_x, p.light_y = light
+    p.max_time = 1e30
+    name = {20: "S1", 26: "S2"}.get(log2n, f"S(2^{log2n})")
+    return p, o, dict(name=name, nx=nx, ny=ny, half=half, grid=grid, light=light, pitch=pitch)
+
+
+def algorithmic_bytes(p, sort_every_step=True):
+    """B_alg = 158 + 16*P + 4*C/N per particle-step (146 + 4*C/N without the sort)."""
+    bits = int(np.ceil(np.log2(p.numCells)))
+    passes = (bits + 7) // 8
+    per = {"controller+integrate+hash": 60 if sort_every_step else 52, "sort": 4 + 16 * passes if sort_every_step else 0,
+           "reorder+celltable": 51 + 4.0 * p.numCells / p.nCells, "collide": 43, "phase": 0}
+    return per, sum(per.values()), passes
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(p, o, geom, pos0, steps, threads, warm=1):
+    """particle-steps/s of the CPU oracle port on this swarm (test infrastructure used as baseline)."""
+    from oracle import binding as ob
+    L = ob.lib()
+    L.prso_set_threads(threads)
+    s = ob.OracleSim(p, geom["half"])
+    s.view("pos")[:] = pos0
+    s.view("rad")[:] = p.min_radius
+    for _ in range(warm):
+        s.update(o.timestep, o.timestep)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.update(o.timestep, o.timestep)
+    dt = time.perf_counter() - t0
+    s.close()
+    L.prso_set_threads(1)
+    return p.nCells * steps / dt, dt
+
+
+def hex_positions(p, geom):
+    """Same generator as Particlebot::initHexBlock, through the library (no GPU needed for the maths
+    but the object needs one; used by the GPU arms) — CPU copy for the reference arm."""
+    nx, ny = geom["nx"], geom["ny"]
+    n = nx * ny
+    i = np.arange(n, dtype=np.uint64)
+    ix, iy = (i % nx).astype(np.float32), (i // nx)
+    row = np.float32(geom["pitch"] * 0.8660254037844386)
+    pitch = np.float32(geom["pitch"])
+    x0 = np.float32(-0.5) * (np.float32(nx - 1) * pitch + np.float32(0.5) * pitch)
+    y0 = np.float32(-0.5) * np.float32(ny - 1) * row
+
+    def mix(z):
+        z = (z + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+    with np.errstate(over="ignore"):
+        h = mix((np.uint64(SEED) << np.uint64(32)) ^ i)
+    jit = np.float32(JITTER_FRAC * p.max_radius)
+    jx = ((h & np.uint64(0xFFFFFF)).astype(np.float32) / np.float32(8388608.0) - np.float32(1.0)) * jit
+    jy = (((h >> np.uint64(24)) & np.uint64(0xFFFFFF)).astype(np.float32) / np.float32(8388608.0) - np.float32(1.0)) * jit
+    x = x0 + ix * pitch + np.where((iy & 1) == 1, np.float32(0.5) * pitch, np.float32(0.0)).astype(np.float32) + jx
+    y = y0 + iy.astype(np.float32) * row + jy
+    return np.stack([x, y], 1).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_cpu(args):
+    """--impl reference: the reference has no CPU implementation; this times the oracle port with
+    every host thread on a bounded sample of the same workload (same lattice, density, physics)."""
+    import particlerobotsimulations_b200 as prs
+    from oracle import binding as ob
+    threads = len(os.sched_getaffinity(0))
+    budget_s = 120.0
+    log2n = args.robots_log2 or (20 if args.gpus == 1 else 26)
+    # probe at 2^14 robots, then take the largest power of four <= the workload that fits the budget
+    p, o, geom = swarm_config(prs, 14)
+    rate, _ = cpu_oracle_throughput(p, o, geom, hex_positions(p, geom), 3, threads)
+    sample = 14
+    while sample + 2 <= log2n and (1 << (sample + 2)) * (args.steps + args.warmup) / rate < budget_s:
+        sample += 2
+    p, o, geom = swarm_config(prs, sample)
+    pos0 = hex_positions(p, geom)
+    L = ob.lib()
+    L.prso_set_threads(threads)
+    s = ob.OracleSim(p, geom["half"])
+    s.view("pos")[:] = pos0
+    s.view("rad")[:] = p.min_radius
+    for _ in range(args.warmup):
+        s.update(o.timestep, o.timestep)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.update(o.timestep, o.timestep)
+    dt = time.perf_counter() - t0
+    value = p.nCells * args.steps / dt
+    sample_txt = f"{geom['name']} lattice cut to 2^{sample} robots ({geom['nx']}x{geom['ny']}), {args.steps} steps, sort every step"
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"S1 synthetic hex swarm (2^{log2n} robots), CPU sample 2^{sample}", "sort_interval": "timestep"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference ships no CPU path: OpenMP C++ restatement (oracle/prs_oracle.cpp) on the host cores",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import particlerobotsimulations_b200 as prs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from particlerobotsimulations_b200 import multigpu
+        return multigpu.bench_slabs(args, rank, world, local_rank)
+
+    torch.cuda.set_device(local_rank)
+    lib = prs.lib()
+    ref_cuda = args.impl == "ref-cuda"
+    log2n = args.robots_log2 or 20
+    r1 = ref_cuda or args.workload == "r1"
+    if r1:
+        # R1: the largest hex block the reference's hard-coded +-64 world / 512^2 grid holds
+        p, o, geom = swarm_config(prs, 0, world64=True, nx=640, ny=640)
+        geom["name"] = "R1"
+    else:
+        p, o, geom = swarm_config(prs, log2n)
+    n = int(p.nCells)
+    sort_interval = o.timestep if args.sort_interval is None else args.sort_interval
+    stream = torch.cuda.current_stream()
+    lib.prs_set_stream(C.c_void_p(stream.cuda_stream))
+    lib.prs_set_collide_mode(args.collide_mode)
+
+    if ref_cuda:
+        from oracle import binding as ob
+        if not os.path.exists(ob.REFCUDA_PATH):
+            print(json.dumps({"impl": "ref-cuda", "unavailable": "oracle/_ref/libprs_refcuda.so not built"}))
+            return
+        sim = prs.Simulation(p, geom["half"], prs.BACKEND_EXTERNAL, ob.REFCUDA_PATH)
+    else:
+        sim = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
+    sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], JITTER_FRAC * p.max_radius, SEED)
+    pos0 = sim.get(prs.POSITION)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        sim.update(o.timestep, sort_interval)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, L2 flushed between steps (outside the event pairs) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lib.prs_launch_count(1)
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize()
+    launches = int(lib.prs_launch_count(0))
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(np.sum(step_ms))
+    # back-to-back (warm L2), one event pair around K steps
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.steps):
+        step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    b2b_ms = a.elapsed_time(b)
+    clocks = sampler.stop()
+
+    value = n * args.steps / (total_ms * 1e-3)
+
+    # ---- per-stage event timing (native fused path only) ----
+    stages, roofline, roofline_step = None, None, None
+    peak, peak_src = measured_peak()
+    per_bytes, b_alg, passes = algorithmic_bytes(p, sort_interval <= o.timestep)
+    if not ref_cuda:
+        lib.prs_stage_timing(1)
+        for _ in range(args.steps):
+            flush.fill_(1)
+            step()
+        ms = (C.c_float * 5)()
+        cnt = (C.c_uint * 5)()
+        lib.prs_stage_times(ms, cnt)
+        lib.prs_stage_timing(0)
+        stages = {}
+        for i, name in enumerate(STAGES):
+            if cnt[i]:
+                avg_us = 1e3 * ms[i] / cnt[i]
+                gbs = per_bytes[name] * n / (avg_us * 1e-6) / 1e9 if per_bytes[name] else None
+                stages[name] = {"avg_us": avg_us, "alg_bytes_per_robot": per_bytes[name], "achieved_GBps": gbs,
+                                "frac_of_hbm_peak": (gbs / peak) if gbs else None}
+        dom = max(stages, key=lambda k: stages[k]["avg_us"])
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": stages[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                    "note": "collide is FP32/MUFU-issue-bound (IEEE div/sqrt per neighbour pair), not HBM-bound; "
+                            "see roofline_step for the whole-step HBM fraction"}
+    step_gbs = b_alg * value / 1e9
+    roofline_step = {"bound": "hbm", "alg_bytes_per_particle_step": b_alg, "radix_passes": passes, "achieved": step_gbs,
+                     "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "peak_source": peak_src}
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
+    h_pos = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    h_vel = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    h_rad = torch.empty((n,), dtype=torch.float32).pin_memory()
+    for which, t in ((prs.POSITION, h_pos), (prs.VELOCITY, h_vel), (prs.RADII, h_rad)):
+        lib.prs_sim_get(sim._h, which, t.data_ptr(), t.numel() * 4)
+    e2e_steps = max(3, min(args.steps, 50))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for which, t in ((prs.POSITION, h_pos), (prs.VELOCITY, h_vel), (prs.RADII, h_rad)):
+            lib.prs_sim_set(sim._h, which, t.data_ptr(), 0, t.numel() * 4)
+        step()
+        for which, t in ((prs.POSITION, h_pos), (prs.VELOCITY, h_vel), (prs.RADII, h_rad)):
+            lib.prs_sim_get(sim._h, which, t.data_ptr(), t.numel() * 4)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": n * e2e_steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 20 * n,
+           "d2h_bytes_per_step": 20 * n, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "what": "copyArrayToDevice(pos,vel,rad from pinned host) -> Particlebot::update -> copyArrayFromDevice(pos,vel,rad)"}
+
+    finite = bool(np.isfinite(sim.get(prs.POSITION)).all())
+    sim.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1): oracle port, all threads, a few steps of the same swarm ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        cpu_log2 = min(log2n, 18)
+        pc, oc, gc = swarm_config(prs, cpu_log2)
+        rate, dt = cpu_oracle_throughput(pc, oc, gc, hex_positions(pc, gc), 4, threads)
+        cpu = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+               "sample": f"same lattice cut to 2^{cpu_log2} robots, 4 steps after 1 warm-up, sort every step ({dt:.1f} s)"}
+
+    line = {
+        "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{geom['name']}: {n} robots, hex {geom['nx']}x{geom['ny']} pitch {geom['pitch']}, "
+                               f"world +-{geom['half']:g}, grid {geom['grid']}^2, light {geom['light']}",
+                   "sort_interval": "timestep (sort every step)" if sort_interval <= o.timestep else sort_interval,
+                   "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)"},
+        "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
+        "stages": stages, "cpu_baseline": cpu, "state_finite": finite,
+    }
+    if ref_cuda:
+        line["impl"] = "ref-cuda"
+        line["config"]["workload"] += " [reference kernels compiled verbatim; reference world +-64, grid 512^2]"
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "ref-cuda"])
+    ap.add_argument("--robots-log2", type=int, default=None)
+    ap.add_argument("--sort-interval", type=float, default=None)
+    ap.add_argument("--collide-mode", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="s1", choices=["s1", "r1"],
+                    help="s1: 2^robots_log2 hex swarm in its own world; r1: 640x640 swarm in the reference's +-64 world")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_reference_cpu(args)
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,8 +119,17 @@ typedef struct {
   unsigned *hash, *index, *cellStart, *cellEnd;                          /* grid tables */
   float *sortedPos, *sortedVel, *sortedRad;                              /* sorted copies */
   unsigned nCells, numCells;
+  /* optional: float4 {x, y, radius, original-index bits} per sorted slot.  When non-null the fused
+   * step fills THIS instead of sortedPos/sortedRad (prs_unpack_sorted converts on demand) and,
+   * unless constrained_contraction is set, does not produce absForce_a (nothing reads it then). */
+  float *sortedPR;
 } prs_step_buffers;
 void prs_fused_step(const prs_step_buffers *b, float time, float deltaTime, int do_sort);
+
+void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n);
+/* self-test: number of operand pairs for which the shared-reciprocal division used by collide
+ * differs from __fdiv_rn (must be 0) */
+unsigned long long prs_selftest_div(const float *d_x, const float *d_d, unsigned n);
 
 /* ---- simulation object (class Particlebot, include/prs_particlebot.hpp) for C callers ---- */
 typedef struct prs_sim prs_sim;

@@ -109,6 +109,7 @@ class Particlebot {
   float *dSortedPos, *tempPos1, *tempPos2, *dSortedVel, *dSortedRad;
   unsigned *dGridParticleHash, *dGridParticleIndex, *dCellStart, *dCellEnd;
   float *dMinD; /* device scalar for the fused path's light-distance reduction */
+  float *dSortedPR; /* fused path: packed float4 sorted copy (see prs_step_buffers) */
 
   float time;
   SimParams params;

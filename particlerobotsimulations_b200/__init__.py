@@ -68,7 +68,7 @@ class RunOptions(C.Structure):
 class StepBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "pos", "vel", "rad", "phase", "absForce_a", "absForce_r", "dead", "hash", "index", "cellStart", "cellEnd",
-        "sortedPos", "sortedVel", "sortedRad")] + [("nCells", C.c_uint), ("numCells", C.c_uint)]
+        "sortedPos", "sortedVel", "sortedRad")] + [("nCells", C.c_uint), ("numCells", C.c_uint), ("sortedPR", C.c_void_p)]
 
 
 _lib = None
@@ -101,6 +101,7 @@ SIGNATURES = {
     "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),
     "prs_centroid": (None, [_VP, _I, _VP, _VP]),
     "prs_sort_pairs": (None, [_VP, _VP, _VP, _VP, _U, _I]),
+    "prs_unpack_sorted": (None, [_VP, _VP, _VP, _U]), "prs_selftest_div": (C.c_ulonglong, [_VP, _VP, _U]),
     "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
     "prs_params_defaults": (None, [C.POINTER(SimParams), C.POINTER(RunOptions)]),
     "prs_params_load_cfg": (_I, [C.c_char_p, C.POINTER(SimParams), C.POINTER(RunOptions)]),

@@ -115,6 +115,52 @@ k_reorder(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, floa
   sortedVel[k] = v;
 }
 
+/* Fused-path variant of the gather: same cell tables, but the sorted copy is packed for the
+ * collide kernel's 128-bit neighbour loads — float4 {x, y, radius, original index bits} plus the
+ * float2 velocity (24 B written per robot instead of 20, one LDG.128 per neighbour instead of
+ * three loads; north_star (1)). */
+__global__ void __launch_bounds__(256)
+k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, float4 *__restrict__ sortedPR,
+                 float2 *__restrict__ sortedVel, const uint32_t *__restrict__ hash, const uint32_t *__restrict__ index,
+                 const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad,
+                 uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t h = hash[k];
+  const uint32_t src = index[k];
+  const uint32_t hp = (k > 0) ? hash[k - 1] : 0u;
+  const float2 p = pos[src];
+  const float2 v = vel[src];
+  const float r = rad[src];
+  if (k == 0 || h != hp) {
+    cellStart[h] = k;
+    if (k > 0) cellEnd[hp] = k;
+  }
+  if (k == n - 1) cellEnd[h] = k + 1;
+  sortedPR[k] = make_float4(p.x, p.y, r, __uint_as_float(src));
+  sortedVel[k] = v;
+}
+/* packed -> the reference's sortedPos / sortedRad arrays (only when a caller asks for them) */
+__global__ void __launch_bounds__(256) k_unpack_sorted(const float4 *__restrict__ pr, float2 *__restrict__ sortedPos,
+                                                       float *__restrict__ sortedRad, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float4 q = pr[k];
+  sortedPos[k] = make_float2(q.x, q.y);
+  sortedRad[k] = q.z;
+}
+
+/* bit-compare of the shared-reciprocal division against __fdiv_rn (self-test, see prs_collide.cuh) */
+__global__ void k_selftest_div(const float *__restrict__ x, const float *__restrict__ d, uint32_t n,
+                               unsigned long long *__restrict__ mismatches) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r1 = prs::rcp_refined(d[i]);
+  const float q = prs::div_shared(x[i], d[i], r1, prs::div_fast_ok(d[i]));
+  const float w = __fdiv_rn(x[i], d[i]);
+  if (__float_as_uint(q) != __float_as_uint(w) && !(q != q && w != w)) atomicAdd(mismatches, 1ull);
+}
+
 /* Euler step + wall bounce for one robot (result of integrate_functor, :53-103) */
 __device__ __forceinline__ void integrate_one(float2 &pos, float2 &vel, float rad, float dt) {
   const float W = c_prm.world_half;
@@ -695,14 +741,43 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
   }
+  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
+  if (b->sortedPR) {
+    {
+      StageScope t(PRS_STAGE_REORDER);
+      PRS_CUDA(cudaMemsetAsync(b->cellStart, 0xff, (size_t)b->numCells * sizeof(unsigned), g_prs.stream));
+      PRS_LAUNCH(k_reorder_packed, div_up(n, 256), 256, 0, b->cellStart, b->cellEnd, (float4 *)b->sortedPR,
+                 (float2 *)b->sortedVel, b->hash, b->index, (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
+    }
+    StageScope t(PRS_STAGE_COLLIDE);
+    prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
+    prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+    return;
+  }
   {
     StageScope t(PRS_STAGE_REORDER);
     reorderDataAndFindCellStart(b->cellStart, b->cellEnd, b->sortedPos, b->sortedVel, b->sortedRad, b->hash, b->index,
                                 b->pos, b->vel, b->rad, n, b->numCells);
   }
   StageScope t(PRS_STAGE_COLLIDE);
-  collide(b->vel, b->absForce_a, b->absForce_r, b->sortedPos, b->sortedVel, b->sortedRad, b->index, b->cellStart,
-          b->cellEnd, n, b->numCells, dt);
+  prs_launch_collide((float2 *)b->vel, b->absForce_a, b->absForce_r, (const float2 *)b->sortedPos,
+                     (const float2 *)b->sortedVel, b->sortedRad, b->index, b->cellStart, b->cellEnd, n, dt, need_fa);
+}
+
+void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n) {
+  if (!n) return;
+  PRS_LAUNCH(k_unpack_sorted, div_up(n, 256), 256, 0, (const float4 *)sortedPR, (float2 *)sortedPos, sortedRad, n);
+}
+
+unsigned long long prs_selftest_div(const float *d_x, const float *d_d, unsigned n) {
+  unsigned long long *dm, h = 0;
+  PRS_CUDA(cudaMalloc(&dm, sizeof(h)));
+  PRS_CUDA(cudaMemsetAsync(dm, 0, sizeof(h), g_prs.stream));
+  PRS_LAUNCH(k_selftest_div, div_up(n, 256), 256, 0, d_x, d_d, n, dm);
+  PRS_CUDA(cudaMemcpyAsync(&h, dm, sizeof(h), cudaMemcpyDeviceToHost, g_prs.stream));
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+  PRS_CUDA(cudaFree(dm));
+  return h;
 }
 
 void prs_stage_timing(int enable) {

@@ -151,16 +151,32 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
   const uint32_t tbase = block_excl_scan256(total, s_warp_tot);  /* digit start inside the tile */
   const uint32_t gex = block_excl_scan256(ghist[tid], s_warp_tot); /* digit start in the output */
 
+  /* Look-back, one thread per digit.  With <= ~300 tiles every tile is resident at once and the
+   * walk back to the nearest published PREFIX is long; the predecessors' words are therefore
+   * fetched LOOKBACK at a time (independent volatile loads in flight together) and consumed in
+   * order, stopping at the first word that is not published yet. */
+  constexpr int LOOKBACK = 8;
   uint32_t excl = 0;
   if (tile != 0) {
     int64_t t = (int64_t)tile - 1;
-    while (true) {
-      const uint32_t v = status[(size_t)t * RADIX + tid];
-      const uint32_t f = v & ~VALUE_MASK;
-      if (f == 0) continue; /* not published yet; the tile is resident (ids are handed out in start order) */
-      excl += v & VALUE_MASK;
-      if (f == FLAG_PREFIX) break;
-      t--;
+    bool done = false;
+    while (!done) {
+      uint32_t v[LOOKBACK];
+#pragma unroll
+      for (int i = 0; i < LOOKBACK; i++) {
+        const int64_t tt = t - i;
+        v[i] = (tt >= 0) ? status[(size_t)tt * RADIX + tid] : (uint32_t)(2u << 30); /* before tile 0: PREFIX with value 0 */
+      }
+      int used = 0;
+#pragma unroll
+      for (int i = 0; i < LOOKBACK; i++) {
+        const uint32_t f = v[i] & ~VALUE_MASK;
+        if (done || used != i || f == 0) continue; /* consume strictly in order */
+        excl += v[i] & VALUE_MASK;
+        used = i + 1;
+        if (f == FLAG_PREFIX) done = true;
+      }
+      t -= used;
     }
   }
   status[(size_t)tile * RADIX + tid] = (excl + count) | FLAG_PREFIX;

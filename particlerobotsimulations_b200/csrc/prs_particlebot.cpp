@@ -155,6 +155,8 @@ void Particlebot::_initialize() {
   be_.allocateArray((void **)&dDead, sizeof(int) * n);
   be_.allocateArray((void **)&dState, (size_t)48 * n);
   be_.allocateArray((void **)&dMinD, 64);
+  dSortedPR = 0;
+  if (backend_kind_ == PRS_BACKEND_FUSED) be_.allocateArray((void **)&dSortedPR, sizeof(float) * 4 * n + 16);
 
   /* The reference reads absForce_a/r (and the cell tables) before anything wrote them and relies
    * on fresh allocations being zero; make that explicit. */
@@ -184,6 +186,7 @@ void Particlebot::_finalize() {
                   dAbsForce_a, dAbsForce_r, dGridParticleHash, dGridParticleIndex, dCellStart, dCellEnd, dDead,
                   dState, dMinD};
   for (void *b : bufs) be_.freeArray(b);
+  if (dSortedPR) be_.freeArray(dSortedPR);
   if (be_.dl_handle) dlclose(be_.dl_handle);
 }
 
@@ -224,7 +227,7 @@ bool Particlebot::update(float deltaTime, float sort_interval) {
     b.pos = dPos; b.vel = dVel; b.rad = dRad; b.phase = dphase; b.absForce_a = dAbsForce_a; b.absForce_r = dAbsForce_r;
     b.dead = dDead; b.hash = dGridParticleHash; b.index = dGridParticleIndex; b.cellStart = dCellStart;
     b.cellEnd = dCellEnd; b.sortedPos = dSortedPos; b.sortedVel = dSortedVel; b.sortedRad = dSortedRad;
-    b.nCells = params.nCells; b.numCells = params.numCells;
+    b.nCells = params.nCells; b.numCells = params.numCells; b.sortedPR = dSortedPR;
     prs_fused_step(&b, time, deltaTime, sort_step ? 1 : 0);
   } else {
     /* the reference's own call sequence */
@@ -527,7 +530,11 @@ void *Particlebot::devicePtr(int which) {
     case PHASE: return dphase;       case FREQUENCY: return dfreq; case DEAD: return dDead;
     case 100: return dAbsForce_a;    case 101: return dAbsForce_r; case 102: return dGridParticleHash;
     case 103: return dGridParticleIndex; case 104: return dCellStart; case 105: return dCellEnd;
-    case 106: return dSortedPos;     case 107: return dSortedVel;  case 108: return dSortedRad;
+    case 106: case 108:
+      /* the fused path keeps the sorted copy packed; materialise the reference's arrays on demand */
+      if (dSortedPR) prs_unpack_sorted(dSortedPR, dSortedPos, dSortedRad, params.nCells);
+      return which == 106 ? (void *)dSortedPos : (void *)dSortedRad;
+    case 107: return dSortedVel;
     case 109: return dState;
   }
   return 0;

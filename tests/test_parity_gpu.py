@@ -93,6 +93,20 @@ def test_sort_bit_exact_and_stable(n, bits):
             assert np.array_equal(d_k.get(), r_k.get()) and np.array_equal(d_v.get(), r_v.get())
 
 
+def test_shared_reciprocal_division_is_correctly_rounded():
+    """collide's exact variant divides two numerators by one denominator with a shared refined
+    reciprocal (prs_collide.cuh); it must return the bits of the IEEE division the reference uses."""
+    L = prs.lib()
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    x = (rng.standard_normal(n) * np.exp(rng.uniform(-18, 3, n))).astype(np.float32)
+    d = np.exp(rng.uniform(-16, 3, n)).astype(np.float32)
+    x[:8] = [0.0, -0.0, 1e-40, -1e-38, np.inf, 1e38, 3e-31, np.nan]
+    d[8:16] = [0.0, 1e-40, np.inf, 1e38, 1e-38, 1.0, 3.0, 1e-31]
+    dx, dd = Dev(x), Dev(d)
+    assert L.prs_selftest_div(dx.ptr, dd.ptr, n) == 0
+
+
 def _grid_pipeline(L, p, pos, vel, rad):
     n = len(rad)
     d = dict(pos=Dev(pos), vel=Dev(vel), rad=Dev(rad), hash=Dev(4 * n, np.uint32), index=Dev(4 * n, np.uint32),
