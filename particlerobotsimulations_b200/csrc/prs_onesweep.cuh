@@ -8,7 +8,7 @@
  * ascending by 32-bit key, STABLE (equal keys keep their input order, i.e. ascending robot index
  * after calcHash).  Only ceil(key_bits/8) digits are processed: cell keys are < numCells.
  *
- * Per tile (256 threads x 16 keys): keys are ranked warp by warp with __match_any_sync (lanes
+ * Per tile (512 threads x 16 keys): keys are ranked warp by warp with __match_any_sync (lanes
  * holding the same digit elect a leader that bumps a per-warp digit counter in shared memory),
  * per-warp counters are prefix-summed across warps by one thread per digit, the tile's digit
  * counts are published as AGGREGATE, the exclusive prefix over earlier tiles is fetched by
@@ -25,34 +25,51 @@ namespace prs_sort {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;
 constexpr int WARPS = THREADS / 32;
 constexpr int ITEMS = 16;
-constexpr int TILE = THREADS * ITEMS;
+constexpr int TILE = THREADS * ITEMS; /* 8192 pairs per tile: 2^20 pairs = 128 tiles, all resident at once */
 constexpr int MAX_PASSES = 4;
+constexpr int HIST_THREADS = 256;
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PREFIX = 2u << 30;
 constexpr uint32_t VALUE_MASK = (1u << 30) - 1;
 
-/* digit histograms of every pass in one sweep; same-digit lanes are merged with match_any before
- * touching shared memory (cell keys of neighbouring robots share their high digits). */
-__global__ void __launch_bounds__(THREADS) k_histogram(const uint32_t *__restrict__ keys, uint32_t n,
-                                                       uint32_t *__restrict__ ghist, int npass) {
+/* dynamic shared memory of k_onesweep */
+struct __align__(16) Smem {
+  uint32_t cnt[WARPS][RADIX];   /* per-warp digit counters -> exclusive offsets across warps */
+  uint32_t tile_base[RADIX];    /* first slot of each digit inside the tile */
+  uint32_t gbase[RADIX];        /* output position of slot 0 of each digit minus its tile slot */
+  uint32_t keys[TILE];
+  uint32_t vals[TILE];
+  uint32_t warp_tot[WARPS];
+  uint32_t tile;
+};
+
+/* Digit histograms of every pass in one sweep.  Cell keys of neighbouring robots share their
+ * high digits, so a warp whose 32 keys agree on a digit adds 32 with one atomic; mixed warps use
+ * plain shared-memory atomics (few-way conflicts). */
+__global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t *__restrict__ keys, uint32_t n,
+                                                            uint32_t *__restrict__ ghist, int npass) {
   __shared__ uint32_t sh[MAX_PASSES][RADIX];
-  for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += THREADS) (&sh[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&sh[0][0])[i] = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t n_round = (n + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n_round; i += gridDim.x * THREADS) {
+  for (uint32_t i = blockIdx.x * HIST_THREADS + threadIdx.x; i < n_round; i += gridDim.x * HIST_THREADS) {
     const bool valid = i < n;
     const uint32_t k = valid ? keys[i] : 0u;
     const uint32_t active = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      for (int p = 0; p < npass; p++) {
-        const uint32_t d = (k >> (p * RADIX_BITS)) & (RADIX - 1);
-        const uint32_t m = __match_any_sync(active, d);
-        if ((uint32_t)(__ffs(m) - 1) == lane) atomicAdd(&sh[p][d], (uint32_t)__popc(m));
+    const int src = __ffs(active) - 1;
+    for (int p = 0; p < npass; p++) {
+      const uint32_t d = (k >> (p * RADIX_BITS)) & (RADIX - 1);
+      const uint32_t d0 = __shfl_sync(0xffffffffu, d, src);
+      const bool uniform = __all_sync(0xffffffffu, !valid || d == d0);
+      if (uniform) {
+        if ((int)lane == src) atomicAdd(&sh[p][d0], (uint32_t)__popc(active));
+      } else if (valid) {
+        atomicAdd(&sh[p][d], 1u);
       }
     }
   }
@@ -74,8 +91,8 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
   return inc - v;
 }
 
-/* exclusive scan of one value per thread over the 256-thread block */
-__device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t *s_warp_tot) {
+/* exclusive scan over the block of one value per thread (threads >= RADIX pass 0) */
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp_tot) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t tot;
   uint32_t ex = warp_excl_scan(v, lane, &tot);
@@ -90,24 +107,18 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t *s_w
 
 /* One digit pass.  vin == nullptr means "values are the input positions" (first pass after
  * calcHash, where index[i] = i), which saves reading 4 B per pair. */
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
            uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ ghist,
            volatile uint32_t *status, uint32_t *tile_counter) {
-  __shared__ uint32_t s_cnt[WARPS][RADIX];
-  __shared__ uint32_t s_tile_base[RADIX];
-  __shared__ uint32_t s_gbase[RADIX];
-  __shared__ uint32_t s_keys[TILE];
-  __shared__ uint32_t s_vals[TILE];
-  __shared__ uint32_t s_warp_tot[WARPS];
-  __shared__ uint32_t s_tile;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-#pragma unroll
-  for (int w = 0; w < WARPS; w++) s_cnt[w][tid] = 0;
+  if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
+  for (int i = tid; i < WARPS * RADIX; i += THREADS) (&S.cnt[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t tile = s_tile;
+  const uint32_t tile = S.tile;
   const uint32_t tile_base = tile * (uint32_t)TILE;
   const uint32_t tile_valid = min((uint32_t)TILE, n - tile_base);
   const uint32_t wbase = tile_base + warp * (ITEMS * 32);
@@ -119,16 +130,21 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
     const uint32_t i = wbase + t * 32 + lane;
     key[t] = (i < n) ? kin[i] : 0xffffffffu; /* padding sorts to the very end of the tile */
   }
+  /* stable ranks inside the warp's 512 keys: lanes holding the same digit are found with
+   * match_any (one vote when the whole warp agrees), their leader bumps the warp's counter */
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int t = 0; t < ITEMS; t++) {
     const uint32_t d = (key[t] >> shift) & (RADIX - 1);
-    const uint32_t m = __match_any_sync(0xffffffffu, d);
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+    uint32_t m;
+    if (__all_sync(0xffffffffu, d == d0)) m = 0xffffffffu;
+    else m = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(m) - 1;
     uint32_t prev = 0;
     if ((int)lane == leader) {
-      prev = s_cnt[warp][d];
-      s_cnt[warp][d] = prev + __popc(m);
+      prev = S.cnt[warp][d];
+      S.cnt[warp][d] = prev + __popc(m);
     }
     prev = __shfl_sync(0xffffffffu, prev, leader);
     rank[t] = (uint16_t)(prev + __popc(m & lt_mask));
@@ -136,69 +152,72 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
   }
   __syncthreads();
 
-  /* thread `tid` owns digit `tid`: warp counts -> exclusive offsets across warps */
-  uint32_t total = 0;
+  /* thread d < 256 owns digit d: warp counts -> exclusive offsets across warps */
+  uint32_t total = 0, count = 0;
+  if (tid < RADIX) {
 #pragma unroll
-  for (int w = 0; w < WARPS; w++) {
-    const uint32_t cw = s_cnt[w][tid];
-    s_cnt[w][tid] = total;
-    total += cw;
-  }
-  uint32_t count = total;
-  if (tid == RADIX - 1) count -= (uint32_t)TILE - tile_valid; /* padding is not data */
-  if (tile != 0) status[(size_t)tile * RADIX + tid] = count | FLAG_AGG;
-
-  const uint32_t tbase = block_excl_scan256(total, s_warp_tot);  /* digit start inside the tile */
-  const uint32_t gex = block_excl_scan256(ghist[tid], s_warp_tot); /* digit start in the output */
-
-  /* Look-back, one thread per digit.  With <= ~300 tiles every tile is resident at once and the
-   * walk back to the nearest published PREFIX is long; the predecessors' words are therefore
-   * fetched LOOKBACK at a time (independent volatile loads in flight together) and consumed in
-   * order, stopping at the first word that is not published yet. */
-  constexpr int LOOKBACK = 8;
-  uint32_t excl = 0;
-  if (tile != 0) {
-    int64_t t = (int64_t)tile - 1;
-    bool done = false;
-    while (!done) {
-      uint32_t v[LOOKBACK];
-#pragma unroll
-      for (int i = 0; i < LOOKBACK; i++) {
-        const int64_t tt = t - i;
-        v[i] = (tt >= 0) ? status[(size_t)tt * RADIX + tid] : (uint32_t)(2u << 30); /* before tile 0: PREFIX with value 0 */
-      }
-      int used = 0;
-#pragma unroll
-      for (int i = 0; i < LOOKBACK; i++) {
-        const uint32_t f = v[i] & ~VALUE_MASK;
-        if (done || used != i || f == 0) continue; /* consume strictly in order */
-        excl += v[i] & VALUE_MASK;
-        used = i + 1;
-        if (f == FLAG_PREFIX) done = true;
-      }
-      t -= used;
+    for (int w = 0; w < WARPS; w++) {
+      const uint32_t cw = S.cnt[w][tid];
+      S.cnt[w][tid] = total;
+      total += cw;
     }
+    count = total;
+    if (tid == RADIX - 1) count -= (uint32_t)TILE - tile_valid; /* padding is not data */
+    if (tile != 0) status[(size_t)tile * RADIX + tid] = count | FLAG_AGG;
   }
-  status[(size_t)tile * RADIX + tid] = (excl + count) | FLAG_PREFIX;
-  s_tile_base[tid] = tbase;
-  s_gbase[tid] = gex + excl - tbase;
+  const uint32_t tbase = block_excl_scan(total, S.warp_tot);                               /* digit start inside the tile */
+  const uint32_t gex = block_excl_scan(tid < RADIX ? ghist[tid] : 0u, S.warp_tot);         /* digit start in the output */
+
+  /* Look-back, one thread per digit.  Up to a few hundred tiles are resident at once and finish
+   * ranking together, so the walk back to the nearest published PREFIX is long; the
+   * predecessors' words are therefore fetched LOOKBACK at a time (independent volatile loads in
+   * flight together) and consumed in order, stopping at the first word not published yet. */
+  if (tid < RADIX) {
+    constexpr int LOOKBACK = 16;
+    uint32_t excl = 0;
+    if (tile != 0) {
+      int64_t t = (int64_t)tile - 1;
+      bool done = false;
+      while (!done) {
+        uint32_t v[LOOKBACK];
+#pragma unroll
+        for (int i = 0; i < LOOKBACK; i++) {
+          const int64_t tt = t - i;
+          v[i] = (tt >= 0) ? status[(size_t)tt * RADIX + tid] : (uint32_t)(2u << 30); /* before tile 0: PREFIX 0 */
+        }
+        int used = 0;
+#pragma unroll
+        for (int i = 0; i < LOOKBACK; i++) {
+          const uint32_t f = v[i] & ~VALUE_MASK;
+          if (done || used != i || f == 0) continue; /* consume strictly in order */
+          excl += v[i] & VALUE_MASK;
+          used = i + 1;
+          if (f == (uint32_t)(2u << 30)) done = true;
+        }
+        t -= used;
+      }
+    }
+    status[(size_t)tile * RADIX + tid] = (excl + count) | FLAG_PREFIX;
+    S.tile_base[tid] = tbase;
+    S.gbase[tid] = gex + excl - tbase;
+  }
   __syncthreads();
 
 #pragma unroll
   for (int t = 0; t < ITEMS; t++) {
     const uint32_t d = (key[t] >> shift) & (RADIX - 1);
-    const uint32_t p = s_tile_base[d] + s_cnt[warp][d] + rank[t];
+    const uint32_t p = S.tile_base[d] + S.cnt[warp][d] + rank[t];
     const uint32_t i = wbase + t * 32 + lane;
-    s_keys[p] = key[t];
-    s_vals[p] = (i < n) ? (vin ? vin[i] : i) : 0u;
+    S.keys[p] = key[t];
+    S.vals[p] = (i < n) ? (vin ? vin[i] : i) : 0u;
   }
   __syncthreads();
   for (uint32_t j = tid; j < tile_valid; j += THREADS) {
-    const uint32_t k = s_keys[j];
+    const uint32_t k = S.keys[j];
     const uint32_t d = (k >> shift) & (RADIX - 1);
-    const uint32_t o = s_gbase[d] + j;
+    const uint32_t o = S.gbase[d] + j;
     kout[o] = k;
-    vout[o] = s_vals[j];
+    vout[o] = S.vals[j];
   }
 }
 

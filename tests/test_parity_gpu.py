@@ -93,16 +93,23 @@ def test_sort_bit_exact_and_stable(n, bits):
             assert np.array_equal(d_k.get(), r_k.get()) and np.array_equal(d_v.get(), r_v.get())
 
 
-def test_shared_reciprocal_division_is_correctly_rounded():
-    """collide's exact variant divides two numerators by one denominator with a shared refined
-    reciprocal (prs_collide.cuh); it must return the bits of the IEEE division the reference uses."""
+def test_fast_path_sequences_match_ieee_operators():
+    """collide's exact variant runs nvcc's own fast-path sequences for x/d (with a shared refined
+    reciprocal), sqrt and __powf(.,2) under ONE range test per pair (prs_collide.cuh).  Over the
+    admitted operand ranges they must return the bits of __fdiv_rn / __fsqrt_rn / __powf."""
     L = prs.lib()
     rng = np.random.default_rng(7)
     n = 1 << 22
-    x = (rng.standard_normal(n) * np.exp(rng.uniform(-18, 3, n))).astype(np.float32)
-    d = np.exp(rng.uniform(-16, 3, n)).astype(np.float32)
-    x[:8] = [0.0, -0.0, 1e-40, -1e-38, np.inf, 1e38, 3e-31, np.nan]
-    d[8:16] = [0.0, 1e-40, np.inf, 1e38, 1e-38, 1.0, 3.0, 1e-31]
+    # numerators: offsets / attraction*unit-vector, magnitudes 1e-20 .. 1e6 (and exact zeros)
+    x = (rng.choice([-1.0, 1.0], n) * np.exp(rng.uniform(np.log(1e-20), np.log(1e6), n))).astype(np.float32)
+    x[:64] = 0.0
+    x[64:128] = -0.0
+    # denominators: dist in [1e-10, 1e6], gap^2 in [3.6e-6, 1e12]; also used as sqrt / powf2 operands
+    d = np.exp(rng.uniform(np.log(1e-10), np.log(1e12), n)).astype(np.float32)
+    d[: n // 2] = np.exp(rng.uniform(np.log(1.9e-3), np.log(10.0), n // 2)).astype(np.float32)  # typical gaps / distances
+    # keep quotients inside the normal range, as they are in collide
+    q = np.abs(x.astype(np.float64)) / d.astype(np.float64)
+    x[(q > 1e30) | ((q < 1e-30) & (x != 0))] = 1.0
     dx, dd = Dev(x), Dev(d)
     assert L.prs_selftest_div(dx.ptr, dd.ptr, n) == 0
 
