@@ -793,4 +793,24 @@ unsigned long long prs_selftest_div(const float *d_x, const float *d_d, unsigned
   return h[0] + h[1] + h[2];
 }
 
+void prs_stage_timing(int enable) {
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+  g_prs.stage_timing = enable != 0;
+  g_prs.spans.clear();
+  g_prs.ev_used = 0;
+}
+/* sums the recorded spans per stage (ms) and their counts, then clears them */
+void prs_stage_times(float *ms, unsigned *counts) {
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+  for (int s = 0; s < PRS_NUM_STAGES; s++) { ms[s] = 0.0f; counts[s] = 0; }
+  for (const auto &sp : g_prs.spans) {
+    float t = 0.0f;
+    PRS_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+    ms[sp.stage] += t;
+    counts[sp.stage]++;
+  }
+  g_prs.spans.clear();
+  g_prs.ev_used = 0;
+}
+
 }  // extern "C"
