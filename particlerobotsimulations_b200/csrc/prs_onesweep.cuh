@@ -8,7 +8,7 @@
  * ascending by 32-bit key, STABLE (equal keys keep their input order, i.e. ascending robot index
  * after calcHash).  Only ceil(key_bits/8) digits are processed: cell keys are < numCells.
  *
- * Per tile (512 threads x 16 keys): keys are ranked warp by warp with __match_any_sync (lanes
+ * Per tile (512 threads x 8 keys): keys are ranked warp by warp with __match_any_sync (lanes
  * holding the same digit elect a leader that bumps a per-warp digit counter in shared memory),
  * per-warp counters are prefix-summed across warps by one thread per digit, the tile's digit
  * counts are published as AGGREGATE, the exclusive prefix over earlier tiles is fetched by
@@ -27,8 +27,8 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int THREADS = 512;
 constexpr int WARPS = THREADS / 32;
-constexpr int ITEMS = 16;
-constexpr int TILE = THREADS * ITEMS; /* 8192 pairs per tile: 2^20 pairs = 128 tiles, all resident at once */
+constexpr int ITEMS = 8;
+constexpr int TILE = THREADS * ITEMS; /* 4096 pairs per tile, two tiles resident per SM: short per-warp dependency chains */
 constexpr int MAX_PASSES = 4;
 constexpr int HIST_THREADS = 256;
 
@@ -137,9 +137,8 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
   for (int t = 0; t < ITEMS; t++) {
     const uint32_t d = (key[t] >> shift) & (RADIX - 1);
     const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
-    uint32_t m;
-    if (__all_sync(0xffffffffu, d == d0)) m = 0xffffffffu;
-    else m = __match_any_sync(0xffffffffu, d);
+    uint32_t m = 0xffffffffu;
+    if (!__all_sync(0xffffffffu, d == d0)) m = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(m) - 1;
     uint32_t prev = 0;
     if ((int)lane == leader) {
