@@ -126,6 +126,25 @@ typedef struct {
 } prs_step_buffers;
 void prs_fused_step(const prs_step_buffers *b, float time, float deltaTime, int do_sort);
 
+/* ---- slab (multi-GPU) building blocks: the fused step cut where ranks exchange robots ----
+ * (particlerobotsimulations_b200/multigpu.py drives them; DESIGN.md "multi-GPU") */
+void prs_slab_k1(float *pos, float *vel, float *rad, const float *phase, const float *absForce_a,
+                 const float *absForce_r, const int *dead, unsigned *hash, unsigned *index, float time, float dt,
+                 unsigned n, int do_hash);
+void prs_slab_sort(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys, unsigned *out_vals,
+                   unsigned n, int vals_are_iota);
+void prs_slab_gather(float *sortedPR, float *sortedVel, const unsigned *index, const float *pos, const float *vel,
+                     const float *rad, unsigned n);
+void prs_slab_cell_table(unsigned *cellStart, unsigned *cellEnd, const unsigned *hash, unsigned n, unsigned slot0,
+                         unsigned cell_lo, unsigned ncells);
+void prs_slab_lower_bounds(const unsigned *hash, unsigned n, const unsigned *d_bounds, unsigned nb, unsigned *d_out);
+void prs_slab_collide(float *newVel, float *absForce_a, float *absForce_r, const float *sortedPR,
+                      const float *sortedVel, const unsigned *cellStart, const unsigned *cellEnd, unsigned k_begin,
+                      unsigned k_end, float dt);
+/* orders the robots of each cell by global id (ties of the local sort are by local slot) */
+void prs_slab_fix_ties(const unsigned *hash_sorted, unsigned *index_sorted, const unsigned *gid, unsigned n);
+void prs_curand_setup_ids(struct curandStateXORWOW *state, const unsigned *gid, unsigned n);
+
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n);
 /* self-test: number of operand pairs for which the shared-reciprocal division used by collide
  * differs from __fdiv_rn (must be 0) */

@@ -101,6 +101,11 @@ SIGNATURES = {
     "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),
     "prs_centroid": (None, [_VP, _I, _VP, _VP]),
     "prs_sort_pairs": (None, [_VP, _VP, _VP, _VP, _U, _I]),
+    "prs_slab_k1": (None, [_VP] * 9 + [_F, _F, _U, _I]), "prs_slab_sort": (None, [_VP, _VP, _VP, _VP, _U, _I]),
+    "prs_slab_gather": (None, [_VP] * 6 + [_U]), "prs_slab_cell_table": (None, [_VP, _VP, _VP, _U, _U, _U, _U]),
+    "prs_slab_lower_bounds": (None, [_VP, _U, _VP, _U, _VP]),
+    "prs_slab_collide": (None, [_VP] * 7 + [_U, _U, _F]), "prs_curand_setup_ids": (None, [_VP, _VP, _U]),
+    "prs_slab_fix_ties": (None, [_VP, _VP, _VP, _U]),
     "prs_unpack_sorted": (None, [_VP, _VP, _VP, _U]), "prs_selftest_div": (C.c_ulonglong, [_VP, _VP, _U]),
     "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
     "prs_params_defaults": (None, [C.POINTER(SimParams), C.POINTER(RunOptions)]),

@@ -140,6 +140,73 @@ k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEn
   sortedPR[k] = make_float4(p.x, p.y, r, __uint_as_float(src));
   sortedVel[k] = v;
 }
+/* Slab (multi-GPU) variants: the gather and the cell table are separate because the table is
+ * built over [lower halo | owned | upper halo] once the neighbours' rows have arrived.
+ * slot_of: what goes into pr.w for owned robots (their local slot, the scatter target). */
+__global__ void __launch_bounds__(256)
+k_gather_packed(float4 *__restrict__ sortedPR, float2 *__restrict__ sortedVel, const uint32_t *__restrict__ index,
+                const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t src = index[k];
+  const float2 p = pos[src];
+  sortedPR[k] = make_float4(p.x, p.y, rad[src], __uint_as_float(src));
+  sortedVel[k] = vel[src];
+}
+/* cellStart/cellEnd over a sorted key array whose slot numbering starts at `slot0` */
+__global__ void __launch_bounds__(256)
+k_cell_table(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, const uint32_t *__restrict__ hash,
+             uint32_t n, uint32_t slot0) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t h = hash[k];
+  const uint32_t hp = (k > 0) ? hash[k - 1] : 0u;
+  if (k == 0 || h != hp) {
+    cellStart[h] = slot0 + k;
+    if (k > 0) cellEnd[hp] = slot0 + k;
+  }
+  if (k == n - 1) cellEnd[h] = slot0 + k + 1;
+}
+/* first slot whose key is >= bound[i] (binary search; used to cut halo rows out of the sorted keys) */
+__global__ void k_lower_bounds(const uint32_t *__restrict__ hash, uint32_t n, const uint32_t *__restrict__ bounds,
+                               uint32_t nb, uint32_t *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const uint32_t key = bounds[i];
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (hash[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  out[i] = lo;
+}
+/* Slab ranks hold their robots in arbitrary local slots, but the reference's stable sort leaves the
+ * robots of one cell in ascending ORIGINAL index.  After the local sort (ties by local slot) the
+ * thread at each cell start insertion-sorts that cell's few entries by global id, so forces are
+ * summed in exactly the single-GPU order (bit-equal results across any number of slabs). */
+__global__ void __launch_bounds__(256)
+k_fix_ties_by_gid(const uint32_t *__restrict__ hash, uint32_t *__restrict__ index, const uint32_t *__restrict__ gid, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t h = hash[k];
+  if (k > 0 && hash[k - 1] == h) return; /* not a cell start */
+  uint32_t e = k + 1;
+  while (e < n && hash[e] == h) e++;
+  for (uint32_t a = k + 1; a < e; a++) {
+    const uint32_t slot = index[a];
+    const uint32_t g = gid[slot];
+    uint32_t b = a;
+    while (b > k && gid[index[b - 1]] > g) { index[b] = index[b - 1]; b--; }
+    index[b] = slot;
+  }
+}
+/* XORWOW states for robots that carry GLOBAL ids (slab ranks): subsequence = global id, so every
+ * robot's noise stream is the one the single-GPU run (and the reference) gives it */
+__global__ void __launch_bounds__(256) k_curand_setup_ids(curandState *__restrict__ st, const uint32_t *__restrict__ gid, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) curand_init(c_prm.p.seed, gid[i], 0, &st[i]);
+}
+
 /* packed -> the reference's sortedPos / sortedRad arrays (only when a caller asks for them) */
 __global__ void __launch_bounds__(256) k_unpack_sorted(const float4 *__restrict__ pr, float2 *__restrict__ sortedPos,
                                                        float *__restrict__ sortedRad, uint32_t n) {
@@ -774,6 +841,69 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
   StageScope t(PRS_STAGE_COLLIDE);
   prs_launch_collide((float2 *)b->vel, b->absForce_a, b->absForce_r, (const float2 *)b->sortedPos,
                      (const float2 *)b->sortedVel, b->sortedRad, b->index, b->cellStart, b->cellEnd, n, dt, need_fa);
+}
+
+/* ---- slab (multi-GPU) building blocks: the fused step cut at the points where ranks exchange ---- */
+void prs_slab_k1(float *pos, float *vel, float *rad, const float *phase, const float *absForce_a,
+                 const float *absForce_r, const int *dead, unsigned *hash, unsigned *index, float time, float dt,
+                 unsigned n, int do_hash) {
+  if (!n) return;
+  const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
+  StageScope t(PRS_STAGE_K1);
+  if (do_hash)
+    PRS_LAUNCH(k_control_integrate_hash<true>, div_up(n, 256), 256, 0, (float2 *)pos, (float2 *)vel, rad, phase,
+               absForce_a, absForce_r, dead, hash, index, time, dt, run_controller, n);
+  else
+    PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)pos, (float2 *)vel, rad, phase,
+               absForce_a, absForce_r, dead, hash, index, time, dt, run_controller, n);
+}
+void prs_slab_sort(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys, unsigned *out_vals,
+                   unsigned n, int vals_are_iota) {
+  StageScope t(PRS_STAGE_SORT);
+  sort_pairs(in_keys, in_vals, out_keys, out_vals, n, key_bits_of_grid(), vals_are_iota != 0);
+}
+void prs_slab_gather(float *sortedPR, float *sortedVel, const unsigned *index, const float *pos, const float *vel,
+                     const float *rad, unsigned n) {
+  if (!n) return;
+  StageScope t(PRS_STAGE_REORDER);
+  PRS_LAUNCH(k_gather_packed, div_up(n, 256), 256, 0, (float4 *)sortedPR, (float2 *)sortedVel, index,
+             (const float2 *)pos, (const float2 *)vel, rad, n);
+}
+/* clears cellStart for cells [cell_lo, cell_lo + ncells) and builds the table from n sorted keys */
+void prs_slab_cell_table(unsigned *cellStart, unsigned *cellEnd, const unsigned *hash, unsigned n, unsigned slot0,
+                         unsigned cell_lo, unsigned ncells) {
+  StageScope t(PRS_STAGE_REORDER);
+  PRS_CUDA(cudaMemsetAsync(cellStart + cell_lo, 0xff, (size_t)ncells * sizeof(unsigned), g_prs.stream));
+  if (!n) return;
+  PRS_LAUNCH(k_cell_table, div_up(n, 256), 256, 0, cellStart, cellEnd, hash, n, slot0);
+}
+void prs_slab_lower_bounds(const unsigned *hash, unsigned n, const unsigned *d_bounds, unsigned nb, unsigned *d_out) {
+  if (!nb) return;
+  PRS_LAUNCH(k_lower_bounds, div_up(nb, 32), 32, 0, hash, n, d_bounds, nb, d_out);
+}
+/* collide for sorted slots [k_begin, k_end) of the concatenated [halo | owned | halo] arrays;
+ * results are scattered to pr.w of each slot (the owner's local slot) */
+void prs_slab_collide(float *newVel, float *absForce_a, float *absForce_r, const float *sortedPR,
+                      const float *sortedVel, const unsigned *cellStart, const unsigned *cellEnd, unsigned k_begin,
+                      unsigned k_end, float dt) {
+  if (k_end <= k_begin) return;
+  if (g_prs.h_prm.p.nDead == -1) {
+    fprintf(stderr, "prs_slab_collide: object-transport mode (nDead == -1) is single-GPU only\n");
+    exit(EXIT_FAILURE);
+  }
+  StageScope t(PRS_STAGE_COLLIDE);
+  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
+  prs::PackedLayout in{(const float4 *)sortedPR, (const float2 *)sortedVel};
+  prs_launch_collide_t((float2 *)newVel, absForce_a, absForce_r, in, cellStart, cellEnd, k_end, dt, need_fa, k_begin);
+}
+void prs_slab_fix_ties(const unsigned *hash_sorted, unsigned *index_sorted, const unsigned *gid, unsigned n) {
+  if (!n) return;
+  StageScope t(PRS_STAGE_SORT);
+  PRS_LAUNCH(k_fix_ties_by_gid, div_up(n, 256), 256, 0, hash_sorted, index_sorted, gid, n);
+}
+void prs_curand_setup_ids(struct curandStateXORWOW *state, const unsigned *gid, unsigned n) {
+  if (!n) return;
+  PRS_LAUNCH(k_curand_setup_ids, div_up(n, 256), 256, 0, (curandState *)state, gid, n);
 }
 
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n) {
