@@ -242,6 +242,70 @@ def test_collide_wraparound_stencil_uses_cell_path():
     assert util.rel_err(out[0].get(), v_o, max(float(np.abs(v_o).max()), 1e-3)) < TOL_ORACLE
 
 
+def _collide_vs_reference(p, o, pos, vel, rad, stale_shift=None):
+    """collide (C-ABI) on a hand-made swarm: bits vs the reference kernels, tolerance vs the oracle.
+    stale_shift moves the robots AFTER the tables are built (Q1: stale table, current-position cell)."""
+    n = len(rad)
+    L = prs.lib()
+
+    def run(lib):
+        d = _grid_pipeline(lib, p, pos, vel, rad)
+        spos = d["spos"].get(np.float32, (n, 2))
+        if stale_shift is not None:
+            spos = (spos + stale_shift).astype(np.float32)
+            d["spos"].set(spos)
+        out = [Dev(np.zeros((n, 2), np.float32)), Dev(np.zeros(n, np.float32)), Dev(np.zeros(n, np.float32))]
+        lib.collide(out[0].ptr, out[1].ptr, out[2].ptr, d["spos"].ptr, d["svel"].ptr, d["srad"].ptr, d["index"].ptr,
+                    d["cs"].ptr, d["ce"].ptr, n, p.numCells, o.timestep)
+        return [x.get() for x in out], d, spos
+
+    (v, fa, fr), d, spos = run(L)
+    v_o, fa_o, fr_o = np.zeros((n, 2), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    svel, srad = d["svel"].get(np.float32, (n, 2)), d["srad"].get()
+    idx, cs, ce = d["index"].get(), d["cs"].get(), d["ce"].get()
+    ob.lib().prso_collide(C.byref(p), v_o.ctypes.data, fa_o.ctypes.data, fr_o.ctypes.data, spos.ctypes.data,
+                          svel.ctypes.data, srad.ctypes.data, idx.ctypes.data, cs.ctypes.data, ce.ctypes.data, n, o.timestep)
+    assert np.all(np.isfinite(v_o))
+    assert util.rel_err(v, v_o, max(float(np.abs(v_o).max()), 1e-3)) < TOL_ORACLE
+    if util.refcuda_available():
+        (v_r, fa_r, fr_r), _, _ = run(util.refcuda())
+        assert np.array_equal(v.view(np.uint32), v_r.view(np.uint32))
+        assert np.array_equal(fa.view(np.uint32), fa_r.view(np.uint32))
+        assert np.array_equal(fr.view(np.uint32), fr_r.view(np.uint32))
+    return v, fa, fr
+
+
+def test_collide_cold_path_for_pairs_outside_the_admitted_ranges():
+    """The hot loop runs range-test-free sequences and only accumulates the test; robots with a pair
+    outside the admitted operand ranges (denormal-scale offsets, zero contact force, tiny distances)
+    are recomputed with the IEEE operators.  Results must carry the reference's bits either way."""
+    p, o = util.cfg("example")
+    rng = np.random.default_rng(11)
+    n = 600
+    p.nCells = n
+    pos, vel, rad = _random_swarm(p, n, rng, spread=3.0)
+    # denormal-scale x offsets between neighbours around the origin (offset components << 1e-12)
+    pos[0] = (1e-30, 0.05); pos[1] = (3e-30, -0.07); pos[2] = (-2e-33, 0.11)
+    # pairs a hair apart (dist^2 < 1e-20)
+    pos[3] = (1e-11, 0.3); pos[4] = (3e-11, 0.3)
+    # exact x alignment (offset exactly 0 is admitted) and an exactly touching, relatively resting pair
+    pos[5] = (1.0, 0.25); pos[6] = (1.0, 0.40); vel[5] = vel[6] = (0.01, 0.0)
+    rad[5] = rad[6] = np.float32(0.075)
+    _collide_vs_reference(p, o, pos.astype(np.float32), vel, rad)
+
+
+def test_collide_stale_table_self_slot_outside_own_stencil_row():
+    """Between sorts the table is stale (Q1): the robot's current cell can differ from the cell it is
+    filed under, so its own slot may sit in any stencil row range — or in none."""
+    p, o = util.cfg("example")
+    rng = np.random.default_rng(12)
+    n = 800
+    p.nCells = n
+    pos, vel, rad = _random_swarm(p, n, rng, spread=3.0)
+    shift = ((rng.random((n, 2), dtype=np.float32) - 0.5) * np.float32(1.6)).astype(np.float32)  # up to +-3.4 cells
+    _collide_vs_reference(p, o, pos, vel, rad, stale_shift=shift)
+
+
 @pytest.mark.parametrize("name", ["example", "example_object_transport"])
 def test_integrate_controller_phase_noise(name):
     p, o = util.cfg(name)
