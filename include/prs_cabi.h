@@ -110,6 +110,11 @@ void prs_centroid(const float *pos, int n, float *d_scratch, float *d_out);
 void prs_sort_pairs(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys,
                     unsigned *out_vals, unsigned n, int key_bits);
 
+/* tuning aid: per-tile phase stamps of the sort kernels (8 x uint64 nanoseconds per tile and pass) */
+void prs_sort_set_timeline(unsigned long long *device_buf);
+unsigned prs_sort_tile_size(void);
+void prs_sort_set_threads(int threads_per_tile); /* 512, 1024, or 0 = chosen by size (default) */
+
 /* Fused whole step on the reference's buffers (same observable results as the call sequence
  * updateRad_light_wave -> integrateSystem -> [calcHash, sortParticlebots] ->
  * reorderDataAndFindCellStart -> collide of particlebot.cpp:238-296):

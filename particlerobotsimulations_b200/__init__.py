@@ -101,6 +101,7 @@ SIGNATURES = {
     "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),
     "prs_centroid": (None, [_VP, _I, _VP, _VP]),
     "prs_sort_pairs": (None, [_VP, _VP, _VP, _VP, _U, _I]),
+    "prs_sort_set_timeline": (None, [_VP]), "prs_sort_tile_size": (_U, []), "prs_sort_set_threads": (None, [_I]),
     "prs_slab_k1": (None, [_VP] * 9 + [_F, _F, _U, _I]), "prs_slab_sort": (None, [_VP, _VP, _VP, _VP, _U, _I]),
     "prs_slab_gather": (None, [_VP] * 6 + [_U]), "prs_slab_cell_table": (None, [_VP, _VP, _VP, _U, _U, _U, _U]),
     "prs_slab_lower_bounds": (None, [_VP, _U, _VP, _U, _VP]),

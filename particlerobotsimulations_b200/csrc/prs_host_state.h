@@ -17,6 +17,8 @@ struct PrsHostState {
   float world_half = 64.0f;           /* reference wall (kernel_impl.cuh:75-97) */
   int collide_mode = 0;               /* 0 exact, 1 fast */
   prs_sort::Workspace sort_ws;
+  int sort_threads = 0;               /* tile shape of k_onesweep: 512 / 1024 threads, 0 = by size */
+  unsigned long long *sort_timeline = nullptr; /* tuning aid, see prs_sort_set_timeline */
   /* optional per-stage CUDA-event timing of the fused step (bench.py's roofline numbers) */
   bool stage_timing = false;
   std::vector<cudaEvent_t> ev_pool;

@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) k_update_col(const float *__restrict__ ra
 /* ------------------------------------------------------------------------------------------
  * sort driver
  * ------------------------------------------------------------------------------------------ */
-static void ensure_sort_workspace(uint32_t n, int npass) {
+static void ensure_sort_workspace(uint32_t n, int npass, int tile_pairs) {
   prs_sort::Workspace &w = g_prs.sort_ws;
   if (w.cap_pairs < n) {
     for (int b = 0; b < 2; b++) {
@@ -555,12 +555,26 @@ static void ensure_sort_workspace(uint32_t n, int npass) {
     }
     w.cap_pairs = n;
   }
-  const size_t need = prs_sort::meta_words(n, npass);
+  const size_t need = prs_sort::meta_words(n, npass, tile_pairs);
   if (w.cap_meta < need) {
     if (w.meta) PRS_CUDA(cudaFree(w.meta));
     PRS_CUDA(cudaMalloc(&w.meta, need * 4));
     w.cap_meta = need;
   }
+}
+
+template <int NT>
+static void launch_onesweep(unsigned tiles, const uint32_t *src_k, const uint32_t *src_v, uint32_t *dst_k, uint32_t *dst_v,
+                            uint32_t n, int shift, const uint32_t *ghist, uint32_t *status, uint32_t *counter,
+                            unsigned long long *timeline) {
+  static bool smem_opt_in = false;
+  if (!smem_opt_in) {
+    PRS_CUDA(cudaFuncSetAttribute(prs_sort::k_onesweep<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(prs_sort::Smem<NT>)));
+    smem_opt_in = true;
+  }
+  PRS_LAUNCH(prs_sort::k_onesweep<NT>, tiles, NT, sizeof(prs_sort::Smem<NT>), src_k, src_v, dst_k, dst_v, n, shift, ghist,
+             status, counter, timeline);
 }
 
 /* stable sort of n pairs by the low key_bits of the key; result in out_* (may alias in_*).
@@ -572,28 +586,32 @@ static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out
   if (key_bits < 1) key_bits = 1;
   if (key_bits > 32) key_bits = 32;
   const int npass = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
-  ensure_sort_workspace(n, npass);
+  /* tile shape: 1024 threads x 8 pairs while all tiles fit one wave (one per SM), else 512 x 8 with two
+   * tiles resident per SM; prs_sort_set_threads() pins one of them */
+  const int nt = g_prs.sort_threads ? g_prs.sort_threads : ((n <= 148u * 8192u) ? 1024 : 512);
+  const int tile_pairs = nt * ITEMS;
+  ensure_sort_workspace(n, npass, tile_pairs);
   Workspace &w = g_prs.sort_ws;
-  const uint32_t tiles = div_up(n, TILE);
+  const uint32_t tiles = div_up(n, tile_pairs);
   uint32_t *ghist = w.meta;
   uint32_t *counters = w.meta + MAX_PASSES * RADIX;
   uint32_t *status = counters + MAX_PASSES;
-  PRS_CUDA(cudaMemsetAsync(w.meta, 0, meta_words(n, npass) * 4, g_prs.stream));
+  PRS_CUDA(cudaMemsetAsync(w.meta, 0, meta_words(n, npass, tile_pairs) * 4, g_prs.stream));
   const unsigned hist_blocks = min(div_up(n, HIST_THREADS * 8), 148u * 8u);
   PRS_LAUNCH(k_histogram, hist_blocks, HIST_THREADS, 0, in_k, n, ghist, npass);
-  static bool smem_opt_in = false;
-  if (!smem_opt_in) {
-    PRS_CUDA(cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    smem_opt_in = true;
-  }
   const uint32_t *src_k = in_k, *src_v = vals_are_iota ? nullptr : in_v;
   for (int p = 0; p < npass; p++) {
     /* ping-pong through the two scratch pairs so that the LAST pass lands in out_* */
     uint32_t *dst_k, *dst_v;
     if (p == npass - 1) { dst_k = out_k; dst_v = out_v; }
     else { dst_k = w.keys[p & 1]; dst_v = w.vals[p & 1]; }
-    PRS_LAUNCH(k_onesweep, tiles, THREADS, sizeof(Smem), src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
-               status + (size_t)p * tiles * RADIX, counters + p);
+    unsigned long long *tl = g_prs.sort_timeline ? g_prs.sort_timeline + (size_t)p * tiles * 8 : nullptr;
+    if (nt == 512)
+      launch_onesweep<512>(tiles, src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
+                           status + (size_t)p * tiles * RADIX, counters + p, tl);
+    else
+      launch_onesweep<1024>(tiles, src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
+                            status + (size_t)p * tiles * RADIX, counters + p, tl);
     src_k = dst_k;
     src_v = dst_v;
   }
@@ -797,6 +815,13 @@ void prs_centroid(const float *pos, int n, float *d_scratch, float *d_out) {
   PRS_LAUNCH(k_centroid_partial, nb, 256, 0, (const float2 *)pos, (uint32_t)n, (double2 *)d_scratch);
   PRS_LAUNCH(k_centroid_final, 1, 1, 0, (const double2 *)d_scratch, nb, (uint32_t)n, d_out);
 }
+
+/* tuning aid: when set, the next sorts write 8 %globaltimer stamps per tile and pass into buf
+ * (device memory, passes * tiles * 8 words); nullptr switches it off */
+void prs_sort_set_timeline(unsigned long long *buf) { g_prs.sort_timeline = buf; }
+unsigned prs_sort_tile_size(void) { return (unsigned)((g_prs.sort_threads ? g_prs.sort_threads : 512) * prs_sort::ITEMS); }
+/* tile shape of the sort: 512 (several tiles per SM) or 1024 threads x 8 pairs */
+void prs_sort_set_threads(int nt) { g_prs.sort_threads = (nt == 1024) ? 1024 : (nt == 512 ? 512 : 0); }
 
 void prs_sort_pairs(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys, unsigned *out_vals,
                     unsigned n, int key_bits) {

@@ -8,12 +8,26 @@
  * ascending by 32-bit key, STABLE (equal keys keep their input order, i.e. ascending robot index
  * after calcHash).  Only ceil(key_bits/8) digits are processed: cell keys are < numCells.
  *
- * Per tile (512 threads x 8 keys): keys are ranked warp by warp with __match_any_sync (lanes
- * holding the same digit elect a leader that bumps a per-warp digit counter in shared memory),
- * per-warp counters are prefix-summed across warps by one thread per digit, the tile's digit
- * counts are published as AGGREGATE, the exclusive prefix over earlier tiles is fetched by
- * look-back (one thread per digit), the pairs are staged in shared memory in tile-sorted order
- * and written out in runs, so global stores are coalesced.
+ * Per tile (NT threads x 8 pairs; NT = 512 with several tiles resident per SM, or 1024):
+ *   1. keys AND values are requested up front (the values are not needed before step 5, but
+ *      their HBM latency would otherwise sit in the middle of the tile's critical path);
+ *   2. keys are ranked warp by warp: the lanes holding the same digit find each other through a
+ *      shared-memory word per (warp, digit) — atomicOr of the lane bit, read back — and the lowest
+ *      lane bumps the warp's digit counter (stable: ranks follow lane order, then item order);
+ *   3. per-warp counters are prefix-summed across warps, the tile's digit counts are published as
+ *      AGGREGATE words;
+ *   4. WIDE look-back: 32 or 64 predecessor words per digit are requested in one L2 round trip
+ *      (2 or 4 lanes per digit, 16 words each) ...
+ *   5. ... and while those loads are in flight the pairs are scattered into shared memory in
+ *      tile-sorted order; then the predecessors' words are consumed (run of published words up to
+ *      the first inclusive PREFIX; retry from the first unpublished one), the tile's PREFIX is
+ *      published;
+ *   6. the staged pairs are written out in digit runs, so global stores are coalesced.
+ *
+ * Tuning history (B200, %globaltimer stamps per phase, scripts/sort_timeline.py): MATCH.ANY and
+ * 8-ballot matching made step 2 the longest phase (MATCH serialises over the distinct values of
+ * a warp, ballots cost ~60 instructions per key); a 16-word look-back kept most in-flight tiles
+ * in the aggregate-only state, so every tile walked back through all of them.
  *
  * HBM bytes per pair: 4 (histogram sweep) + 16 per digit pass.
  */
@@ -23,12 +37,18 @@
 
 namespace prs_sort {
 
+/* optional per-tile phase stamps (nanoseconds, %globaltimer) for tuning: 8 words per tile */
+__device__ __forceinline__ void stamp(unsigned long long *timeline, uint32_t tile, int phase) {
+  if (timeline && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    timeline[(size_t)tile * 8 + phase] = t;
+  }
+}
+
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int THREADS = 512;
-constexpr int WARPS = THREADS / 32;
 constexpr int ITEMS = 8;
-constexpr int TILE = THREADS * ITEMS; /* 4096 pairs per tile, two tiles resident per SM: short per-warp dependency chains */
 constexpr int MAX_PASSES = 4;
 constexpr int HIST_THREADS = 256;
 
@@ -36,14 +56,29 @@ constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PREFIX = 2u << 30;
 constexpr uint32_t VALUE_MASK = (1u << 30) - 1;
 
-/* dynamic shared memory of k_onesweep */
+template <int NT>
+struct Cfg {
+  static constexpr int THREADS = NT;
+  static constexpr int WARPS = NT / 32;
+  static constexpr int TILE = NT * ITEMS;
+  static constexpr int GROUPS = NT / RADIX;            /* groups of 8 warps in the cross-warp prefix */
+  static constexpr int DIGITS_PER_WARP = RADIX / WARPS; /* look-back: digits owned by a warp */
+  static constexpr int LANES_PER_DIGIT = 32 / DIGITS_PER_WARP;
+  static_assert(WARPS / GROUPS == 8 && (NT == 512 || NT == 1024), "supported tile shapes");
+};
+
+/* dynamic shared memory of k_onesweep (NT = 512: 68 KB, NT = 1024: 133 KB) */
+template <int NT>
 struct __align__(16) Smem {
-  uint32_t cnt[WARPS][RADIX];   /* per-warp digit counters -> exclusive offsets across warps */
-  uint32_t tile_base[RADIX];    /* first slot of each digit inside the tile */
-  uint32_t gbase[RADIX];        /* output position of slot 0 of each digit minus its tile slot */
-  uint32_t keys[TILE];
-  uint32_t vals[TILE];
-  uint32_t warp_tot[WARPS];
+  uint32_t cnt[Cfg<NT>::WARPS][RADIX]; /* per-warp digit counters -> exclusive offsets across warps */
+  uint32_t part[Cfg<NT>::GROUPS][RADIX]; /* digit totals of each group of 8 warps */
+  uint32_t tile_base[RADIX];          /* first slot of each digit inside the tile */
+  uint32_t gbase[RADIX];              /* output position of slot 0 of each digit minus its tile slot */
+  uint32_t count[RADIX];              /* this tile's digit counts (padding removed) */
+  uint32_t mask[Cfg<NT>::WARPS][RADIX]; /* (warp, digit) match words of the ranking loop */
+  uint32_t keys[Cfg<NT>::TILE];       /* staging of the tile in sorted order */
+  uint32_t vals[Cfg<NT>::TILE];
+  uint32_t warp_tot[2][8];
   uint32_t tile;
 };
 
@@ -91,126 +126,219 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
   return inc - v;
 }
 
-/* exclusive scan over the block of one value per thread (threads >= RADIX pass 0) */
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp_tot) {
+/* exclusive scans over digits 0..255 of TWO values held by threads 0..255 (one set of barriers);
+ * every thread of the block must call it */
+__device__ __forceinline__ void excl_scan2_256(uint32_t &a, uint32_t &b, uint32_t (*s_tot)[8]) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t tot;
-  uint32_t ex = warp_excl_scan(v, lane, &tot);
-  if (lane == 0) s_warp_tot[warp] = tot;
+  uint32_t ta = 0, tb = 0, ea = 0, eb = 0;
+  if (warp < 8) {
+    ea = warp_excl_scan(a, lane, &ta);
+    eb = warp_excl_scan(b, lane, &tb);
+    if (lane == 0) { s_tot[0][warp] = ta; s_tot[1][warp] = tb; }
+  }
   __syncthreads();
-  uint32_t add = 0;
+  if (warp < 8) {
 #pragma unroll
-  for (int w = 0; w < WARPS; w++) add += (w < (int)warp) ? s_warp_tot[w] : 0u;
-  __syncthreads();
-  return ex + add;
+    for (int w = 0; w < 8; w++) {
+      ea += (w < (int)warp) ? s_tot[0][w] : 0u;
+      eb += (w < (int)warp) ? s_tot[1][w] : 0u;
+    }
+    a = ea;
+    b = eb;
+  }
 }
 
 /* One digit pass.  vin == nullptr means "values are the input positions" (first pass after
  * calcHash, where index[i] = i), which saves reading 4 B per pair. */
-__global__ void __launch_bounds__(THREADS, 2)
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT == 512) ? 2 : 1)
 k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
            uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ ghist,
-           volatile uint32_t *status, uint32_t *tile_counter) {
+           volatile uint32_t *status, uint32_t *tile_counter, unsigned long long *timeline) {
+  using C = Cfg<NT>;
+  constexpr int THREADS = C::THREADS, WARPS = C::WARPS, TILE = C::TILE, GROUPS = C::GROUPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+  Smem<NT> &S = *reinterpret_cast<Smem<NT> *>(smem_raw);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
-  for (int i = tid; i < WARPS * RADIX; i += THREADS) (&S.cnt[0][0])[i] = 0;
+  for (int i = tid; i < WARPS * RADIX; i += THREADS) { (&S.cnt[0][0])[i] = 0; (&S.mask[0][0])[i] = 0; }
+  const uint32_t gh = (tid < RADIX) ? ghist[tid] : 0u; /* requested now, needed in step 3 */
   __syncthreads();
   const uint32_t tile = S.tile;
+  stamp(timeline, tile, 0);
   const uint32_t tile_base = tile * (uint32_t)TILE;
   const uint32_t tile_valid = min((uint32_t)TILE, n - tile_base);
   const uint32_t wbase = tile_base + warp * (ITEMS * 32);
 
-  uint32_t key[ITEMS];
-  uint16_t rank[ITEMS];
+  /* 1. keys and values */
+  uint32_t key[ITEMS], val[ITEMS];
 #pragma unroll
   for (int t = 0; t < ITEMS; t++) {
     const uint32_t i = wbase + t * 32 + lane;
     key[t] = (i < n) ? kin[i] : 0xffffffffu; /* padding sorts to the very end of the tile */
   }
-  /* stable ranks inside the warp's 512 keys: lanes holding the same digit are found with
-   * match_any (one vote when the whole warp agrees), their leader bumps the warp's counter */
-  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int t = 0; t < ITEMS; t++) {
+    const uint32_t i = wbase + t * 32 + lane;
+    val[t] = (i < n) ? (vin ? vin[i] : i) : 0u;
+  }
+
+  /* 2. EARLY COUNTS: per-warp digit counts with plain shared-memory atomics (order is irrelevant
+   * for counting), so that the tile's aggregate can be published long before the stable ranking
+   * is done — by the time the successors look back, it is there. */
 #pragma unroll
   for (int t = 0; t < ITEMS; t++) {
     const uint32_t d = (key[t] >> shift) & (RADIX - 1);
     const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
-    uint32_t m = 0xffffffffu;
-    if (!__all_sync(0xffffffffu, d == d0)) m = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(m) - 1;
-    uint32_t prev = 0;
-    if ((int)lane == leader) {
-      prev = S.cnt[warp][d];
-      S.cnt[warp][d] = prev + __popc(m);
+    if (__all_sync(0xffffffffu, d == d0)) {
+      if (lane == 0) S.cnt[warp][d] += 32u; /* only this warp touches its counters */
+    } else {
+      atomicAdd(&S.cnt[warp][d], 1u);
     }
-    prev = __shfl_sync(0xffffffffu, prev, leader);
-    rank[t] = (uint16_t)(prev + __popc(m & lt_mask));
     __syncwarp();
   }
   __syncthreads();
+  stamp(timeline, tile, 1);
 
-  /* thread d < 256 owns digit d: warp counts -> exclusive offsets across warps */
-  uint32_t total = 0, count = 0;
-  if (tid < RADIX) {
+  /* 3. warp counts -> exclusive offsets across the warps: thread (digit, group of 8 warps) */
+  const uint32_t dg = tid & (RADIX - 1), grp = tid >> RADIX_BITS;
+  {
+    uint32_t c[8], run = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; w++) {
-      const uint32_t cw = S.cnt[w][tid];
-      S.cnt[w][tid] = total;
-      total += cw;
+    for (int w = 0; w < 8; w++) c[w] = S.cnt[grp * 8 + w][dg];
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t cw = c[w]; c[w] = run; run += cw; }
+    S.part[grp][dg] = run;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int g = 0; g < GROUPS; g++) {
+      const uint32_t pg = S.part[g][dg];
+      before += (g < (int)grp) ? pg : 0u;
+      total += pg;
     }
-    count = total;
-    if (tid == RADIX - 1) count -= (uint32_t)TILE - tile_valid; /* padding is not data */
-    if (tile != 0) status[(size_t)tile * RADIX + tid] = count | FLAG_AGG;
+    uint32_t tbase = 0, gex = 0;
+    if (grp == 0) {
+      uint32_t count = total;
+      if (dg == RADIX - 1) count -= (uint32_t)TILE - tile_valid; /* padding is not data */
+      S.count[dg] = count;
+      if (tile != 0) status[(size_t)tile * RADIX + dg] = count | FLAG_AGG;
+      tbase = total;
+      gex = gh;
+    }
+    excl_scan2_256(tbase, gex, S.warp_tot); /* digit start inside the tile / in the output */
+    if (tid < RADIX) {
+      S.tile_base[tid] = tbase;
+      S.gbase[tid] = gex - tbase;
+    }
+    __syncthreads();
+    /* cnt[w][d] becomes the first staging slot of warp w's keys with digit d */
+    const uint32_t off = S.tile_base[dg] + before;
+#pragma unroll
+    for (int w = 0; w < 8; w++) S.cnt[grp * 8 + w][dg] = off + c[w];
   }
-  const uint32_t tbase = block_excl_scan(total, S.warp_tot);                               /* digit start inside the tile */
-  const uint32_t gex = block_excl_scan(tid < RADIX ? ghist[tid] : 0u, S.warp_tot);         /* digit start in the output */
+  __syncthreads();
+  stamp(timeline, tile, 2);
 
-  /* Look-back, one thread per digit.  Up to a few hundred tiles are resident at once and finish
-   * ranking together, so the walk back to the nearest published PREFIX is long; the
-   * predecessors' words are therefore fetched LOOKBACK at a time (independent volatile loads in
-   * flight together) and consumed in order, stopping at the first word not published yet. */
-  if (tid < RADIX) {
-    constexpr int LOOKBACK = 16;
-    uint32_t excl = 0;
-    if (tile != 0) {
-      int64_t t = (int64_t)tile - 1;
-      bool done = false;
-      while (!done) {
-        uint32_t v[LOOKBACK];
+  /* 4. wide look-back, first trip requested here.  Warp w owns DIGITS_PER_WARP digits; lane =
+   * (digit, part): part q fetches the 16 predecessors t-16q .. t-16q-15 of its digit. */
+  constexpr int B = 16;
+  constexpr int LPD = C::LANES_PER_DIGIT, DPW = C::DIGITS_PER_WARP;
+  const uint32_t ld = warp * DPW + (lane & (DPW - 1)), lq = lane / DPW;
+  uint32_t excl = 0;
+  bool done = (tile == 0);
+  int64_t t_next = (int64_t)tile - 1;
+  uint32_t v[B];
+  auto request = [&]() {
+    const int64_t first = t_next - (int64_t)(B * lq);
 #pragma unroll
-        for (int i = 0; i < LOOKBACK; i++) {
-          const int64_t tt = t - i;
-          v[i] = (tt >= 0) ? status[(size_t)tt * RADIX + tid] : (uint32_t)(2u << 30); /* before tile 0: PREFIX 0 */
-        }
-        int used = 0;
+    for (int i = 0; i < B; i++) {
+      const int64_t tt = first - i;
+      v[i] = (!done && tt >= 0) ? (uint32_t)status[(size_t)tt * RADIX + ld] : (uint32_t)(2u << 30); /* before tile 0: PREFIX 0 */
+    }
+  };
+  request();
+
+  /* 5. stable ranking straight into the staging area, while the predecessors' words are in
+   * flight.  The lanes holding the same digit find each other through a shared-memory word per
+   * (warp, digit): every lane ORs its lane bit in and reads the word back; the lowest lane (the
+   * leader) clears it and advances the warp's slot cursor of that digit.  A warp whose 32 keys
+   * share the digit — the common case for the high digits of cell keys — skips the exchange. */
+  {
+    const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-        for (int i = 0; i < LOOKBACK; i++) {
-          const uint32_t f = v[i] & ~VALUE_MASK;
-          if (done || used != i || f == 0) continue; /* consume strictly in order */
-          excl += v[i] & VALUE_MASK;
-          used = i + 1;
-          if (f == (uint32_t)(2u << 30)) done = true;
+    for (int t = 0; t < ITEMS; t++) {
+      const uint32_t d = (key[t] >> shift) & (RADIX - 1);
+      const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+      uint32_t m = 0xffffffffu;
+      if (!__all_sync(0xffffffffu, d == d0)) {
+        atomicOr(&S.mask[warp][d], 1u << lane);
+        __syncwarp();
+        m = *reinterpret_cast<volatile uint32_t *>(&S.mask[warp][d]);
+        __syncwarp();
+      }
+      const int leader = __ffs(m) - 1;
+      uint32_t slot = 0;
+      if ((int)lane == leader) {
+        S.mask[warp][d] = 0;
+        slot = S.cnt[warp][d];
+        S.cnt[warp][d] = slot + __popc(m);
+      }
+      slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(m & lt_mask);
+      S.keys[slot] = key[t];
+      S.vals[slot] = val[t];
+      __syncwarp();
+    }
+  }
+  stamp(timeline, tile, 3);
+
+  while (true) {
+    uint32_t sum = 0, used = 0, st = 0; /* st: 0 ran through, 1 hit a PREFIX, 2 hit an unpublished word */
+    uint32_t all_and = v[0], all_or = v[0];
+#pragma unroll
+    for (int i = 1; i < B; i++) { all_and &= v[i]; all_or |= v[i]; }
+    if ((all_and >> 30) == 1u && (all_or >> 30) == 1u) { /* 16 aggregates: the common case */
+#pragma unroll
+      for (int i = 0; i < B; i++) sum += v[i];
+      sum -= (uint32_t)B << 30;
+      used = B;
+    } else {
+#pragma unroll
+      for (int i = 0; i < B; i++) {
+        const uint32_t f = v[i] >> 30;
+        if (st == 0) {
+          if (f == 0) st = 2;
+          else { sum += v[i] & VALUE_MASK; used++; if (f == 2) st = 1; }
         }
-        t -= used;
       }
     }
-    status[(size_t)tile * RADIX + tid] = (excl + count) | FLAG_PREFIX;
-    S.tile_base[tid] = tbase;
-    S.gbase[tid] = gex + excl - tbase;
-  }
-  __syncthreads();
-
+    /* stitch the parts of each digit together in order */
+    const uint32_t packed = used | (st << 8);
+    uint32_t tot = 0, adv = 0, fin = 0;
 #pragma unroll
-  for (int t = 0; t < ITEMS; t++) {
-    const uint32_t d = (key[t] >> shift) & (RADIX - 1);
-    const uint32_t p = S.tile_base[d] + S.cnt[warp][d] + rank[t];
-    const uint32_t i = wbase + t * 32 + lane;
-    S.keys[p] = key[t];
-    S.vals[p] = (i < n) ? (vin ? vin[i] : i) : 0u;
+    for (int q = 0; q < LPD; q++) {
+      const uint32_t sq = __shfl_sync(0xffffffffu, sum, (lane & (DPW - 1)) + DPW * q);
+      const uint32_t pq = __shfl_sync(0xffffffffu, packed, (lane & (DPW - 1)) + DPW * q);
+      if (fin == 0) { tot += sq; adv += pq & 0xffu; fin = pq >> 8; }
+    }
+    if (!done) {
+      excl += tot;
+      t_next -= adv;
+      if (fin == 1) done = true;
+    }
+    if (!__any_sync(0xffffffffu, !done)) break;
+    request();
   }
+  if (lq == 0) {
+    status[(size_t)tile * RADIX + ld] = (excl + S.count[ld]) | FLAG_PREFIX;
+    S.gbase[ld] += excl;
+  }
+  stamp(timeline, tile, 4);
   __syncthreads();
+  stamp(timeline, tile, 5);
+
+  /* 6. write out in digit runs */
   for (uint32_t j = tid; j < tile_valid; j += THREADS) {
     const uint32_t k = S.keys[j];
     const uint32_t d = (k >> shift) & (RADIX - 1);
@@ -218,6 +346,7 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
     kout[o] = k;
     vout[o] = S.vals[j];
   }
+  stamp(timeline, tile, 6);
 }
 
 /* Persistent scratch of the sort: ping-pong pair buffers, histograms, tile status.  Grown on
@@ -229,8 +358,8 @@ struct Workspace {
   size_t cap_pairs = 0, cap_meta = 0;
 };
 
-inline size_t meta_words(uint32_t n, int npass) {
-  const size_t tiles = (n + TILE - 1) / TILE;
+inline size_t meta_words(uint32_t n, int npass, int tile_pairs) {
+  const size_t tiles = (n + tile_pairs - 1) / tile_pairs;
   return (size_t)MAX_PASSES * RADIX + MAX_PASSES + (size_t)npass * tiles * RADIX;
 }
 
