@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 PITCH = 0.17   # BASELINE.md S1 says 0.155 (= 2*min_radius): that crystal is numerically unstable in the reference's DEM model
 JITTER_FRAC = 0.01
 SEED = 5555
-STAGES = ["controller+integrate+hash", "sort", "reorder+celltable", "collide", "phase"]
+STAGES = ["controller+integrate+hash", "sort", "reorder+celltable", "collide", "phase", "exchange"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -71,7 +71,7 @@ def algorithmic_bytes(p, sort_every_step=True):
     bits = int(np.ceil(np.log2(p.numCells)))
     passes = (bits + 7) // 8
     per = {"controller+integrate+hash": 60 if sort_every_step else 52, "sort": 4 + 16 * passes if sort_every_step else 0,
-           "reorder+celltable": 51 + 4.0 * p.numCells / p.nCells, "collide": 43, "phase": 0}
+           "reorder+celltable": 51 + 4.0 * p.numCells / p.nCells, "collide": 43, "phase": 0, "exchange": 0}
     return per, sum(per.values()), passes
 
 
@@ -304,8 +304,8 @@ def run_gpu(args):
         for _ in range(args.steps):
             flush.fill_(1)
             step()
-        ms = (C.c_float * 5)()
-        cnt = (C.c_uint * 5)()
+        ms = (C.c_float * 6)()
+        cnt = (C.c_uint * 6)()
         lib.prs_stage_times(ms, cnt)
         lib.prs_stage_timing(0)
         stages = {}

@@ -131,24 +131,59 @@ typedef struct {
 } prs_step_buffers;
 void prs_fused_step(const prs_step_buffers *b, float time, float deltaTime, int do_sort);
 
-/* ---- slab (multi-GPU) building blocks: the fused step cut where ranks exchange robots ----
- * (particlerobotsimulations_b200/multigpu.py drives them; DESIGN.md "multi-GPU") */
-void prs_slab_k1(float *pos, float *vel, float *rad, const float *phase, const float *absForce_a,
-                 const float *absForce_r, const int *dead, unsigned *hash, unsigned *index, float time, float dt,
-                 unsigned n, int do_hash);
-void prs_slab_sort(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys, unsigned *out_vals,
-                   unsigned n, int vals_are_iota);
-void prs_slab_gather(float *sortedPR, float *sortedVel, const unsigned *index, const float *pos, const float *vel,
-                     const float *rad, unsigned n);
-void prs_slab_cell_table(unsigned *cellStart, unsigned *cellEnd, const unsigned *hash, unsigned n, unsigned slot0,
-                         unsigned cell_lo, unsigned ncells);
-void prs_slab_lower_bounds(const unsigned *hash, unsigned n, const unsigned *d_bounds, unsigned nb, unsigned *d_out);
-void prs_slab_collide(float *newVel, float *absForce_a, float *absForce_r, const float *sortedPR,
-                      const float *sortedVel, const unsigned *cellStart, const unsigned *cellEnd, unsigned k_begin,
-                      unsigned k_end, float dt);
-/* orders the robots of each cell by global id (ties of the local sort are by local slot) */
-void prs_slab_fix_ties(const unsigned *hash_sorted, unsigned *index_sorted, const unsigned *gid, unsigned n);
-void prs_curand_setup_ids(struct curandStateXORWOW *state, const unsigned *gid, unsigned n);
+/* ---- slab (multi-GPU) engine: the fused step cut where ranks exchange robots, every count kept
+ * on the device (csrc/prs_slab.cuh; particlerobotsimulations_b200/multigpu.py drives it;
+ * DESIGN.md "multi-GPU").  A rank owns grid rows [row_lo, row_hi). ---- */
+enum { /* words of prs_slab.counts (device uint32[16]) */
+  PRS_SC_N = 0,        /* robots owned (local slots [0, n)) */
+  PRS_SC_NLO = 1, PRS_SC_NHI = 2,     /* halo robots received from the lower / upper neighbour */
+  PRS_SC_KDN = 3, PRS_SC_KUP = 4,     /* halo robots sent down / up */
+  PRS_SC_MIGDN = 5, PRS_SC_MIGUP = 6, /* robots migrating down / up this step */
+  PRS_SC_LEAVERS = 7, PRS_SC_HOLES = 8, PRS_SC_KEEPERS = 9, /* compaction scratch */
+  PRS_SC_ERR = 10,     /* sticky error bits, PRS_SLAB_ERR_* */
+  PRS_SC_STAT_MIG = 11, PRS_SC_STAT_HALO = 12 /* running totals */
+};
+enum {
+  PRS_SLAB_ERR_MIG_CAP = 1,    /* more migrants than mig_cap in one step */
+  PRS_SLAB_ERR_HALO_CAP = 2,   /* a halo longer than halo_cap */
+  PRS_SLAB_ERR_CAPACITY = 4,   /* more robots than cap */
+  PRS_SLAB_ERR_TWO_SLABS = 8,  /* a robot crossed more than one slab between two sorts */
+  PRS_SLAB_ERR_LEFT_WORLD = 16 /* a robot left the rows of the first / last slab (hash wrap-around) */
+};
+typedef struct {
+  /* owned robots, local slots [0, cap) */
+  float *pos, *vel, *rad, *phase, *absForce_a, *absForce_r;
+  int *dead;
+  unsigned *gid;       /* global robot id (original index of the single-GPU run) */
+  void *rng;           /* curandStateXORWOW[cap], seeded by global id */
+  unsigned *hash;      /* cell key per local slot */
+  unsigned *scratch;   /* uint32[cap] */
+  /* sorted view, [halo_cap | cap | halo_cap] slots: lower halo ends at halo_cap, owned start there */
+  float *sortedPR, *sortedVel;
+  unsigned *hash_cat, *index_sorted;
+  unsigned *cellStart, *cellEnd;    /* whole-grid tables (only this rank's rows are used) */
+  unsigned *counts;    /* device uint32[16], PRS_SC_* */
+  unsigned *lists;     /* device uint32[6 * mig_cap] */
+  unsigned cap, halo_cap, mig_cap;
+  unsigned row_lo, row_hi, halo_rows;
+  int has_dn, has_up;  /* neighbours below (rank - 1) / above (rank + 1) exist */
+} prs_slab;
+/* exchange buffers are uint32 arrays: word 0 = record count, then structure-of-arrays records */
+size_t prs_slab_mig_words(unsigned mig_cap);
+size_t prs_slab_halo_words(unsigned halo_cap);
+void prs_slab_rng_setup(const prs_slab *s, unsigned n);
+void prs_slab_k1(const prs_slab *s, float time, float dt, int do_hash);
+void prs_slab_migrate_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up);
+void prs_slab_migrate_unpack(const prs_slab *s, const unsigned *recv_dn, const unsigned *recv_up);
+void prs_slab_sort(const prs_slab *s);
+void prs_slab_gather(const prs_slab *s);
+void prs_slab_halo_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up);
+void prs_slab_halo_unpack(const prs_slab *s, const unsigned *recv_dn, const unsigned *recv_up);
+void prs_slab_cell_table(const prs_slab *s);
+void prs_slab_collide(const prs_slab *s, float dt);
+void prs_slab_min_light_distance(const prs_slab *s, float *d_min_d);
+void prs_slab_update_phase(const prs_slab *s, float spacing, const float *d_min_d);
+void prs_slab_add_noise(const prs_slab *s, float std);
 
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n);
 /* self-test: number of operand pairs for which the shared-reciprocal division used by collide

@@ -71,6 +71,22 @@ class StepBuffers(C.Structure):
         "sortedPos", "sortedVel", "sortedRad")] + [("nCells", C.c_uint), ("numCells", C.c_uint), ("sortedPR", C.c_void_p)]
 
 
+class Slab(C.Structure):
+    """Mirror of prs_slab (include/prs_cabi.h): one rank's slab of the swarm, device pointers."""
+
+    _fields_ = [(n, C.c_void_p) for n in (
+        "pos", "vel", "rad", "phase", "absForce_a", "absForce_r", "dead", "gid", "rng", "hash", "scratch",
+        "sortedPR", "sortedVel", "hash_cat", "index_sorted", "cellStart", "cellEnd", "counts", "lists")] + [
+        (n, C.c_uint) for n in ("cap", "halo_cap", "mig_cap", "row_lo", "row_hi", "halo_rows")] + [
+        ("has_dn", C.c_int), ("has_up", C.c_int)]
+
+
+# words of Slab.counts (PRS_SC_*) and error bits (PRS_SLAB_ERR_*)
+SC_N, SC_NLO, SC_NHI, SC_KDN, SC_KUP, SC_MIGDN, SC_MIGUP, SC_LEAVERS, SC_HOLES, SC_KEEPERS, SC_ERR, SC_STAT_MIG, SC_STAT_HALO = range(13)
+SLAB_ERRORS = {1: "more migrants than mig_cap in one step", 2: "a halo longer than halo_cap", 4: "more robots than the slab capacity",
+               8: "a robot crossed more than one slab between two sorts", 16: "a robot left the grid rows of the outermost slab"}
+SLAB_MIG_WORDS, SLAB_HALO_WORDS = 23, 7
+
 _lib = None
 
 # name -> (restype, argtypes); the reference's entry points first (include/prs_cabi.h part 1)
@@ -102,11 +118,14 @@ SIGNATURES = {
     "prs_centroid": (None, [_VP, _I, _VP, _VP]),
     "prs_sort_pairs": (None, [_VP, _VP, _VP, _VP, _U, _I]),
     "prs_sort_set_timeline": (None, [_VP]), "prs_sort_tile_size": (_U, []), "prs_sort_set_threads": (None, [_I]),
-    "prs_slab_k1": (None, [_VP] * 9 + [_F, _F, _U, _I]), "prs_slab_sort": (None, [_VP, _VP, _VP, _VP, _U, _I]),
-    "prs_slab_gather": (None, [_VP] * 6 + [_U]), "prs_slab_cell_table": (None, [_VP, _VP, _VP, _U, _U, _U, _U]),
-    "prs_slab_lower_bounds": (None, [_VP, _U, _VP, _U, _VP]),
-    "prs_slab_collide": (None, [_VP] * 7 + [_U, _U, _F]), "prs_curand_setup_ids": (None, [_VP, _VP, _U]),
-    "prs_slab_fix_ties": (None, [_VP, _VP, _VP, _U]),
+    "prs_slab_mig_words": (C.c_size_t, [_U]), "prs_slab_halo_words": (C.c_size_t, [_U]),
+    "prs_slab_rng_setup": (None, [_VP, _U]), "prs_slab_k1": (None, [_VP, _F, _F, _I]),
+    "prs_slab_migrate_pack": (None, [_VP, _VP, _VP]), "prs_slab_migrate_unpack": (None, [_VP, _VP, _VP]),
+    "prs_slab_sort": (None, [_VP]), "prs_slab_gather": (None, [_VP]),
+    "prs_slab_halo_pack": (None, [_VP, _VP, _VP]), "prs_slab_halo_unpack": (None, [_VP, _VP, _VP]),
+    "prs_slab_cell_table": (None, [_VP]), "prs_slab_collide": (None, [_VP, _F]),
+    "prs_slab_min_light_distance": (None, [_VP, _VP]), "prs_slab_update_phase": (None, [_VP, _F, _VP]),
+    "prs_slab_add_noise": (None, [_VP, _F]),
     "prs_unpack_sorted": (None, [_VP, _VP, _VP, _U]), "prs_selftest_div": (C.c_ulonglong, [_VP, _VP, _U]),
     "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
     "prs_params_defaults": (None, [C.POINTER(SimParams), C.POINTER(RunOptions)]),

@@ -26,7 +26,7 @@ struct PrsHostState {
   struct StageSpan { int stage; cudaEvent_t a, b; };
   std::vector<StageSpan> spans;
 };
-enum { PRS_STAGE_K1 = 0, PRS_STAGE_SORT = 1, PRS_STAGE_REORDER = 2, PRS_STAGE_COLLIDE = 3, PRS_STAGE_PHASE = 4, PRS_NUM_STAGES = 5 };
+enum { PRS_STAGE_K1 = 0, PRS_STAGE_SORT = 1, PRS_STAGE_REORDER = 2, PRS_STAGE_COLLIDE = 3, PRS_STAGE_PHASE = 4, PRS_STAGE_EXCHANGE = 5, PRS_NUM_STAGES = 6 };
 extern PrsHostState g_prs;
 
 void prs_fail(const char *what, cudaError_t e, const char *file, int line);

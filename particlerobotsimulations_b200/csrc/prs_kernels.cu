@@ -140,73 +140,6 @@ k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEn
   sortedPR[k] = make_float4(p.x, p.y, r, __uint_as_float(src));
   sortedVel[k] = v;
 }
-/* Slab (multi-GPU) variants: the gather and the cell table are separate because the table is
- * built over [lower halo | owned | upper halo] once the neighbours' rows have arrived.
- * slot_of: what goes into pr.w for owned robots (their local slot, the scatter target). */
-__global__ void __launch_bounds__(256)
-k_gather_packed(float4 *__restrict__ sortedPR, float2 *__restrict__ sortedVel, const uint32_t *__restrict__ index,
-                const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad, uint32_t n) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t src = index[k];
-  const float2 p = pos[src];
-  sortedPR[k] = make_float4(p.x, p.y, rad[src], __uint_as_float(src));
-  sortedVel[k] = vel[src];
-}
-/* cellStart/cellEnd over a sorted key array whose slot numbering starts at `slot0` */
-__global__ void __launch_bounds__(256)
-k_cell_table(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, const uint32_t *__restrict__ hash,
-             uint32_t n, uint32_t slot0) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t h = hash[k];
-  const uint32_t hp = (k > 0) ? hash[k - 1] : 0u;
-  if (k == 0 || h != hp) {
-    cellStart[h] = slot0 + k;
-    if (k > 0) cellEnd[hp] = slot0 + k;
-  }
-  if (k == n - 1) cellEnd[h] = slot0 + k + 1;
-}
-/* first slot whose key is >= bound[i] (binary search; used to cut halo rows out of the sorted keys) */
-__global__ void k_lower_bounds(const uint32_t *__restrict__ hash, uint32_t n, const uint32_t *__restrict__ bounds,
-                               uint32_t nb, uint32_t *__restrict__ out) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nb) return;
-  const uint32_t key = bounds[i];
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (hash[mid] < key) lo = mid + 1; else hi = mid;
-  }
-  out[i] = lo;
-}
-/* Slab ranks hold their robots in arbitrary local slots, but the reference's stable sort leaves the
- * robots of one cell in ascending ORIGINAL index.  After the local sort (ties by local slot) the
- * thread at each cell start insertion-sorts that cell's few entries by global id, so forces are
- * summed in exactly the single-GPU order (bit-equal results across any number of slabs). */
-__global__ void __launch_bounds__(256)
-k_fix_ties_by_gid(const uint32_t *__restrict__ hash, uint32_t *__restrict__ index, const uint32_t *__restrict__ gid, uint32_t n) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t h = hash[k];
-  if (k > 0 && hash[k - 1] == h) return; /* not a cell start */
-  uint32_t e = k + 1;
-  while (e < n && hash[e] == h) e++;
-  for (uint32_t a = k + 1; a < e; a++) {
-    const uint32_t slot = index[a];
-    const uint32_t g = gid[slot];
-    uint32_t b = a;
-    while (b > k && gid[index[b - 1]] > g) { index[b] = index[b - 1]; b--; }
-    index[b] = slot;
-  }
-}
-/* XORWOW states for robots that carry GLOBAL ids (slab ranks): subsequence = global id, so every
- * robot's noise stream is the one the single-GPU run (and the reference) gives it */
-__global__ void __launch_bounds__(256) k_curand_setup_ids(curandState *__restrict__ st, const uint32_t *__restrict__ gid, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) curand_init(c_prm.p.seed, gid[i], 0, &st[i]);
-}
-
 /* packed -> the reference's sortedPos / sortedRad arrays (only when a caller asks for them) */
 __global__ void __launch_bounds__(256) k_unpack_sorted(const float4 *__restrict__ pr, float2 *__restrict__ sortedPos,
                                                        float *__restrict__ sortedRad, uint32_t n) {
@@ -315,8 +248,9 @@ __global__ void __launch_bounds__(256)
 k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, float *__restrict__ rad,
                          const float *__restrict__ phase, const float *__restrict__ fa, const float *__restrict__ fr,
                          const int *__restrict__ dead, uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
-                         float time, float dt, int run_controller, uint32_t n) {
+                         float time, float dt, int run_controller, uint32_t n, const uint32_t *__restrict__ n_dev) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
   if (i >= n) return;
   float2 p = pos[i];
   float2 v = vel[i];
@@ -389,8 +323,9 @@ __device__ int in_shadow(float px, float py) {
  * device memory (d_min_d != nullptr) */
 __global__ void __launch_bounds__(256) k_update_phase(const float2 *__restrict__ pos, float *__restrict__ phase,
                                                       float spacing, float min_d_host, const float *__restrict__ d_min_d,
-                                                      uint32_t n) {
+                                                      uint32_t n, const uint32_t *__restrict__ n_dev) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
   if (i >= n) return;
   const float min_d = d_min_d ? d_min_d[0] : min_d_host;
   const float2 p = pos[i];
@@ -411,7 +346,8 @@ __global__ void __launch_bounds__(256) k_update_phase(const float2 *__restrict__
  * (particlebot.cpp:214-228); the _rn intrinsics below evaluate the same correctly rounded
  * square / sum / square root (no FMA), and positive floats order like their bit patterns. */
 __global__ void __launch_bounds__(256) k_min_light_distance(const float2 *__restrict__ pos, uint32_t n,
-                                                            uint32_t *__restrict__ out_bits) {
+                                                            uint32_t *__restrict__ out_bits, const uint32_t *__restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   float m = __int_as_float(0x7f7f7f7f);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float2 p = pos[i];
@@ -431,8 +367,9 @@ __global__ void __launch_bounds__(256) k_curand_setup(curandState *__restrict__ 
   if (i < n) curand_init(c_prm.p.seed, i, 0, &st[i]);
 }
 __global__ void __launch_bounds__(256) k_add_normal_noise(curandState *__restrict__ st, float *__restrict__ val,
-                                                          float std, uint32_t n) {
+                                                          float std, uint32_t n, const uint32_t *__restrict__ n_dev) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
   if (i >= n) return;
   const float noise = std * curand_normal(st + i);
   val[i] += noise;
@@ -566,7 +503,7 @@ static void ensure_sort_workspace(uint32_t n, int npass, int tile_pairs) {
 template <int NT>
 static void launch_onesweep(unsigned tiles, const uint32_t *src_k, const uint32_t *src_v, uint32_t *dst_k, uint32_t *dst_v,
                             uint32_t n, int shift, const uint32_t *ghist, uint32_t *status, uint32_t *counter,
-                            unsigned long long *timeline) {
+                            unsigned long long *timeline, const uint32_t *n_dev) {
   static bool smem_opt_in = false;
   if (!smem_opt_in) {
     PRS_CUDA(cudaFuncSetAttribute(prs_sort::k_onesweep<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -574,13 +511,15 @@ static void launch_onesweep(unsigned tiles, const uint32_t *src_k, const uint32_
     smem_opt_in = true;
   }
   PRS_LAUNCH(prs_sort::k_onesweep<NT>, tiles, NT, sizeof(prs_sort::Smem<NT>), src_k, src_v, dst_k, dst_v, n, shift, ghist,
-             status, counter, timeline);
+             status, counter, timeline, n_dev);
 }
 
 /* stable sort of n pairs by the low key_bits of the key; result in out_* (may alias in_*).
  * vals_are_iota: in_vals[i] == i is known (skips reading them in the first pass). */
 static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out_k, uint32_t *out_v, uint32_t n,
-                       int key_bits, bool vals_are_iota) {
+                       int key_bits, bool vals_are_iota, const uint32_t *n_dev = nullptr) {
+  /* n_dev != nullptr: the pair count lives on the device (slab ranks), n is its upper bound —
+   * grids and scratch are sized for n, tiles past the real count exit at once */
   using namespace prs_sort;
   if (n == 0) return;
   if (key_bits < 1) key_bits = 1;
@@ -598,7 +537,7 @@ static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out
   uint32_t *status = counters + MAX_PASSES;
   PRS_CUDA(cudaMemsetAsync(w.meta, 0, meta_words(n, npass, tile_pairs) * 4, g_prs.stream));
   const unsigned hist_blocks = min(div_up(n, HIST_THREADS * 8), 148u * 8u);
-  PRS_LAUNCH(k_histogram, hist_blocks, HIST_THREADS, 0, in_k, n, ghist, npass);
+  PRS_LAUNCH(k_histogram, hist_blocks, HIST_THREADS, 0, in_k, n, ghist, npass, n_dev);
   const uint32_t *src_k = in_k, *src_v = vals_are_iota ? nullptr : in_v;
   for (int p = 0; p < npass; p++) {
     /* ping-pong through the two scratch pairs so that the LAST pass lands in out_* */
@@ -608,10 +547,10 @@ static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out
     unsigned long long *tl = g_prs.sort_timeline ? g_prs.sort_timeline + (size_t)p * tiles * 8 : nullptr;
     if (nt == 512)
       launch_onesweep<512>(tiles, src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
-                           status + (size_t)p * tiles * RADIX, counters + p, tl);
+                           status + (size_t)p * tiles * RADIX, counters + p, tl, n_dev);
     else
       launch_onesweep<1024>(tiles, src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
-                            status + (size_t)p * tiles * RADIX, counters + p, tl);
+                            status + (size_t)p * tiles * RADIX, counters + p, tl, n_dev);
     src_k = dst_k;
     src_v = dst_v;
   }
@@ -732,7 +671,7 @@ void updateRad_light_wave(float * /*pos*/, float *absForce_a, float *absForce_r,
 void updatePhase(float *pos, float *phase, float spacing, float /*max_d*/, float min_d, int nCells) {
   if (nCells <= 0) return;
   PRS_LAUNCH(k_update_phase, div_up(nCells, 256), 256, 0, (const float2 *)pos, phase, spacing, min_d,
-             (const float *)nullptr, (uint32_t)nCells);
+             (const float *)nullptr, (uint32_t)nCells, (const uint32_t *)nullptr);
 }
 
 void curand_setup(struct curandStateXORWOW *state, int N) {
@@ -741,7 +680,7 @@ void curand_setup(struct curandStateXORWOW *state, int N) {
 }
 void add_normal_noise(struct curandStateXORWOW *state, float *val, float std, int N) {
   if (N <= 0) return;
-  PRS_LAUNCH(k_add_normal_noise, div_up(N, 256), 256, 0, (curandState *)state, val, std, (uint32_t)N);
+  PRS_LAUNCH(k_add_normal_noise, div_up(N, 256), 256, 0, (curandState *)state, val, std, (uint32_t)N, (const uint32_t *)nullptr);
 }
 
 void calcCOG(float *pos, float *temppos, float *temppos1, int nCells, float time, int hist_steps, float hist_int) {
@@ -803,11 +742,11 @@ void prs_min_light_distance(const float *pos, int n, float *d_min_d) {
   PRS_CUDA(cudaMemsetAsync(d_min_d, 0x7f, sizeof(float), g_prs.stream));
   if (n <= 0) return;
   const unsigned blocks = min(div_up((unsigned)n, 256 * 4), 148u * 8u);
-  PRS_LAUNCH(k_min_light_distance, blocks, 256, 0, (const float2 *)pos, (uint32_t)n, (uint32_t *)d_min_d);
+  PRS_LAUNCH(k_min_light_distance, blocks, 256, 0, (const float2 *)pos, (uint32_t)n, (uint32_t *)d_min_d, (const uint32_t *)nullptr);
 }
 void prs_update_phase_dev(const float *pos, float *phase, float spacing, const float *d_min_d, int n) {
   if (n <= 0) return;
-  PRS_LAUNCH(k_update_phase, div_up(n, 256), 256, 0, (const float2 *)pos, phase, spacing, 0.0f, d_min_d, (uint32_t)n);
+  PRS_LAUNCH(k_update_phase, div_up(n, 256), 256, 0, (const float2 *)pos, phase, spacing, 0.0f, d_min_d, (uint32_t)n, (const uint32_t *)nullptr);
 }
 void prs_centroid(const float *pos, int n, float *d_scratch, float *d_out) {
   if (n <= 0) return;
@@ -836,14 +775,14 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     {
       StageScope t(PRS_STAGE_K1);
       PRS_LAUNCH(k_control_integrate_hash<true>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
-                 b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
+                 b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n, (const uint32_t *)nullptr);
     }
     StageScope t(PRS_STAGE_SORT);
     sort_pairs(b->hash, b->index, b->hash, b->index, n, key_bits_of_grid(), true);
   } else {
     StageScope t(PRS_STAGE_K1);
     PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
-               b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n);
+               b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n, (const uint32_t *)nullptr);
   }
   const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
   if (b->sortedPR) {
@@ -868,68 +807,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
                      (const float2 *)b->sortedVel, b->sortedRad, b->index, b->cellStart, b->cellEnd, n, dt, need_fa);
 }
 
-/* ---- slab (multi-GPU) building blocks: the fused step cut at the points where ranks exchange ---- */
-void prs_slab_k1(float *pos, float *vel, float *rad, const float *phase, const float *absForce_a,
-                 const float *absForce_r, const int *dead, unsigned *hash, unsigned *index, float time, float dt,
-                 unsigned n, int do_hash) {
-  if (!n) return;
-  const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
-  StageScope t(PRS_STAGE_K1);
-  if (do_hash)
-    PRS_LAUNCH(k_control_integrate_hash<true>, div_up(n, 256), 256, 0, (float2 *)pos, (float2 *)vel, rad, phase,
-               absForce_a, absForce_r, dead, hash, index, time, dt, run_controller, n);
-  else
-    PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)pos, (float2 *)vel, rad, phase,
-               absForce_a, absForce_r, dead, hash, index, time, dt, run_controller, n);
-}
-void prs_slab_sort(const unsigned *in_keys, const unsigned *in_vals, unsigned *out_keys, unsigned *out_vals,
-                   unsigned n, int vals_are_iota) {
-  StageScope t(PRS_STAGE_SORT);
-  sort_pairs(in_keys, in_vals, out_keys, out_vals, n, key_bits_of_grid(), vals_are_iota != 0);
-}
-void prs_slab_gather(float *sortedPR, float *sortedVel, const unsigned *index, const float *pos, const float *vel,
-                     const float *rad, unsigned n) {
-  if (!n) return;
-  StageScope t(PRS_STAGE_REORDER);
-  PRS_LAUNCH(k_gather_packed, div_up(n, 256), 256, 0, (float4 *)sortedPR, (float2 *)sortedVel, index,
-             (const float2 *)pos, (const float2 *)vel, rad, n);
-}
-/* clears cellStart for cells [cell_lo, cell_lo + ncells) and builds the table from n sorted keys */
-void prs_slab_cell_table(unsigned *cellStart, unsigned *cellEnd, const unsigned *hash, unsigned n, unsigned slot0,
-                         unsigned cell_lo, unsigned ncells) {
-  StageScope t(PRS_STAGE_REORDER);
-  PRS_CUDA(cudaMemsetAsync(cellStart + cell_lo, 0xff, (size_t)ncells * sizeof(unsigned), g_prs.stream));
-  if (!n) return;
-  PRS_LAUNCH(k_cell_table, div_up(n, 256), 256, 0, cellStart, cellEnd, hash, n, slot0);
-}
-void prs_slab_lower_bounds(const unsigned *hash, unsigned n, const unsigned *d_bounds, unsigned nb, unsigned *d_out) {
-  if (!nb) return;
-  PRS_LAUNCH(k_lower_bounds, div_up(nb, 32), 32, 0, hash, n, d_bounds, nb, d_out);
-}
-/* collide for sorted slots [k_begin, k_end) of the concatenated [halo | owned | halo] arrays;
- * results are scattered to pr.w of each slot (the owner's local slot) */
-void prs_slab_collide(float *newVel, float *absForce_a, float *absForce_r, const float *sortedPR,
-                      const float *sortedVel, const unsigned *cellStart, const unsigned *cellEnd, unsigned k_begin,
-                      unsigned k_end, float dt) {
-  if (k_end <= k_begin) return;
-  if (g_prs.h_prm.p.nDead == -1) {
-    fprintf(stderr, "prs_slab_collide: object-transport mode (nDead == -1) is single-GPU only\n");
-    exit(EXIT_FAILURE);
-  }
-  StageScope t(PRS_STAGE_COLLIDE);
-  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
-  prs::PackedLayout in{(const float4 *)sortedPR, (const float2 *)sortedVel};
-  prs_launch_collide_t((float2 *)newVel, absForce_a, absForce_r, in, cellStart, cellEnd, k_end, dt, need_fa, k_begin);
-}
-void prs_slab_fix_ties(const unsigned *hash_sorted, unsigned *index_sorted, const unsigned *gid, unsigned n) {
-  if (!n) return;
-  StageScope t(PRS_STAGE_SORT);
-  PRS_LAUNCH(k_fix_ties_by_gid, div_up(n, 256), 256, 0, hash_sorted, index_sorted, gid, n);
-}
-void prs_curand_setup_ids(struct curandStateXORWOW *state, const unsigned *gid, unsigned n) {
-  if (!n) return;
-  PRS_LAUNCH(k_curand_setup_ids, div_up(n, 256), 256, 0, (curandState *)state, gid, n);
-}
+#include "prs_slab.cuh"
 
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n) {
   if (!n) return;

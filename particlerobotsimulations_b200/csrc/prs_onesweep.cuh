@@ -86,7 +86,9 @@ struct __align__(16) Smem {
  * high digits, so a warp whose 32 keys agree on a digit adds 32 with one atomic; mixed warps use
  * plain shared-memory atomics (few-way conflicts). */
 __global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t *__restrict__ keys, uint32_t n,
-                                                            uint32_t *__restrict__ ghist, int npass) {
+                                                            uint32_t *__restrict__ ghist, int npass,
+                                                            const uint32_t *__restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   __shared__ uint32_t sh[MAX_PASSES][RADIX];
   for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&sh[0][0])[i] = 0;
   __syncthreads();
@@ -154,8 +156,10 @@ template <int NT>
 __global__ void __launch_bounds__(NT, (NT == 512) ? 2 : 1)
 k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
            uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ ghist,
-           volatile uint32_t *status, uint32_t *tile_counter, unsigned long long *timeline) {
+           volatile uint32_t *status, uint32_t *tile_counter, unsigned long long *timeline,
+           const uint32_t *__restrict__ n_dev) {
   using C = Cfg<NT>;
+  if (n_dev) n = *n_dev; /* slab ranks: launched for the capacity, tiles past the real count exit */
   constexpr int THREADS = C::THREADS, WARPS = C::WARPS, TILE = C::TILE, GROUPS = C::GROUPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<NT> &S = *reinterpret_cast<Smem<NT> *>(smem_raw);
@@ -168,6 +172,7 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
   const uint32_t tile = S.tile;
   stamp(timeline, tile, 0);
   const uint32_t tile_base = tile * (uint32_t)TILE;
+  if (tile_base >= n) return; /* uniform for the block; only possible with a device-side count */
   const uint32_t tile_valid = min((uint32_t)TILE, n - tile_base);
   const uint32_t wbase = tile_base + warp * (ITEMS * 32);
 

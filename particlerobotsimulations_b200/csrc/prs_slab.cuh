@@ -1,0 +1,350 @@
+/*
+ * prs_slab.cuh — slab (multi-GPU) engine: the fused step cut at the two points where ranks
+ * exchange robots, with every count kept ON THE DEVICE (DESIGN.md "multi-GPU").
+ * Included by prs_kernels.cu inside its extern "C" block.
+ *
+ * A rank owns the grid rows [row_lo, row_hi).  Nothing in a step needs the host to know how many
+ * robots it owns, how many left, or how long the halos are: kernels are launched for the slab's
+ * CAPACITY and read the live counts from `counts` (uint32[16], PRS_SC_*); the neighbour exchange
+ * moves FIXED-SIZE buffers whose first word is the record count.  So a step is a pure stream of
+ * kernel launches and NCCL sends/receives — no host synchronisation, no device-to-host copy.
+ *
+ *   K1 -> [sort steps: migrate_pack -> exchange -> migrate_unpack -> sort (+ ties by global id)]
+ *      -> gather -> halo_pack -> exchange -> halo_unpack -> cell_table -> collide
+ *
+ * Migration record (23 words, structure-of-arrays with stride mig_cap after the count word):
+ *   pos.xy vel.xy rad phase absForce_a absForce_r dead gid hash rng[12]
+ * Halo record (7 words, stride halo_cap): sortedPR.xyzw sortedVel.xy hash
+ * Errors that the host must hear about (capacity overflow, a robot crossing more than one slab)
+ * set bits in counts[PRS_SC_ERR]; the host polls it asynchronously.
+ */
+#pragma once
+
+#define SLAB_MIG_WORDS 23
+#define SLAB_HALO_WORDS 7
+
+/* -------------------------------------------------------------------------------------------- */
+/* migration                                                                                      */
+/* -------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void slab_store_record(uint32_t *buf, uint32_t stride, uint32_t q, const prs_slab &s, uint32_t i) {
+  uint32_t *o = buf + 1 + q;
+  const float2 p = ((const float2 *)s.pos)[i], v = ((const float2 *)s.vel)[i];
+  o[0 * stride] = __float_as_uint(p.x); o[1 * stride] = __float_as_uint(p.y);
+  o[2 * stride] = __float_as_uint(v.x); o[3 * stride] = __float_as_uint(v.y);
+  o[4 * stride] = __float_as_uint(s.rad[i]); o[5 * stride] = __float_as_uint(s.phase[i]);
+  o[6 * stride] = __float_as_uint(s.absForce_a[i]); o[7 * stride] = __float_as_uint(s.absForce_r[i]);
+  o[8 * stride] = (uint32_t)s.dead[i]; o[9 * stride] = s.gid[i]; o[10 * stride] = s.hash[i];
+  const uint32_t *r = (const uint32_t *)s.rng + (size_t)i * 12;
+#pragma unroll
+  for (int w = 0; w < 12; w++) o[(11 + w) * stride] = r[w];
+}
+__device__ __forceinline__ void slab_load_record(const uint32_t *buf, uint32_t stride, uint32_t q, const prs_slab &s, uint32_t i) {
+  const uint32_t *o = buf + 1 + q;
+  ((float2 *)s.pos)[i] = make_float2(__uint_as_float(o[0 * stride]), __uint_as_float(o[1 * stride]));
+  ((float2 *)s.vel)[i] = make_float2(__uint_as_float(o[2 * stride]), __uint_as_float(o[3 * stride]));
+  s.rad[i] = __uint_as_float(o[4 * stride]); s.phase[i] = __uint_as_float(o[5 * stride]);
+  s.absForce_a[i] = __uint_as_float(o[6 * stride]); s.absForce_r[i] = __uint_as_float(o[7 * stride]);
+  s.dead[i] = (int)o[8 * stride]; s.gid[i] = o[9 * stride]; s.hash[i] = o[10 * stride];
+  uint32_t *r = (uint32_t *)s.rng + (size_t)i * 12;
+#pragma unroll
+  for (int w = 0; w < 12; w++) r[w] = o[(11 + w) * stride];
+}
+__device__ __forceinline__ void slab_move_record(const prs_slab &s, uint32_t dst, uint32_t src) {
+  ((float2 *)s.pos)[dst] = ((const float2 *)s.pos)[src];
+  ((float2 *)s.vel)[dst] = ((const float2 *)s.vel)[src];
+  s.rad[dst] = s.rad[src]; s.phase[dst] = s.phase[src];
+  s.absForce_a[dst] = s.absForce_a[src]; s.absForce_r[dst] = s.absForce_r[src];
+  s.dead[dst] = s.dead[src]; s.gid[dst] = s.gid[src]; s.hash[dst] = s.hash[src];
+  const uint4 *a = (const uint4 *)((const uint32_t *)s.rng + (size_t)src * 12);
+  uint4 *b = (uint4 *)((uint32_t *)s.rng + (size_t)dst * 12);
+  b[0] = a[0]; b[1] = a[1]; b[2] = a[2];
+}
+
+/* resets the per-step counters (everything except n and the statistics) */
+__global__ void k_slab_begin_step(uint32_t *counts) {
+  const int i = threadIdx.x;
+  if (i >= PRS_SC_NLO && i <= PRS_SC_KEEPERS) counts[i] = 0;
+}
+
+/* M1: robots whose new grid row left [row_lo, row_hi) are packed for the neighbour that owns it
+ * and listed; `scratch[i]` = 1 marks a leaver */
+__global__ void __launch_bounds__(256) k_slab_select(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up,
+                                                     uint32_t log2_gx) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t row = s.hash[i] >> log2_gx;
+  const bool dn = row < s.row_lo, up = row >= s.row_hi;
+  s.scratch[i] = (dn || up) ? 1u : 0u;
+  if (!(dn || up)) return;
+  if ((dn && !s.has_dn) || (up && !s.has_up)) { atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_LEFT_WORLD); s.scratch[i] = 0u; return; }
+  const uint32_t q = atomicAdd(&s.counts[dn ? PRS_SC_MIGDN : PRS_SC_MIGUP], 1u);
+  if (q >= s.mig_cap) { atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_MIG_CAP); s.scratch[i] = 0u; return; }
+  slab_store_record(dn ? send_dn : send_up, s.mig_cap, q, s, i);
+  s.lists[atomicAdd(&s.counts[PRS_SC_LEAVERS], 1u)] = i;
+}
+/* M2: with L leavers the survivors must end up in [0, n-L).  Holes = leavers below n-L, movers =
+ * survivors at or above it; both lists have the same length. */
+__global__ void __launch_bounds__(256) k_slab_list_holes(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up) {
+  const uint32_t n = s.counts[PRS_SC_N], L = s.counts[PRS_SC_LEAVERS];
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) { /* the count words of the outgoing buffers */
+    send_dn[0] = min(s.counts[PRS_SC_MIGDN], s.mig_cap);
+    send_up[0] = min(s.counts[PRS_SC_MIGUP], s.mig_cap);
+  }
+  if (q >= L) return;
+  const uint32_t new_n = n - L;
+  uint32_t *holes = s.lists + 2 * s.mig_cap, *movers = s.lists + 4 * s.mig_cap;
+  const uint32_t li = s.lists[q];
+  if (li < new_n) holes[atomicAdd(&s.counts[PRS_SC_HOLES], 1u)] = li;
+  const uint32_t j = new_n + q; /* the L slots of the tail */
+  if (!s.scratch[j]) movers[atomicAdd(&s.counts[PRS_SC_KEEPERS], 1u)] = j;
+}
+/* M3: movers fill the holes; then the arrivals are appended and n is updated */
+__global__ void __launch_bounds__(256) k_slab_fill_holes(prs_slab s) {
+  const uint32_t H = s.counts[PRS_SC_HOLES];
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H) return;
+  slab_move_record(s, s.lists[2 * s.mig_cap + q], s.lists[4 * s.mig_cap + q]);
+}
+__global__ void __launch_bounds__(256) k_slab_append(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up,
+                                                     uint32_t log2_gx) {
+  const uint32_t n = s.counts[PRS_SC_N], L = s.counts[PRS_SC_LEAVERS];
+  const uint32_t c_dn = s.has_dn ? min(recv_dn[0], s.mig_cap) : 0u, c_up = s.has_up ? min(recv_up[0], s.mig_cap) : 0u;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= c_dn + c_up) return;
+  const uint32_t dst = n - L + q;
+  if (dst >= s.cap) { atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_CAPACITY); return; }
+  if (q < c_dn) slab_load_record(recv_dn, s.mig_cap, q, s, dst);
+  else slab_load_record(recv_up, s.mig_cap, q - c_dn, s, dst);
+  const uint32_t row = s.hash[dst] >> log2_gx; /* a robot may cross one slab per sort at most */
+  if (row < s.row_lo || row >= s.row_hi) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_TWO_SLABS);
+}
+__global__ void k_slab_commit_count(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up) {
+  const uint32_t c_dn = s.has_dn ? min(recv_dn[0], s.mig_cap) : 0u, c_up = s.has_up ? min(recv_up[0], s.mig_cap) : 0u;
+  const uint32_t L = s.counts[PRS_SC_LEAVERS];
+  uint32_t n = s.counts[PRS_SC_N] - L + c_dn + c_up;
+  if (n > s.cap) n = s.cap;
+  s.counts[PRS_SC_N] = n;
+  s.counts[PRS_SC_STAT_MIG] += L;
+}
+
+/* -------------------------------------------------------------------------------------------- */
+/* sorted view: gather, ties, halo, cell table                                                    */
+/* -------------------------------------------------------------------------------------------- */
+/* Slab ranks hold their robots in arbitrary local slots, but the reference's stable sort leaves the
+ * robots of one cell in ascending ORIGINAL index.  After the local sort (ties by local slot) the
+ * thread at each cell start insertion-sorts that cell's few entries by global id, so forces are
+ * summed in exactly the single-GPU order (bit-equal results across any number of slabs). */
+__global__ void __launch_bounds__(256)
+k_fix_ties_by_gid(const uint32_t *__restrict__ hash, uint32_t *__restrict__ index, const uint32_t *__restrict__ gid,
+                  const uint32_t *__restrict__ n_dev) {
+  const uint32_t n = *n_dev;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t h = hash[k];
+  if (k > 0 && hash[k - 1] == h) return; /* not a cell start */
+  uint32_t e = k + 1;
+  while (e < n && hash[e] == h) e++;
+  for (uint32_t a = k + 1; a < e; a++) {
+    const uint32_t slot = index[a];
+    const uint32_t g = gid[slot];
+    uint32_t b = a;
+    while (b > k && gid[index[b - 1]] > g) { index[b] = index[b - 1]; b--; }
+    index[b] = slot;
+  }
+}
+/* packed sorted copy of the owned robots at [halo_cap, halo_cap + n); pr.w = local slot (the
+ * scatter target of collide) */
+__global__ void __launch_bounds__(256) k_slab_gather(prs_slab s) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t src = s.index_sorted[k];
+  const float2 p = ((const float2 *)s.pos)[src];
+  ((float4 *)s.sortedPR)[s.halo_cap + k] = make_float4(p.x, p.y, s.rad[src], __uint_as_float(src));
+  ((float2 *)s.sortedVel)[s.halo_cap + k] = ((const float2 *)s.vel)[src];
+}
+/* first owned sorted slot whose key is >= bound (binary search over the device-side count) */
+__device__ __forceinline__ uint32_t slab_lower_bound(const uint32_t *hash, uint32_t n, uint32_t key) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (hash[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+/* The first / last halo_rows grid rows of the owned sorted range are contiguous slices; thread 0
+ * finds them, then the block copies them into the outgoing buffers (count word first). */
+__global__ void __launch_bounds__(256) k_slab_halo_pack(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up,
+                                                        uint32_t gx) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t *hs = s.hash_cat + s.halo_cap; /* owned keys, sorted */
+  __shared__ uint32_t sh[2];
+  if (threadIdx.x == 0) {
+    uint32_t k_dn = 0, k_up = 0;
+    if (s.has_dn) k_dn = slab_lower_bound(hs, n, min(s.row_lo + s.halo_rows, s.row_hi) * gx);
+    if (s.has_up) k_up = n - slab_lower_bound(hs, n, (s.row_hi > s.row_lo + s.halo_rows ? s.row_hi - s.halo_rows : s.row_lo) * gx);
+    if (k_dn > s.halo_cap || k_up > s.halo_cap) {
+      if (blockIdx.x == 0) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_HALO_CAP);
+      k_dn = min(k_dn, s.halo_cap); k_up = min(k_up, s.halo_cap);
+    }
+    sh[0] = k_dn; sh[1] = k_up;
+    if (blockIdx.x == 0) { send_dn[0] = k_dn; send_up[0] = k_up; s.counts[PRS_SC_KDN] = k_dn; s.counts[PRS_SC_KUP] = k_up; }
+  }
+  __syncthreads();
+  const uint32_t k_dn = sh[0], k_up = sh[1];
+  const float4 *pr = (const float4 *)s.sortedPR + s.halo_cap;
+  const float2 *sv = (const float2 *)s.sortedVel + s.halo_cap;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < k_dn + k_up; q += gridDim.x * blockDim.x) {
+    const bool lower = q < k_dn;
+    const uint32_t r = lower ? q : q - k_dn;              /* record number in its buffer */
+    const uint32_t k = lower ? q : n - k_up + r;           /* owned sorted slot */
+    uint32_t *o = (lower ? send_dn : send_up) + 1 + r;
+    const float4 a = pr[k];
+    const float2 v = sv[k];
+    o[0 * s.halo_cap] = __float_as_uint(a.x); o[1 * s.halo_cap] = __float_as_uint(a.y);
+    o[2 * s.halo_cap] = __float_as_uint(a.z); o[3 * s.halo_cap] = __float_as_uint(a.w);
+    o[4 * s.halo_cap] = __float_as_uint(v.x); o[5 * s.halo_cap] = __float_as_uint(v.y);
+    o[6 * s.halo_cap] = hs[k];
+  }
+}
+/* arrivals go to the flanks: the lower neighbour's rows end at halo_cap, the upper neighbour's
+ * start at halo_cap + n */
+__global__ void __launch_bounds__(256) k_slab_halo_unpack(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t n_lo = s.has_dn ? min(recv_dn[0], s.halo_cap) : 0u, n_hi = s.has_up ? min(recv_up[0], s.halo_cap) : 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    s.counts[PRS_SC_NLO] = n_lo; s.counts[PRS_SC_NHI] = n_hi;
+    s.counts[PRS_SC_STAT_HALO] += n_lo + n_hi;
+  }
+  float4 *pr = (float4 *)s.sortedPR;
+  float2 *sv = (float2 *)s.sortedVel;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_lo + n_hi; q += gridDim.x * blockDim.x) {
+    const bool lower = q < n_lo;
+    const uint32_t r = lower ? q : q - n_lo;
+    const uint32_t k = lower ? s.halo_cap - n_lo + r : s.halo_cap + n + r;
+    const uint32_t *o = (lower ? recv_dn : recv_up) + 1 + r;
+    pr[k] = make_float4(__uint_as_float(o[0 * s.halo_cap]), __uint_as_float(o[1 * s.halo_cap]),
+                        __uint_as_float(o[2 * s.halo_cap]), __uint_as_float(o[3 * s.halo_cap]));
+    sv[k] = make_float2(__uint_as_float(o[4 * s.halo_cap]), __uint_as_float(o[5 * s.halo_cap]));
+    s.hash_cat[k] = o[6 * s.halo_cap];
+  }
+}
+/* cellStart/cellEnd (reference format) over the keys of [lower halo | owned | upper halo] */
+__global__ void __launch_bounds__(256) k_slab_cell_table(prs_slab s) {
+  const uint32_t n_lo = s.counts[PRS_SC_NLO], n_tot = n_lo + s.counts[PRS_SC_N] + s.counts[PRS_SC_NHI];
+  const uint32_t slot0 = s.halo_cap - n_lo;
+  const uint32_t *hash = s.hash_cat + slot0;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_tot) return;
+  const uint32_t h = hash[k];
+  const uint32_t hp = (k > 0) ? hash[k - 1] : 0u;
+  if (k == 0 || h != hp) {
+    s.cellStart[h] = slot0 + k;
+    if (k > 0) s.cellEnd[hp] = slot0 + k;
+  }
+  if (k == n_tot - 1) s.cellEnd[h] = slot0 + k + 1;
+}
+/* XORWOW states for robots that carry GLOBAL ids: subsequence = global id, so every robot's noise
+ * stream is the one the single-GPU run (and the reference) gives it */
+__global__ void __launch_bounds__(256) k_curand_setup_ids(curandState *__restrict__ st, const uint32_t *__restrict__ gid, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) curand_init(c_prm.p.seed, gid[i], 0, &st[i]);
+}
+
+/* -------------------------------------------------------------------------------------------- */
+/* C entry points                                                                                 */
+/* -------------------------------------------------------------------------------------------- */
+static uint32_t slab_log2_gx() {
+  uint32_t b = 0;
+  while ((1u << b) < g_prs.h_prm.p.gridSize.x) b++;
+  return b;
+}
+static void slab_check(const prs_slab *s) {
+  if (g_prs.h_prm.p.nDead == -1) {
+    fprintf(stderr, "prs_slab: object-transport mode (nDead == -1) is single-GPU only\n");
+    exit(EXIT_FAILURE);
+  }
+  if (!s->cap || !s->halo_cap || !s->mig_cap) { fprintf(stderr, "prs_slab: zero capacity\n"); exit(EXIT_FAILURE); }
+}
+
+size_t prs_slab_mig_words(unsigned mig_cap) { return 1 + (size_t)SLAB_MIG_WORDS * mig_cap; }
+size_t prs_slab_halo_words(unsigned halo_cap) { return 1 + (size_t)SLAB_HALO_WORDS * halo_cap; }
+
+void prs_slab_rng_setup(const prs_slab *s, unsigned n) {
+  if (!n) return;
+  PRS_LAUNCH(k_curand_setup_ids, div_up(n, 256), 256, 0, (curandState *)s->rng, s->gid, n);
+}
+void prs_slab_k1(const prs_slab *s, float time, float dt, int do_hash) {
+  slab_check(s);
+  const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
+  StageScope t(PRS_STAGE_K1);
+  PRS_LAUNCH(k_slab_begin_step, 1, 32, 0, s->counts);
+  if (do_hash)
+    PRS_LAUNCH(k_control_integrate_hash<true>, div_up(s->cap, 256), 256, 0, (float2 *)s->pos, (float2 *)s->vel, s->rad, s->phase,
+               s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap, s->counts + PRS_SC_N);
+  else
+    PRS_LAUNCH(k_control_integrate_hash<false>, div_up(s->cap, 256), 256, 0, (float2 *)s->pos, (float2 *)s->vel, s->rad, s->phase,
+               s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap, s->counts + PRS_SC_N);
+}
+void prs_slab_migrate_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up) {
+  StageScope t(PRS_STAGE_EXCHANGE);
+  PRS_LAUNCH(k_slab_select, div_up(s->cap, 256), 256, 0, *s, send_dn, send_up, slab_log2_gx());
+  PRS_LAUNCH(k_slab_list_holes, div_up(2 * s->mig_cap, 256), 256, 0, *s, send_dn, send_up);
+}
+void prs_slab_migrate_unpack(const prs_slab *s, const unsigned *recv_dn, const unsigned *recv_up) {
+  StageScope t(PRS_STAGE_EXCHANGE);
+  PRS_LAUNCH(k_slab_fill_holes, div_up(2 * s->mig_cap, 256), 256, 0, *s);
+  PRS_LAUNCH(k_slab_append, div_up(2 * s->mig_cap, 256), 256, 0, *s, recv_dn, recv_up, slab_log2_gx());
+  PRS_LAUNCH(k_slab_commit_count, 1, 1, 0, *s, recv_dn, recv_up);
+}
+/* (hash, local slot) of the owned robots sorted by hash into hash_cat[halo_cap ..] / index_sorted,
+ * robots of one cell in ascending global id */
+void prs_slab_sort(const prs_slab *s) {
+  StageScope t(PRS_STAGE_SORT);
+  sort_pairs(s->hash, nullptr, s->hash_cat + s->halo_cap, s->index_sorted, s->cap, key_bits_of_grid(), true, s->counts + PRS_SC_N);
+  PRS_LAUNCH(k_fix_ties_by_gid, div_up(s->cap, 256), 256, 0, s->hash_cat + s->halo_cap, s->index_sorted, s->gid, s->counts + PRS_SC_N);
+}
+void prs_slab_gather(const prs_slab *s) {
+  StageScope t(PRS_STAGE_REORDER);
+  PRS_LAUNCH(k_slab_gather, div_up(s->cap, 256), 256, 0, *s);
+}
+void prs_slab_halo_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up) {
+  StageScope t(PRS_STAGE_EXCHANGE);
+  PRS_LAUNCH(k_slab_halo_pack, min(div_up(2 * s->halo_cap, 256), 592u), 256, 0, *s, send_dn, send_up, g_prs.h_prm.p.gridSize.x);
+}
+void prs_slab_halo_unpack(const prs_slab *s, const unsigned *recv_dn, const unsigned *recv_up) {
+  StageScope t(PRS_STAGE_EXCHANGE);
+  PRS_LAUNCH(k_slab_halo_unpack, min(div_up(2 * s->halo_cap, 256), 592u), 256, 0, *s, recv_dn, recv_up);
+}
+/* clears cellStart for the rows this rank can see and builds the table over [halo | owned | halo] */
+void prs_slab_cell_table(const prs_slab *s) {
+  StageScope t(PRS_STAGE_REORDER);
+  const unsigned gx = g_prs.h_prm.p.gridSize.x, gy = g_prs.h_prm.p.gridSize.y;
+  const unsigned r0 = s->row_lo > s->halo_rows ? s->row_lo - s->halo_rows : 0u;
+  const unsigned r1 = min(s->row_hi + s->halo_rows, gy);
+  PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(r1 - r0) * gx * sizeof(unsigned), g_prs.stream));
+  PRS_LAUNCH(k_slab_cell_table, div_up(s->cap + 2 * s->halo_cap, 256), 256, 0, *s);
+}
+/* collide for the owned sorted slots [halo_cap, halo_cap + n); results go to the local slots */
+void prs_slab_collide(const prs_slab *s, float dt) {
+  slab_check(s);
+  StageScope t(PRS_STAGE_COLLIDE);
+  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
+  prs::PackedLayout in{(const float4 *)s->sortedPR, (const float2 *)s->sortedVel};
+  prs_launch_collide_t((float2 *)s->vel, s->absForce_a, s->absForce_r, in, s->cellStart, s->cellEnd, s->halo_cap + s->cap, dt,
+                       need_fa, s->halo_cap, s->counts + PRS_SC_N);
+}
+void prs_slab_min_light_distance(const prs_slab *s, float *d_min_d) {
+  PRS_CUDA(cudaMemsetAsync(d_min_d, 0x7f, sizeof(float), g_prs.stream));
+  const unsigned blocks = min(div_up(s->cap, 256 * 4), 148u * 8u);
+  PRS_LAUNCH(k_min_light_distance, blocks, 256, 0, (const float2 *)s->pos, s->cap, (uint32_t *)d_min_d, s->counts + PRS_SC_N);
+}
+void prs_slab_update_phase(const prs_slab *s, float spacing, const float *d_min_d) {
+  PRS_LAUNCH(k_update_phase, div_up(s->cap, 256), 256, 0, (const float2 *)s->pos, s->phase, spacing, 0.0f, d_min_d, s->cap,
+             s->counts + PRS_SC_N);
+}
+void prs_slab_add_noise(const prs_slab *s, float std) {
+  PRS_LAUNCH(k_add_normal_noise, div_up(s->cap, 256), 256, 0, (curandState *)s->rng, s->phase, std, s->cap, s->counts + PRS_SC_N);
+}

@@ -9,37 +9,43 @@ the sorted arrays, so the world is cut into horizontal slabs of grid rows, one p
        the generator state travels with its robot and is seeded by GLOBAL id)
     2. controller + integrate (+ hash on sort steps) on the owned robots           (prs_slab_k1)
     3. [sort steps]  MIGRATION: robots whose new row left the slab are packed (full state record,
-       88 B) and sent to the neighbour that owns the row; arrivals are appended     (isend/irecv)
+       92 B) for the neighbour that owns the row, the survivors are compacted, arrivals appended
+                                              (prs_slab_migrate_pack / exchange / _migrate_unpack)
     4. [sort steps]  local onesweep sort of (hash, local slot), ties put in global-id order
-                                                                  (prs_slab_sort, prs_slab_fix_ties)
-    5. gather into the packed sorted layout at a fixed offset                       (prs_slab_gather)
+                                                                                   (prs_slab_sort)
+    5. gather into the packed sorted layout at a fixed offset                    (prs_slab_gather)
     6. HALO: the first/last HALO_ROWS grid rows of the sorted range are contiguous slices; they
-       are sent to the lower/upper neighbour and received into the flanks            (isend/irecv)
-    7. cell table over [lower halo | owned | upper halo]                            (prs_slab_cell_table)
-    8. collide over the owned range, results scattered to local slots                (prs_slab_collide)
+       are packed, sent to the lower/upper neighbour and unpacked into the flanks
+                                                    (prs_slab_halo_pack / exchange / _halo_unpack)
+    7. cell table over [lower halo | owned | upper halo]                      (prs_slab_cell_table)
+    8. collide over the owned range, results scattered to local slots            (prs_slab_collide)
 
-The data path has no collective: only neighbour sends of <= a few MB (latency-bound on NVLink),
-one 4-byte all_reduce per phase update, and two small all_gathers of counts per step (the host
-needs them to size the transfers — the two host syncs of the step).  Ownership changes only on
-sort steps (the table is frozen between sorts), HALO_ROWS = 3 = the 2-row stencil +
-1 guard row for drift between sorts.  Limits of this version: the hash wrap-around (Q9) is not
-exchanged — the world must fit the grid — a robot may cross at most one slab per sort, object
-transport (nDead == -1) is single-GPU only.  Robots of one cell are ordered by GLOBAL id after the
-local sort (prs_slab_fix_ties), which is the order the reference's stable sort gives them, so the
-forces are summed in the single-GPU order and the results are bit-equal for any number of slabs.
+EVERY COUNT LIVES ON THE DEVICE (csrc/prs_slab.cuh): kernels are launched for the slab's capacity
+and read the live robot / halo / migrant counts from a 16-word device array; the exchanges move
+fixed-size buffers whose first word is the record count.  A step is therefore a pure stream of
+kernel launches and neighbour sends/receives — no host synchronisation and no device-to-host
+copy anywhere in it (overflow and "crossed two slabs" conditions set sticky error bits that
+`check()` reads when the caller asks).  The data path has no collective: neighbour transfers of a
+few MB (latency-bound on NVLink) and one 4-byte all_reduce per phase update.  Ownership changes
+only on sort steps (the table is frozen between sorts); HALO_ROWS = 3 = the 2-row
+stencil + 1 guard row for drift between sorts.  Limits of this version: the hash wrap-around (Q9)
+is not exchanged — the world must fit the grid — a robot may cross at most one slab per sort,
+object transport (nDead == -1) is single-GPU only.  Robots of one cell are ordered by GLOBAL id
+after the local sort, which is the order the reference's stable sort gives them, so the forces are
+summed in the single-GPU order and the results are bit-equal for any number of slabs.
 
 The compute calls go through a small backend object so that the CPU tests can drive the same
 host logic with a stand-in (tests/test_multigpu_cpu.py injects one built on the oracle).
 """
 import ctypes as C
-import math
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
+import particlerobotsimulations_b200 as prs
+
 HALO_ROWS = 3
-RECORD_FIELDS = ("pos", "vel", "rad", "phase", "fa", "fr", "dead", "gid", "rng", "hash")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -91,52 +97,72 @@ def slab_rows(params, ny, pitch, world):
 
 # --------------------------------------------------------------------------------------------------
 class CudaBackend:
-    """The slab building blocks of libparticlebot_b200.so on CUDA tensors (current torch stream)."""
+    """The slab engine of libparticlebot_b200.so on CUDA tensors (current torch stream)."""
 
     def __init__(self, params, world_half):
-        import particlerobotsimulations_b200 as prs
         self.lib = prs.lib()
         self.lib.prs_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
         self.lib.prs_set_world_half_extent(world_half)
         self.lib.setParameters(C.byref(params))
+        self.slab = None
+
+    def bind(self, sim):
+        """device pointers of `sim`'s tensors -> prs_slab"""
+        s, sl = sim.s, prs.Slab()
+        for name, t in (("pos", s.pos), ("vel", s.vel), ("rad", s.rad), ("phase", s.phase), ("absForce_a", s.fa),
+                        ("absForce_r", s.fr), ("dead", s.dead), ("gid", s.gid), ("rng", s.rng), ("hash", s.hash),
+                        ("scratch", s.scratch), ("sortedPR", sim.pr), ("sortedVel", sim.svel), ("hash_cat", sim.hash_cat),
+                        ("index_sorted", sim.index_sorted), ("cellStart", sim.cs), ("cellEnd", sim.ce),
+                        ("counts", sim.counts), ("lists", sim.lists)):
+            setattr(sl, name, t.data_ptr())
+        sl.cap, sl.halo_cap, sl.mig_cap = sim.cap, sim.halo_cap, sim.mig_cap
+        sl.row_lo, sl.row_hi, sl.halo_rows = sim.R_lo, sim.R_hi, HALO_ROWS
+        sl.has_dn, sl.has_up = int(sim.rank > 0), int(sim.rank < sim.world - 1)
+        self.slab = sl
+        self._ref = C.byref(sl)
 
     @staticmethod
     def _p(t):
         return C.c_void_p(t.data_ptr())
 
-    def k1(self, s, time, dt, n, do_hash):
-        self.lib.prs_slab_k1(self._p(s.pos), self._p(s.vel), self._p(s.rad), self._p(s.phase), self._p(s.fa),
-                             self._p(s.fr), self._p(s.dead), self._p(s.hash), self._p(s.index), time, dt, n, int(do_hash))
+    def rng_setup(self, n):
+        self.lib.prs_slab_rng_setup(self._ref, n)
 
-    def sort(self, keys_in, keys_out, vals_out, n, gid):
-        """(hash, local slot) sorted by hash, robots of one cell in ascending GLOBAL id"""
-        self.lib.prs_slab_sort(self._p(keys_in), None, self._p(keys_out), self._p(vals_out), n, 1)
-        self.lib.prs_slab_fix_ties(self._p(keys_out), self._p(vals_out), self._p(gid), n)
+    def k1(self, time, dt, do_hash):
+        self.lib.prs_slab_k1(self._ref, time, dt, int(do_hash))
 
-    def gather(self, pr, svel, index, s, n):
-        self.lib.prs_slab_gather(self._p(pr), self._p(svel), self._p(index), self._p(s.pos), self._p(s.vel), self._p(s.rad), n)
+    def migrate_pack(self, send_dn, send_up):
+        self.lib.prs_slab_migrate_pack(self._ref, self._p(send_dn), self._p(send_up))
 
-    def cell_table(self, cs, ce, hash_cat, n, slot0, cell_lo, ncells):
-        self.lib.prs_slab_cell_table(self._p(cs), self._p(ce), self._p(hash_cat), n, slot0, cell_lo, ncells)
+    def migrate_unpack(self, recv_dn, recv_up):
+        self.lib.prs_slab_migrate_unpack(self._ref, self._p(recv_dn), self._p(recv_up))
 
-    def lower_bounds(self, hash_sorted, n, bounds, out):
-        self.lib.prs_slab_lower_bounds(self._p(hash_sorted), n, self._p(bounds), bounds.numel(), self._p(out))
+    def sort(self):
+        self.lib.prs_slab_sort(self._ref)
 
-    def collide(self, s, pr, svel, cs, ce, k_begin, k_end, dt):
-        self.lib.prs_slab_collide(self._p(s.vel), self._p(s.fa), self._p(s.fr), self._p(pr), self._p(svel), self._p(cs),
-                                  self._p(ce), k_begin, k_end, dt)
+    def gather(self):
+        self.lib.prs_slab_gather(self._ref)
 
-    def min_light_distance(self, pos, n, out):
-        self.lib.prs_min_light_distance(self._p(pos), n, self._p(out))
+    def halo_pack(self, send_dn, send_up):
+        self.lib.prs_slab_halo_pack(self._ref, self._p(send_dn), self._p(send_up))
 
-    def update_phase(self, pos, phase, spacing, min_d, n):
-        self.lib.prs_update_phase_dev(self._p(pos), self._p(phase), spacing, self._p(min_d), n)
+    def halo_unpack(self, recv_dn, recv_up):
+        self.lib.prs_slab_halo_unpack(self._ref, self._p(recv_dn), self._p(recv_up))
 
-    def rng_setup(self, rng, gid, n):
-        self.lib.prs_curand_setup_ids(self._p(rng), self._p(gid), n)
+    def cell_table(self):
+        self.lib.prs_slab_cell_table(self._ref)
 
-    def add_noise(self, rng, phase, std, n):
-        self.lib.add_normal_noise(self._p(rng), self._p(phase), std, n)
+    def collide(self, dt):
+        self.lib.prs_slab_collide(self._ref, dt)
+
+    def min_light_distance(self, out):
+        self.lib.prs_slab_min_light_distance(self._ref, self._p(out))
+
+    def update_phase(self, spacing, min_d):
+        self.lib.prs_slab_update_phase(self._ref, spacing, self._p(min_d))
+
+    def add_noise(self, std):
+        self.lib.prs_slab_add_noise(self._ref, std)
 
 
 class _State:
@@ -147,39 +173,44 @@ class SlabSim:
     """One rank's slab of the swarm.  `backend` supplies the compute calls (CudaBackend or a test
     stand-in); `group` is the torch.distributed process group (None = default)."""
 
-    def __init__(self, params, opt, backend, rank, world, device, pos, gid, rows, capacity=None, group=None):
+    def __init__(self, params, opt, backend, rank, world, device, pos, gid, rows, capacity=None, halo_cap=None,
+                 mig_cap=None, group=None):
         self.p, self.opt, self.be = params, opt, backend
         self.rank, self.world, self.dev, self.group = rank, world, device, group
         self.R_lo, self.R_hi = rows[rank], rows[rank + 1]
         self.GX, self.GY = int(params.gridSize.x), int(params.gridSize.y)
-        self.n = int(len(gid))
-        cap = capacity or int(self.n * 1.25) + 65536
-        self.cap = cap
-        self.halo_cap = max(65536, int(cap * 0.1))
+        n = int(len(gid))
+        cap = self.cap = capacity or int(n * 1.25) + 65536
+        self.halo_cap = halo_cap or max(65536, int(cap * 0.1))
+        self.mig_cap = mig_cap or max(4096, cap // 128)
         f32, i32 = torch.float32, torch.int32
         s = self.s = _State()
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
         s.pos, s.vel = z((cap, 2), f32), z((cap, 2), f32)
         s.rad, s.phase, s.fa, s.fr = z(cap, f32), z(cap, f32), z(cap, f32), z(cap, f32)
-        s.dead, s.gid, s.hash, s.index = z(cap, i32), z(cap, i32), z(cap, i32), z(cap, i32)
+        s.dead, s.gid, s.hash, s.scratch = z(cap, i32), z(cap, i32), z(cap, i32), z(cap, i32)
         s.rng = z((cap, 12), i32)
-        s.pos[: self.n] = torch.from_numpy(np.ascontiguousarray(pos)).to(device)
-        s.gid[: self.n] = torch.from_numpy(np.ascontiguousarray(gid).astype(np.int32)).to(device)
-        s.rad[: self.n] = float(np.float32(params.min_radius))
-        self.hash_sorted, self.index_sorted = z(cap, i32), z(cap, i32)
+        s.pos[:n] = torch.from_numpy(np.ascontiguousarray(pos)).to(device)
+        s.gid[:n] = torch.from_numpy(np.ascontiguousarray(gid).astype(np.int32)).to(device)
+        s.rad[:n] = float(np.float32(params.min_radius))
         ncat = cap + 2 * self.halo_cap
         self.pr, self.svel, self.hash_cat = z((ncat, 4), f32), z((ncat, 2), f32), z(ncat, i32)
+        self.index_sorted = z(cap, i32)
         self.cs = torch.full((int(params.numCells),), -1, dtype=i32, device=device)
         self.ce = z(int(params.numCells), i32)
+        self.counts = z(16, i32)
+        self.counts[prs.SC_N] = n
+        self.lists = z(6 * self.mig_cap, i32)
         self.min_d = z(16, f32)
-        self.bounds = torch.tensor([min(self.R_lo + HALO_ROWS, self.GY) * self.GX, max(self.R_hi - HALO_ROWS, 0) * self.GX],
-                                   dtype=i32, device=device)
-        self.bounds_out = z(2, i32)
+        mw, hw = 1 + prs.SLAB_MIG_WORDS * self.mig_cap, 1 + prs.SLAB_HALO_WORDS * self.halo_cap
+        self.mig_send = [z(mw, i32), z(mw, i32)]      # [down, up]
+        self.mig_recv = [z(mw, i32), z(mw, i32)]
+        self.halo_send = [z(hw, i32), z(hw, i32)]
+        self.halo_recv = [z(hw, i32), z(hw, i32)]
         self.time = np.float32(0.0)
-        self.n_lo = self.n_hi = 0
         self.sorted_once = False
-        self.stats = dict(migrated=0, halo=0)
-        self.be.rng_setup(s.rng, s.gid, self.n)
+        self.be.bind(self)
+        self.be.rng_setup(n)
 
     # ---- helpers ---------------------------------------------------------------------------------
     @staticmethod
@@ -187,118 +218,66 @@ class SlabSim:
         t, T, d = np.float32(time), np.float32(interval), np.float32(dt)
         return bool(t - T * np.floor(t / T) < d)
 
-    def _neigh(self):
-        return (self.rank - 1 if self.rank > 0 else None), (self.rank + 1 if self.rank < self.world - 1 else None)
-
-    def _all_counts(self, a, b):
-        """every rank's (a, b): one small all_gather and the host sync that sizes the transfers"""
-        mine = torch.tensor([a, b], dtype=torch.int64, device=self.dev)
-        out = [torch.zeros(2, dtype=torch.int64, device=self.dev) for _ in range(self.world)]
-        dist.all_gather(out, mine, group=self.group)
-        return [tuple(int(v) for v in t.tolist()) for t in out]
-
-    def _exchange(self, send_dn, send_up, recv_dn, recv_up):
-        """lists of tensors to/from the lower (dn) and upper (up) neighbour, posted as one batch"""
-        dn, up = self._neigh()
+    def _exchange(self, send, recv):
+        """fixed-size buffers to / from the lower (index 0) and upper (index 1) neighbour, one batch;
+        ordered on the device stream, the host does not wait for the data"""
+        dn = self.rank - 1 if self.rank > 0 else None
+        up = self.rank + 1 if self.rank < self.world - 1 else None
         ops = []
-        for t in send_dn:
-            ops.append(dist.P2POp(dist.isend, t, dn, group=self.group))
-        for t in send_up:
-            ops.append(dist.P2POp(dist.isend, t, up, group=self.group))
-        for t in recv_dn:
-            ops.append(dist.P2POp(dist.irecv, t, dn, group=self.group))
-        for t in recv_up:
-            ops.append(dist.P2POp(dist.irecv, t, up, group=self.group))
+        if dn is not None:
+            ops.append(dist.P2POp(dist.isend, send[0], dn, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[0], dn, group=self.group))
+        if up is not None:
+            ops.append(dist.P2POp(dist.isend, send[1], up, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[1], up, group=self.group))
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
 
-    # ---- migration (sort steps) --------------------------------------------------------------------
-    def _migrate(self):
-        s, n = self.s, self.n
-        rows = torch.div(s.hash[:n], self.GX, rounding_mode="floor")
-        down, up = rows < self.R_lo, rows >= self.R_hi      # empty on the edge ranks by construction
-        dn_rank, up_rank = self._neigh()
-        idx_dn, idx_up = torch.nonzero(down).flatten(), torch.nonzero(up).flatten()
-        counts = self._all_counts(idx_dn.numel(), idx_up.numel())
-        n_from_dn = counts[dn_rank][1] if dn_rank is not None else 0
-        n_from_up = counts[up_rank][0] if up_rank is not None else 0
-        if not any(c[0] or c[1] for c in counts):
-            return
-        fields = [s.pos, s.vel, s.rad, s.phase, s.fa, s.fr, s.dead, s.gid, s.rng, s.hash]
-        send_dn = [f[idx_dn].contiguous() for f in fields] if idx_dn.numel() else []
-        send_up = [f[idx_up].contiguous() for f in fields] if idx_up.numel() else []
-        recv_dn = [torch.empty((n_from_dn,) + tuple(f.shape[1:]), dtype=f.dtype, device=self.dev) for f in fields] if n_from_dn else []
-        recv_up = [torch.empty((n_from_up,) + tuple(f.shape[1:]), dtype=f.dtype, device=self.dev) for f in fields] if n_from_up else []
-        self._exchange(send_dn, send_up, recv_dn, recv_up)
-        n_leave = idx_dn.numel() + idx_up.numel()
-        n_new = n - n_leave + n_from_dn + n_from_up
-        assert n_new <= self.cap, "slab capacity exceeded"
-        if n_leave:
-            keep = torch.nonzero(~(down | up)).flatten()
-        for k, f in enumerate(fields):
-            parts = [f[keep] if n_leave else f[:n]]
-            if n_from_dn:
-                parts.append(recv_dn[k])
-            if n_from_up:
-                parts.append(recv_up[k])
-            if len(parts) > 1 or n_leave:
-                f[:n_new] = torch.cat(parts) if len(parts) > 1 else parts[0]
-        # a robot may cross one slab at most: every arrival must now sit in this slab's rows
-        if n_from_dn or n_from_up:
-            r2 = torch.div(s.hash[n - n_leave:n_new], self.GX, rounding_mode="floor")
-            assert bool(((r2 >= self.R_lo) & (r2 < self.R_hi)).all()), "a robot crossed more than one slab in one step"
-        self.stats["migrated"] += n_leave
-        self.n = n_new
+    def host_counts(self):
+        """the device counters (one small device-to-host copy; NOT part of a step)"""
+        return self.counts.cpu().numpy().astype(np.int64)
 
-    # ---- halo ----------------------------------------------------------------------------------------
-    def _halo(self):
-        n, HC = self.n, self.halo_cap
-        dn_rank, up_rank = self._neigh()
-        # slots of the first / last HALO_ROWS rows of the owned sorted range
-        self.be.lower_bounds(self.hash_sorted, n, self.bounds, self.bounds_out)
-        b0, b1 = (int(v) for v in self.bounds_out.tolist())
-        k_dn = b0 if dn_rank is not None else 0
-        k_up = (n - b1) if up_rank is not None else 0
-        counts = self._all_counts(k_dn, k_up)
-        n_lo = counts[dn_rank][1] if dn_rank is not None else 0
-        n_hi = counts[up_rank][0] if up_rank is not None else 0
-        assert n_lo <= HC and n_hi <= HC, "halo capacity exceeded"
-        own = slice(HC, HC + n)
-        self.hash_cat[own] = self.hash_sorted[:n]
-        send_dn = [self.pr[HC:HC + k_dn], self.svel[HC:HC + k_dn], self.hash_cat[HC:HC + k_dn]] if k_dn else []
-        send_up = [self.pr[HC + n - k_up:HC + n], self.svel[HC + n - k_up:HC + n], self.hash_cat[HC + n - k_up:HC + n]] if k_up else []
-        recv_dn = [self.pr[HC - n_lo:HC], self.svel[HC - n_lo:HC], self.hash_cat[HC - n_lo:HC]] if n_lo else []
-        recv_up = [self.pr[HC + n:HC + n + n_hi], self.svel[HC + n:HC + n + n_hi], self.hash_cat[HC + n:HC + n + n_hi]] if n_hi else []
-        self._exchange(send_dn, send_up, recv_dn, recv_up)
-        self.n_lo, self.n_hi = n_lo, n_hi
-        self.stats["halo"] += n_lo + n_hi
+    @property
+    def n(self):
+        return int(self.host_counts()[prs.SC_N])
+
+    @property
+    def stats(self):
+        c = self.host_counts()
+        return dict(migrated=int(c[prs.SC_STAT_MIG]), halo=int(c[prs.SC_STAT_HALO]))
+
+    def check(self):
+        """raises if a capacity was exceeded or a robot crossed two slabs (sticky device-side flags)"""
+        err = int(self.host_counts()[prs.SC_ERR])
+        if err:
+            raise RuntimeError(f"rank {self.rank}: " + "; ".join(m for bit, m in prs.SLAB_ERRORS.items() if err & bit))
 
     # ---- one step (Particlebot::update, particlebot.cpp:170-300, cut at the exchanges) ----------------
     def step(self, dt, sort_interval):
-        p, s, be = self.p, self.s, self.be
+        p, be = self.p, self.be
         time = self.time
         phase_step = self._gate(time, p.phase_update_interval, dt)
         sort_step = self._gate(time, sort_interval, dt) or not self.sorted_once
         if phase_step:
-            be.min_light_distance(s.pos, self.n, self.min_d)
+            be.min_light_distance(self.min_d)
             dist.all_reduce(self.min_d[:1], op=dist.ReduceOp.MIN, group=self.group)
-            be.update_phase(s.pos, s.phase, 2.0 * float(np.float32(p.min_radius)), self.min_d, self.n)
+            be.update_phase(2.0 * float(np.float32(p.min_radius)), self.min_d)
             if p.phase_std:
-                be.add_noise(s.rng, s.phase, float(p.phase_std), self.n)
-        be.k1(s, float(time), float(dt), self.n, sort_step)
+                be.add_noise(float(p.phase_std))
+        be.k1(float(time), float(dt), sort_step)
         if sort_step:
-            self._migrate()
-            be.sort(s.hash, self.hash_sorted, self.index_sorted, self.n, s.gid)
+            be.migrate_pack(self.mig_send[0], self.mig_send[1])
+            self._exchange(self.mig_send, self.mig_recv)
+            be.migrate_unpack(self.mig_recv[0], self.mig_recv[1])
+            be.sort()
             self.sorted_once = True
-        HC = self.halo_cap
-        be.gather(self.pr[HC:], self.svel[HC:], self.index_sorted, s, self.n)
-        self._halo()
-        start = HC - self.n_lo
-        n_tot = self.n_lo + self.n + self.n_hi
-        row_lo, row_hi = max(self.R_lo - HALO_ROWS, 0), min(self.R_hi + HALO_ROWS, self.GY)
-        be.cell_table(self.cs, self.ce, self.hash_cat[start:], n_tot, start, row_lo * self.GX, (row_hi - row_lo) * self.GX)
-        be.collide(s, self.pr, self.svel, self.cs, self.ce, HC, HC + self.n, float(dt))
+        be.gather()
+        be.halo_pack(self.halo_send[0], self.halo_send[1])
+        self._exchange(self.halo_send, self.halo_recv)
+        be.halo_unpack(self.halo_recv[0], self.halo_recv[1])
+        be.cell_table()
+        be.collide(float(dt))
         self.time = np.float32(time + np.float32(dt))
 
     # ---- assembling global arrays (tests, observables) -------------------------------------------------
@@ -332,8 +311,12 @@ def make_hex_slab(params, opt, geom, backend_factory, rank, world, device, seed,
     keep = (r >= rows[rank]) & (r < rows[rank + 1])
     be = backend_factory(params, geom["half"])
     n_expected = (nx * ny) // world
+    # halo = HALO_ROWS grid rows of ~nx * cell / lattice-row-pitch robots each; 1.6x head room
+    per_grid_row = nx * float(params.cellSize.y) / (pitch * 0.8660254)
+    halo_cap = int(1.6 * HALO_ROWS * per_grid_row) + 4096
     return SlabSim(params, opt, be, rank, world, device, pos[keep], ids[keep], rows,
-                   capacity=int(n_expected * 1.25) + 65536, group=group)
+                   capacity=int(n_expected * 1.25) + 65536, halo_cap=halo_cap,
+                   mig_cap=max(4096, int(0.5 * per_grid_row)), group=group)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -380,10 +363,12 @@ def bench_slabs(args, rank, world, local_rank):
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
-    own = torch.tensor([sim.n, sim.stats["migrated"], sim.stats["halo"]], dtype=torch.int64, device=dev)
+    sim.check()
+    st = sim.stats
+    own = torch.tensor([sim.n, st["migrated"], st["halo"]], dtype=torch.int64, device=dev)
     owns = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(owns, own)
-    finite = torch.tensor([int(torch.isfinite(sim.s.pos[: sim.n]).all())], device=dev)
+    finite = torch.tensor([int(torch.isfinite(sim.s.pos[: int(own[0])]).all())], device=dev)
     dist.all_reduce(finite, op=dist.ReduceOp.MIN)
     if rank == 0:
         value = n_total * args.steps / (total_ms_max * 1e-3)

@@ -22,7 +22,12 @@ STEPS = 40
 
 
 class OracleBackend:
-    """CPU stand-in for multigpu.CudaBackend (same call surface) on CPU torch tensors."""
+    """CPU stand-in for multigpu.CudaBackend (same call surface, same buffer formats) on CPU torch
+    tensors: numpy + the oracle's kernels.  Counts are read from / written to the same 16-word
+    array the device engine uses (include/prs_cabi.h PRS_SC_*)."""
+
+    MIG_FIELDS = [("pos", 0, 2), ("vel", 2, 2), ("rad", 4, 1), ("phase", 5, 1), ("fa", 6, 1), ("fr", 7, 1),
+                  ("dead", 8, 1), ("gid", 9, 1), ("hash", 10, 1), ("rng", 11, 12)]
 
     def __init__(self, params, world_half):
         self.p, self.half, self.L = params, world_half, ob.lib()
@@ -30,48 +35,146 @@ class OracleBackend:
         self.all_rng = (ob.RngState * n)()
         self.L.prso_curand_setup(self.all_rng, params.seed, n)
 
-    @staticmethod
-    def _a(t):
-        return t.numpy()
+    def bind(self, sim):
+        self.sim = sim
+        self.c = sim.counts.numpy()
+        self.log2gx = int(np.log2(sim.GX))
 
-    def k1(self, s, time, dt, n, do_hash):
+    # -- helpers
+    def _n(self):
+        return int(self.c[prs.SC_N])
+
+    def _field(self, name):
+        s = self.sim.s
+        return getattr(s, name).numpy()
+
+    def _store(self, buf, idx):
+        """records of local slots idx -> structure-of-arrays buffer (count word first)"""
+        b, cap = buf.numpy(), self.sim.mig_cap
+        b[0] = len(idx)
+        for name, w0, nw in self.MIG_FIELDS:
+            a = self._field(name)[idx].reshape(len(idx), nw).view(np.int32)
+            for w in range(nw):
+                b[1 + (w0 + w) * cap: 1 + (w0 + w) * cap + len(idx)] = a[:, w]
+
+    def _load(self, buf, dst):
+        b, cap = buf.numpy(), self.sim.mig_cap
+        c = len(dst)
+        for name, w0, nw in self.MIG_FIELDS:
+            a = self._field(name)
+            rec = np.stack([b[1 + (w0 + w) * cap: 1 + (w0 + w) * cap + c] for w in range(nw)], 1)
+            a[dst] = rec.view(a.dtype).reshape((c,) + a.shape[1:])
+
+    # -- ops
+    def rng_setup(self, n):
+        s = self.sim.s
+        words = np.frombuffer(bytes(self.all_rng), np.int32).reshape(-1, 12)
+        s.rng.numpy()[:n] = words[s.gid.numpy()[:n]]
+
+    def k1(self, time, dt, do_hash):
+        s, n = self.sim.s, self._n()
+        self.c[prs.SC_NLO:prs.SC_KEEPERS + 1] = 0
         P, L = C.byref(self.p), self.L
         if time >= 0:
             L.prso_update_rad(P, s.fa.numpy().ctypes.data, s.fr.numpy().ctypes.data, s.rad.numpy().ctypes.data,
                               s.phase.numpy().ctypes.data, time, dt, s.dead.numpy().ctypes.data, n)
         L.prso_integrate(P, s.pos.numpy().ctypes.data, s.vel.numpy().ctypes.data, s.rad.numpy().ctypes.data, dt, n, self.half)
         if do_hash:
-            L.prso_calc_hash(P, s.pos.numpy().ctypes.data, s.hash.numpy().ctypes.data, s.index.numpy().ctypes.data, n)
+            L.prso_calc_hash(P, s.pos.numpy().ctypes.data, s.hash.numpy().ctypes.data, s.scratch.numpy().ctypes.data, n)
 
-    def sort(self, keys_in, keys_out, vals_out, n, gid):
-        k = keys_in.numpy()[:n]
-        order = np.lexsort((gid.numpy()[:n], k))      # by hash, ties by global id
-        keys_out.numpy()[:n] = k[order]
-        vals_out.numpy()[:n] = order.astype(np.int32)
+    def migrate_pack(self, send_dn, send_up):
+        sim, n = self.sim, self._n()
+        rows = sim.s.hash.numpy()[:n].view(np.uint32) >> self.log2gx
+        dn, up = np.nonzero(rows < sim.R_lo)[0], np.nonzero(rows >= sim.R_hi)[0]
+        assert len(dn) <= sim.mig_cap and len(up) <= sim.mig_cap
+        assert (len(dn) == 0 or sim.rank > 0) and (len(up) == 0 or sim.rank < sim.world - 1)
+        self._store(send_dn, dn)
+        self._store(send_up, up)
+        keep = np.nonzero((rows >= sim.R_lo) & (rows < sim.R_hi))[0]
+        for name, _, _ in self.MIG_FIELDS:
+            a = self._field(name)
+            a[:len(keep)] = a[keep]
+        self.c[prs.SC_LEAVERS] = len(dn) + len(up)
+        self.c[prs.SC_MIGDN], self.c[prs.SC_MIGUP] = len(dn), len(up)
 
-    def gather(self, pr, svel, index, s, n):
-        idx = index.numpy()[:n]
-        out = pr.numpy()
-        out[:n, 0:2] = s.pos.numpy()[idx]
-        out[:n, 2] = s.rad.numpy()[idx]
-        out[:n, 3] = idx.astype(np.uint32).view(np.float32)
-        svel.numpy()[:n] = s.vel.numpy()[idx]
+    def migrate_unpack(self, recv_dn, recv_up):
+        sim = self.sim
+        n_kept = self._n() - int(self.c[prs.SC_LEAVERS])
+        c_dn = int(recv_dn.numpy()[0]) if sim.rank > 0 else 0
+        c_up = int(recv_up.numpy()[0]) if sim.rank < sim.world - 1 else 0
+        assert n_kept + c_dn + c_up <= sim.cap
+        self._load(recv_dn, np.arange(n_kept, n_kept + c_dn))
+        self._load(recv_up, np.arange(n_kept + c_dn, n_kept + c_dn + c_up))
+        rows = sim.s.hash.numpy()[n_kept:n_kept + c_dn + c_up].view(np.uint32) >> self.log2gx
+        assert np.all((rows >= sim.R_lo) & (rows < sim.R_hi)), "a robot crossed more than one slab"
+        self.c[prs.SC_STAT_MIG] += self.c[prs.SC_LEAVERS]
+        self.c[prs.SC_N] = n_kept + c_dn + c_up
 
-    def cell_table(self, cs, ce, hash_cat, n, slot0, cell_lo, ncells):
-        cs_, ce_, h = cs.numpy(), ce.numpy(), hash_cat.numpy()[:n]
-        cs_[cell_lo:cell_lo + ncells] = -1
-        if n == 0:
+    def sort(self):
+        sim, n = self.sim, self._n()
+        k = sim.s.hash.numpy()[:n].view(np.uint32)
+        order = np.lexsort((sim.s.gid.numpy()[:n], k))      # by hash, ties by global id
+        sim.hash_cat.numpy()[sim.halo_cap:sim.halo_cap + n] = k[order].view(np.int32)
+        sim.index_sorted.numpy()[:n] = order.astype(np.int32)
+
+    def gather(self):
+        sim, n, HC = self.sim, self._n(), self.sim.halo_cap
+        idx = sim.index_sorted.numpy()[:n]
+        out = sim.pr.numpy()
+        out[HC:HC + n, 0:2] = sim.s.pos.numpy()[idx]
+        out[HC:HC + n, 2] = sim.s.rad.numpy()[idx]
+        out[HC:HC + n, 3] = idx.astype(np.uint32).view(np.float32)
+        sim.svel.numpy()[HC:HC + n] = sim.s.vel.numpy()[idx]
+
+    def halo_pack(self, send_dn, send_up):
+        sim, n, HC, cap = self.sim, self._n(), self.sim.halo_cap, self.sim.halo_cap
+        hs = sim.hash_cat.numpy()[HC:HC + n].view(np.uint32)
+        k_dn = int(np.searchsorted(hs, min(sim.R_lo + multigpu.HALO_ROWS, sim.R_hi) * sim.GX, "left")) if sim.rank > 0 else 0
+        k_up = n - int(np.searchsorted(hs, max(sim.R_hi - multigpu.HALO_ROWS, sim.R_lo) * sim.GX, "left")) if sim.rank < sim.world - 1 else 0
+        assert k_dn <= cap and k_up <= cap
+        for buf, lo, cnt in ((send_dn, HC, k_dn), (send_up, HC + n - k_up, k_up)):
+            b = buf.numpy()
+            b[0] = cnt
+            pr = sim.pr.numpy()[lo:lo + cnt].view(np.int32)
+            sv = sim.svel.numpy()[lo:lo + cnt].view(np.int32)
+            for w in range(4):
+                b[1 + w * cap: 1 + w * cap + cnt] = pr[:, w]
+            for w in range(2):
+                b[1 + (4 + w) * cap: 1 + (4 + w) * cap + cnt] = sv[:, w]
+            b[1 + 6 * cap: 1 + 6 * cap + cnt] = sim.hash_cat.numpy()[lo:lo + cnt]
+        self.c[prs.SC_KDN], self.c[prs.SC_KUP] = k_dn, k_up
+
+    def halo_unpack(self, recv_dn, recv_up):
+        sim, n, HC, cap = self.sim, self._n(), self.sim.halo_cap, self.sim.halo_cap
+        n_lo = int(recv_dn.numpy()[0]) if sim.rank > 0 else 0
+        n_hi = int(recv_up.numpy()[0]) if sim.rank < sim.world - 1 else 0
+        for buf, lo, cnt in ((recv_dn, HC - n_lo, n_lo), (recv_up, HC + n, n_hi)):
+            b = buf.numpy()
+            sim.pr.numpy()[lo:lo + cnt] = np.stack([b[1 + w * cap: 1 + w * cap + cnt] for w in range(4)], 1).view(np.float32)
+            sim.svel.numpy()[lo:lo + cnt] = np.stack([b[1 + (4 + w) * cap: 1 + (4 + w) * cap + cnt] for w in range(2)], 1).view(np.float32)
+            sim.hash_cat.numpy()[lo:lo + cnt] = b[1 + 6 * cap: 1 + 6 * cap + cnt]
+        self.c[prs.SC_NLO], self.c[prs.SC_NHI] = n_lo, n_hi
+        self.c[prs.SC_STAT_HALO] += n_lo + n_hi
+
+    def cell_table(self):
+        sim, HC = self.sim, self.sim.halo_cap
+        n_lo, n, n_hi = int(self.c[prs.SC_NLO]), self._n(), int(self.c[prs.SC_NHI])
+        slot0, n_tot = HC - n_lo, n_lo + n + n_hi
+        cs_, ce_ = sim.cs.numpy(), sim.ce.numpy()
+        h = sim.hash_cat.numpy()[slot0:slot0 + n_tot].view(np.uint32)
+        r0, r1 = max(sim.R_lo - multigpu.HALO_ROWS, 0), min(sim.R_hi + multigpu.HALO_ROWS, sim.GY)
+        cs_[r0 * sim.GX:r1 * sim.GX] = -1
+        if n_tot == 0:
             return
         first = np.nonzero(np.r_[True, h[1:] != h[:-1]])[0]
         cs_[h[first]] = slot0 + first
         ce_[h[first[1:] - 1]] = slot0 + first[1:]
-        ce_[h[-1]] = slot0 + n
+        ce_[h[-1]] = slot0 + n_tot
 
-    def lower_bounds(self, hash_sorted, n, bounds, out):
-        out.numpy()[:] = np.searchsorted(hash_sorted.numpy()[:n], bounds.numpy(), "left").astype(np.int32)
-
-    def collide(self, s, pr, svel, cs, ce, k_begin, k_end, dt):
-        prn = pr.numpy()                                  # whole buffer: the upper halo lies beyond k_end
+    def collide(self, dt):
+        sim, s, HC = self.sim, self.sim.s, self.sim.halo_cap
+        k_begin, k_end = HC, HC + self._n()
+        prn = sim.pr.numpy()                              # whole buffer: the upper halo lies beyond k_end
         spos = np.ascontiguousarray(prn[:, 0:2])
         srad = np.ascontiguousarray(prn[:, 2])
         cap = s.vel.shape[0]
@@ -80,26 +183,25 @@ class OracleBackend:
         vel = np.zeros((cap + 1, 2), np.float32)
         fa, fr = np.zeros(cap + 1, np.float32), np.zeros(cap + 1, np.float32)
         fr[:cap] = s.fr.numpy()
-        sv = np.ascontiguousarray(svel.numpy())
+        sv = np.ascontiguousarray(sim.svel.numpy())
         self.L.prso_collide(C.byref(self.p), vel.ctypes.data, fa.ctypes.data, fr.ctypes.data, spos.ctypes.data, sv.ctypes.data,
-                            srad.ctypes.data, index.ctypes.data, cs.numpy().ctypes.data, ce.numpy().ctypes.data, k_end, dt)
+                            srad.ctypes.data, index.ctypes.data, sim.cs.numpy().ctypes.data, sim.ce.numpy().ctypes.data, k_end, dt)
         own = index[k_begin:]
         s.vel.numpy()[own] = vel[own]
         s.fa.numpy()[own] = fa[own]
         s.fr.numpy()[own] = fr[own]
 
-    def min_light_distance(self, pos, n, out):
-        out.numpy()[0] = self.L.prso_min_light_distance(C.byref(self.p), pos.numpy().ctypes.data, n) if n else 3e38
+    def min_light_distance(self, out):
+        n = self._n()
+        out.numpy()[0] = self.L.prso_min_light_distance(C.byref(self.p), self.sim.s.pos.numpy().ctypes.data, n) if n else 3e38
 
-    def update_phase(self, pos, phase, spacing, min_d, n):
-        self.L.prso_update_phase(C.byref(self.p), pos.numpy().ctypes.data, phase.numpy().ctypes.data, spacing, float(min_d[0]), n)
+    def update_phase(self, spacing, min_d):
+        s = self.sim.s
+        self.L.prso_update_phase(C.byref(self.p), s.pos.numpy().ctypes.data, s.phase.numpy().ctypes.data, spacing, float(min_d[0]), self._n())
 
-    def rng_setup(self, rng, gid, n):
-        words = np.frombuffer(bytes(self.all_rng), np.int32).reshape(-1, 12)
-        rng.numpy()[:n] = words[gid.numpy()[:n]]
-
-    def add_noise(self, rng, phase, std, n):
-        self.L.prso_add_normal_noise(rng.numpy().ctypes.data, phase.numpy().ctypes.data, std, n)
+    def add_noise(self, std):
+        s = self.sim.s
+        self.L.prso_add_normal_noise(s.rng.numpy().ctypes.data, s.phase.numpy().ctypes.data, std, self._n())
 
 
 def _config():
@@ -122,13 +224,15 @@ def _worker(rank, world, port, out_path):
     torch.set_num_threads(1)
     p, o, geom = _config()
     sim = multigpu.make_hex_slab(p, o, geom, OracleBackend, rank, world, torch.device("cpu"), 5555, 0.01 * p.max_radius)
-    sim.s.vel[: sim.n] = torch.from_numpy(_initial_velocity(sim.s.gid[: sim.n].numpy()))   # makes robots cross slabs
+    n0 = sim.n
+    sim.s.vel[:n0] = torch.from_numpy(_initial_velocity(sim.s.gid[:n0].numpy()))   # makes robots cross slabs
     snaps = {}
     for k in range(1, STEPS + 1):
         sim.step(o.timestep, o.timestep)
         if k in (1, 5, STEPS):
             snaps[k] = sim.gather_global(NX * NY)
     if rank == 0:
+        sim.check()
         np.savez(out_path, migrated=sim.stats["migrated"], halo=sim.stats["halo"],
                  **{f"{key}_{k}": v for k, g in snaps.items() for key, v in g.items()})
     stats = [None] * world

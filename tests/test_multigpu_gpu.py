@@ -38,12 +38,14 @@ def _worker(rank, world, port, out_path):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     p, o, geom = _config()
     sim = multigpu.make_hex_slab(p, o, geom, multigpu.CudaBackend, rank, world, dev, 5555, 0.01 * p.max_radius)
-    sim.s.vel[: sim.n] = torch.from_numpy(_initial_velocity(sim.s.gid[: sim.n].cpu().numpy())).to(dev)
+    n0 = sim.n
+    sim.s.vel[:n0] = torch.from_numpy(_initial_velocity(sim.s.gid[:n0].cpu().numpy())).to(dev)
     snaps = {}
     for k in range(1, STEPS + 1):
         sim.step(o.timestep, o.timestep)
         if k in (1, 10, STEPS):
             snaps[k] = sim.gather_global(NX * NY)
+    sim.check()      # capacity / "crossed two slabs" flags raised on the device
     stats = [None] * world
     dist.all_gather_object(stats, (sim.n, sim.stats["migrated"], sim.stats["halo"]))
     if rank == 0:
