@@ -121,6 +121,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json)"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(kernel)
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -129,8 +137,9 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_throughput(p, o, geom, pos0, steps, threads, warm=1):
-    """particle-steps/s of the CPU oracle port on this swarm (test infrastructure used as baseline)."""
+def cpu_oracle_throughput(p, o, geom, pos0, steps, threads, warm=1, min_seconds=0.0):
+    """particle-steps/s of the CPU oracle port on this swarm (test infrastructure used as baseline);
+    runs `steps` steps, then keeps stepping until min_seconds of CPU work have been timed"""
     from oracle import binding as ob
     L = ob.lib()
     L.prso_set_threads(threads)
@@ -140,12 +149,14 @@ def cpu_oracle_throughput(p, o, geom, pos0, steps, threads, warm=1):
     for _ in range(warm):
         s.update(o.timestep, o.timestep)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    done = 0
+    while done < steps or time.perf_counter() - t0 < min_seconds:
         s.update(o.timestep, o.timestep)
+        done += 1
     dt = time.perf_counter() - t0
     s.close()
     L.prso_set_threads(1)
-    return p.nCells * steps / dt, dt
+    return p.nCells * done / dt, dt, done
 
 
 def hex_positions(p, geom):
@@ -176,6 +187,41 @@ def hex_positions(p, geom):
     return np.stack([x, y], 1).astype(np.float32)
 
 
+
+def timed_steps(torch, sim, dt, sort_interval, steps, warmup, flush):
+    """ms per step of sim.update over `steps` steps (CUDA events on the current stream, L2 flushed between steps)"""
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        sim.update(dt, sort_interval)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(stream)
+        sim.update(dt, sort_interval)
+        b.record(stream)
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def ref_cuda_block(torch, prs, flush, steps=30, warmup=5):
+    """The reference's OWN kernels (oracle/_ref, compiled verbatim for sm_100a) beside this repo's path on
+    R1 — the largest hex block the reference's hard-coded +-64 world holds (640x640 robots)."""
+    from oracle import binding as ob
+    if not os.path.exists(ob.REFCUDA_PATH):
+        return {"unavailable": "oracle/_ref/libprs_refcuda.so not built"}
+    out = {"workload": "R1: 409600 robots, hex 640x640 pitch 0.17, reference world +-64, grid 512^2, sort every step"}
+    for name, backend, ext in (("reference_kernels", prs.BACKEND_EXTERNAL, ob.REFCUDA_PATH), ("this_repo", prs.BACKEND_FUSED, None)):
+        p, o, geom = swarm_config(prs, 0, world64=True, nx=640, ny=640)
+        sim = prs.Simulation(p, geom["half"], backend, ext)
+        sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], JITTER_FRAC * p.max_radius, SEED)
+        ms = timed_steps(torch, sim, o.timestep, o.timestep, steps, warmup, flush)
+        sim.close()
+        out[name] = {"ms_per_step": ms, "value": p.nCells / (ms * 1e-3), "unit": "particle-steps/s"}
+    out["speedup"] = out["reference_kernels"]["ms_per_step"] / out["this_repo"]["ms_per_step"]
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference_cpu(args):
     """--impl reference: the reference has no CPU implementation; this times the oracle port with
@@ -187,7 +233,7 @@ def run_reference_cpu(args):
     log2n = args.robots_log2 or (20 if args.gpus == 1 else 26)
     # probe at 2^14 robots, then take the largest power of four <= the workload that fits the budget
     p, o, geom = swarm_config(prs, 14)
-    rate, _ = cpu_oracle_throughput(p, o, geom, hex_positions(p, geom), 3, threads)
+    rate, _, _ = cpu_oracle_throughput(p, o, geom, hex_positions(p, geom), 3, threads)
     sample = 14
     while sample + 2 <= log2n and (1 << (sample + 2)) * (args.steps + args.warmup) / rate < budget_s:
         sample += 2
@@ -209,7 +255,7 @@ def run_reference_cpu(args):
     line = {
         "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"S1 synthetic hex swarm (2^{log2n} robots), CPU sample 2^{sample}", "sort_interval": "timestep"},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -317,7 +363,8 @@ def run_gpu(args):
                                 "frac_of_hbm_peak": (gbs / peak) if gbs else None}
         dom = max(stages, key=lambda k: stages[k]["avg_us"])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": stages[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                    "frac": stages[dom]["frac_of_hbm_peak"], "traffic": ncu_traffic(dom) if log2n == 20 and not r1 else None,
+                    "peak_source": peak_src,
                     "note": "collide is FP32/MUFU-issue-bound (IEEE div/sqrt per neighbour pair), not HBM-bound; "
                             "see roofline_step for the whole-step HBM fraction"}
     step_gbs = b_alg * value / 1e9
@@ -352,15 +399,20 @@ def run_gpu(args):
     cpu = None
     if not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
-        cpu_log2 = min(log2n, 18)
+        cpu_log2 = min(log2n, 20)
         pc, oc, gc = swarm_config(prs, cpu_log2)
-        rate, dt = cpu_oracle_throughput(pc, oc, gc, hex_positions(pc, gc), 4, threads)
+        rate, dt, done = cpu_oracle_throughput(pc, oc, gc, hex_positions(pc, gc), 4, threads, min_seconds=12.0)
         cpu = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-               "sample": f"same lattice cut to 2^{cpu_log2} robots, 4 steps after 1 warm-up, sort every step ({dt:.1f} s)"}
+               "sample": f"same lattice at 2^{cpu_log2} robots, {done} steps after 1 warm-up, sort every step ({dt:.1f} s of "
+                         f"{threads}-thread OpenMP work; oracle/prs_oracle.cpp)"}
+
+    ref_cuda_cmp = None
+    if not ref_cuda and not args.no_ref_cuda:
+        ref_cuda_cmp = ref_cuda_block(torch, prs, flush)
 
     line = {
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{geom['name']}: {n} robots, hex {geom['nx']}x{geom['ny']} pitch {geom['pitch']}, "
                                f"world +-{geom['half']:g}, grid {geom['grid']}^2, light {geom['light']}",
@@ -368,7 +420,7 @@ def run_gpu(args):
                    "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)"},
         "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
-        "stages": stages, "cpu_baseline": cpu, "state_finite": finite,
+        "stages": stages, "cpu_baseline": cpu, "ref_cuda": ref_cuda_cmp, "state_finite": finite,
     }
     if ref_cuda:
         line["impl"] = "ref-cuda"
@@ -386,6 +438,7 @@ def main():
     ap.add_argument("--sort-interval", type=float, default=None)
     ap.add_argument("--collide-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-kernels-on-R1 comparison block")
     ap.add_argument("--workload", default="s1", choices=["s1", "r1"],
                     help="s1: 2^robots_log2 hex swarm in its own world; r1: 640x640 swarm in the reference's +-64 world")
     args = ap.parse_args()

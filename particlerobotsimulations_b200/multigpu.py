@@ -365,10 +365,52 @@ def bench_slabs(args, rank, world, local_rank):
     total_ms_max = float(t.item())
     sim.check()
     st = sim.stats
-    own = torch.tensor([sim.n, st["migrated"], st["halo"]], dtype=torch.int64, device=dev)
+    n_own = sim.n
+    own = torch.tensor([n_own, st["migrated"], st["halo"]], dtype=torch.int64, device=dev)
     owns = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(owns, own)
-    finite = torch.tensor([int(torch.isfinite(sim.s.pos[: int(own[0])]).all())], device=dev)
+
+    # ---- per-stage event timing on this rank (kernels only; the NCCL transfers sit between the stages) ----
+    lib.prs_stage_timing(1)
+    for _ in range(min(args.steps, 10)):
+        flush.fill_(1)
+        sim.step(o.timestep, sort_interval)
+    ms = (C.c_float * 6)()
+    cnt = (C.c_uint * 6)()
+    lib.prs_stage_times(ms, cnt)
+    lib.prs_stage_timing(0)
+    per_bytes, b_alg, passes = bench.algorithmic_bytes(p, sort_interval <= o.timestep)
+    peak, peak_src = bench.measured_peak()
+    stages = {}
+    for i, name in enumerate(bench.STAGES):
+        if cnt[i]:
+            per_step_us = 1e3 * ms[i] / min(args.steps, 10)
+            gbs = per_bytes[name] * n_own / (per_step_us * 1e-6) / 1e9 if per_bytes[name] else None
+            stages[name] = {"us_per_step": per_step_us, "alg_bytes_per_robot": per_bytes[name], "achieved_GBps": gbs,
+                            "frac_of_hbm_peak": (gbs / peak) if gbs else None}
+
+    # ---- e2e: every rank's pos/vel/rad come from pinned host memory and go back to it every step ----
+    h = {k: torch.empty((n_own,) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in
+         (("pos", sim.s.pos), ("vel", sim.s.vel), ("rad", sim.s.rad))}
+    for k, v in h.items():
+        v.copy_(getattr(sim.s, k)[:n_own])
+    e2e_steps = max(3, min(args.steps, 20))
+    torch.cuda.synchronize()
+    dist.barrier()
+    import time as _time
+    t0 = _time.perf_counter()
+    for _ in range(e2e_steps):
+        for k, v in h.items():
+            getattr(sim.s, k)[:n_own].copy_(v, non_blocking=True)
+        sim.step(o.timestep, sort_interval)
+        for k, v in h.items():
+            v.copy_(getattr(sim.s, k)[:n_own], non_blocking=True)
+        torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = torch.tensor([_time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    finite = torch.tensor([int(torch.isfinite(sim.s.pos[:n_own]).all())], device=dev)
     dist.all_reduce(finite, op=dist.ReduceOp.MIN)
     if rank == 0:
         value = n_total * args.steps / (total_ms_max * 1e-3)
@@ -379,13 +421,20 @@ def bench_slabs(args, rank, world, local_rank):
         line = {
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "strong" if args.robots_log2 else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{geom['name']}: {n_total} robots, hex {geom['nx']}x{geom['ny']} pitch {geom['pitch']}, "
                                    f"world +-{geom['half']:g}, grid {geom['grid']}^2, {world} slabs of grid rows",
                        "sort_interval": "timestep (sort every step)", "collide_mode": "exact",
                        "l2": "flushed between timed steps (256 MiB write)", "halo_rows": HALO_ROWS},
-            "e2e": None, "gpu_launches": launches, "clocks": clocks,
+            "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 20 * n_total,
+                    "d2h_bytes_per_step": 20 * n_total, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "what": "per rank: pos/vel/rad of the owned robots from pinned host -> device, SlabSim.step, device -> pinned host"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": ({"bound": "hbm", "kernel": "collide (rank 0)", "achieved": stages["collide"]["achieved_GBps"], "peak": peak,
+                          "unit": "GB/s", "frac": stages["collide"]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                          "note": "collide is FP32/MUFU-issue-bound, not HBM-bound; see roofline_step"} if "collide" in stages else None),
+            "stages_rank0": stages, "cpu_baseline": None,
             "roofline_step": {"bound": "hbm", "alg_bytes_per_particle_step": b_alg, "radix_passes": passes,
                               "achieved": b_alg * value / 1e9, "peak": peak * world, "unit": "GB/s",
                               "frac": b_alg * value / 1e9 / (peak * world), "peak_source": peak_src + f" x {world} GPUs"},
