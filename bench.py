@@ -76,9 +76,11 @@ def algorithmic_bytes(p, sort_every_step=True):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  Started before the warm-up (the tool
+    needs ~0.1 s to come up), polled every 20 ms; `mark()` brackets the timed region and the report
+    uses the samples inside it (all samples under load if the region was shorter than the polling)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -86,11 +88,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -98,27 +101,43 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """call at the start and at the end of the timed region"""
+        if self.t0 is None:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2])); mx.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        inside = [r for r in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.02]
+        scope = "timed region"
+        if len(inside) < 2:
+            inside, scope = self.lines, "warm-up + timed region + stage timing (timed region shorter than the polling interval)"
+        sm, mx, reasons = parse(inside)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def ncu_traffic(kernel):
@@ -310,13 +329,14 @@ def run_gpu(args):
     def step():
         sim.update(o.timestep, sort_interval)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, L2 flushed between steps (outside the event pairs) ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     lib.prs_launch_count(1)
     torch.cuda.synchronize()
@@ -326,6 +346,7 @@ def run_gpu(args):
         step()
         b.record(stream)
     torch.cuda.synchronize()
+    sampler.mark()
     launches = int(lib.prs_launch_count(0))
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(np.sum(step_ms))
@@ -337,7 +358,6 @@ def run_gpu(args):
     b.record(stream)
     torch.cuda.synchronize()
     b2b_ms = a.elapsed_time(b)
-    clocks = sampler.stop()
 
     value = n * args.steps / (total_ms * 1e-3)
 
@@ -367,6 +387,7 @@ def run_gpu(args):
                     "peak_source": peak_src,
                     "note": "collide is FP32/MUFU-issue-bound (IEEE div/sqrt per neighbour pair), not HBM-bound; "
                             "see roofline_step for the whole-step HBM fraction"}
+    clocks = sampler.stop()
     step_gbs = b_alg * value / 1e9
     roofline_step = {"bound": "hbm", "alg_bytes_per_particle_step": b_alg, "radix_passes": passes, "achieved": step_gbs,
                      "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "peak_source": peak_src}

@@ -130,6 +130,14 @@ typedef struct {
   float *sortedPR;
 } prs_step_buffers;
 void prs_fused_step(const prs_step_buffers *b, float time, float deltaTime, int do_sort);
+/* The fused step sorts by cell BINNING (counting sort whose histogram scan is the cell table,
+ * csrc/prs_cellbin.cuh) while the swarm is known to be sparse (<= 64 robots in the fullest cell,
+ * tracked asynchronously) and numCells <= 16 * nCells; otherwise by the onesweep radix sort.  Both
+ * give identical results.  Callers that rewrite positions through their own copies call
+ * prs_bin_invalidate(); prs_bin_set_mode: 0 auto (default), 1 onesweep only, 2 binning only. */
+void prs_bin_invalidate(void);
+void prs_bin_set_mode(int mode);
+int prs_bin_active(void);
 
 /* ---- slab (multi-GPU) engine: the fused step cut where ranks exchange robots, every count kept
  * on the device (csrc/prs_slab.cuh; particlerobotsimulations_b200/multigpu.py drives it;

@@ -128,6 +128,7 @@ SIGNATURES = {
     "prs_slab_add_noise": (None, [_VP, _F]),
     "prs_unpack_sorted": (None, [_VP, _VP, _VP, _U]), "prs_selftest_div": (C.c_ulonglong, [_VP, _VP, _U]),
     "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
+    "prs_bin_invalidate": (None, []), "prs_bin_set_mode": (None, [_I]), "prs_bin_active": (_I, []),
     "prs_params_defaults": (None, [C.POINTER(SimParams), C.POINTER(RunOptions)]),
     "prs_params_load_cfg": (_I, [C.c_char_p, C.POINTER(SimParams), C.POINTER(RunOptions)]),
     "prs_params_derive_grid": (None, [C.POINTER(SimParams)]),

@@ -1,0 +1,202 @@
+/*
+ * prs_cellbin.cuh — cell binning: the fused step's route from robots to (sorted hash, sorted index,
+ * cellStart, cellEnd) WITHOUT a multi-pass radix sort.  Included by prs_kernels.cu.
+ *
+ * What must come out (bit-exact): the pairs (hash, index) stably sorted by hash —
+ * i.e. robots of one cell in ascending original index (thrust::sort_by_key, particlebot_cuda.cu:377) —
+ * and the reference's cell table (cellStart = 0xffffffff for empty cells, cellEnd untouched for them,
+ * kernel_impl.cuh:469-538).  The keys are cell numbers, so the sort is a counting sort whose
+ * histogram IS the cell table:
+ *
+ *   K1  (k_control_integrate_hash<.., COUNT>)  hash h of each robot + arrival ticket within its cell:
+ *        ticket = atomicAdd(&cellCount[h], 1)                   (order of arrival: arbitrary)
+ *   scan (k_cell_tile_sums, k_cell_apply)  over the C cells:
+ *        cellStart[c] = exclusive sum (or 0xffffffff), cellEnd[c] = start + count (non-empty cells
+ *        only), cellCount[c] = 0 for the next step — this replaces the cudaMemset of the table
+ *   scatter (k_cell_scatter)  robot i -> slot cellStart[h] + ticket: arrival-ordered index list
+ *   K3  (k_reorder_binned)  slot k ranks its index among the few indices of its cell (ascending
+ *        original index = the stable order), writes hash/index and gathers the packed sorted copy
+ *
+ * HBM bytes per robot: K1 +4 (ticket) ; scan 16*C/N ; scatter 8 + 4 (table lookup) + 8 ; K3 +8 —
+ * against 4 + 16 per radix pass, and three dependent tile-chained passes fewer.  The general
+ * onesweep sort (prs_onesweep.cuh) stays behind sortParticlebots / prs_sort_pairs, the per-call
+ * path and the slab path, and is the fused path's route whenever binning is not admitted:
+ * many more cells than robots, or crowded cells (the in-cell ranking is quadratic in the cell
+ * population; the largest population is tracked on the device and reported to the host one step
+ * late, see prs_fused_step).
+ */
+#pragma once
+
+namespace prs_bin {
+
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr uint32_t MAX_RANKED_CELL = 1024; /* populations above this are not ranked (error flag) */
+
+/* The scan over the C cells is two kernels without any inter-block waiting (a single-pass chained
+ * scan was tried first: with ~450 tiles in flight every tile spent most of its life waiting for
+ * its predecessors' aggregates, 44 us for 4 M cells):
+ *   k_cell_tile_sums  tile sums + fullest cell; the LAST block to finish scans the tile sums
+ *   k_cell_apply      exclusive sums inside each tile + the tile's offset -> cellStart / cellEnd,
+ *                     counters back to zero
+ * scratch: [0] blocks done, [1] largest cell population, [2] error flag, [4..4+T) tile sums ->
+ * exclusive tile offsets */
+__device__ __forceinline__ void load_counts(const uint32_t *cellCount, uint32_t c0, uint32_t C, uint32_t (&cnt)[SCAN_ITEMS]) {
+  if (c0 + SCAN_ITEMS <= C) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(cellCount + c0), b = *reinterpret_cast<const uint4 *>(cellCount + c0 + 4);
+    cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w; cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) cnt[i] = (c0 + i < C) ? cellCount[c0 + i] : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch, uint32_t num_tiles) {
+  __shared__ uint32_t s_sum[SCAN_THREADS / 32], s_max[SCAN_THREADS / 32];
+  __shared__ bool s_last;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t cnt[SCAN_ITEMS];
+  load_counts(cellCount, blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS, C, cnt);
+  uint32_t sum = 0, mx = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { sum += cnt[i]; mx = max(mx, cnt[i]); }
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) { s_sum[warp] = sum; s_max[warp] = mx; }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t total = 0, bmax = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) { total += s_sum[w]; bmax = max(bmax, s_max[w]); }
+    scratch[4 + blockIdx.x] = total;
+    /* fullest cell: one atomic per tile at most, none once the running maximum is reached */
+    if (bmax > *reinterpret_cast<volatile uint32_t *>(&scratch[1])) atomicMax(&scratch[1], bmax);
+    __threadfence();
+    s_last = atomicAdd(&scratch[0], 1u) == num_tiles - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  /* last block: exclusive scan of the tile sums, in place */
+  __threadfence();
+  volatile uint32_t *sums = scratch + 4;
+  __shared__ uint32_t s_carry;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < num_tiles; base += SCAN_THREADS) {
+    const uint32_t i = base + tid;
+    const uint32_t v = (i < num_tiles) ? sums[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) s_sum[warp] = inc;
+    __syncthreads();
+    uint32_t before = s_carry, total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+      const uint32_t t = s_sum[w];
+      before += (w < (int)warp) ? t : 0u;
+      total += t;
+    }
+    if (i < num_tiles) sums[i] = before + inc - v;
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
+             const uint32_t *__restrict__ scratch) {
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t c0 = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
+  const uint32_t tile_offset = scratch[4 + blockIdx.x];
+  uint32_t cnt[SCAN_ITEMS];
+  load_counts(cellCount, c0, C, cnt);
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) sum += cnt[i];
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t before = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; w++) before += (w < (int)warp) ? s_warp[w] : 0u;
+  uint32_t run = tile_offset + before + (inc - sum);
+  uint32_t st[SCAN_ITEMS];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    st[i] = cnt[i] ? run : 0xffffffffu;
+    if (cnt[i] && c0 + i < C) cellEnd[c0 + i] = run + cnt[i]; /* empty cells keep their stale cellEnd (reference) */
+    run += cnt[i];
+  }
+  if (c0 + SCAN_ITEMS <= C) {
+    *reinterpret_cast<uint4 *>(cellStart + c0) = make_uint4(st[0], st[1], st[2], st[3]);
+    *reinterpret_cast<uint4 *>(cellStart + c0 + 4) = make_uint4(st[4], st[5], st[6], st[7]);
+    if (sum) { /* counters back to zero for the next step */
+      *reinterpret_cast<uint4 *>(cellCount + c0) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4 *>(cellCount + c0 + 4) = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+      if (c0 + i < C) { cellStart[c0 + i] = st[i]; cellCount[c0 + i] = 0u; }
+  }
+}
+
+/* robot i goes to slot cellStart[hash] + ticket of the arrival-ordered list */
+__global__ void __launch_bounds__(256)
+k_cell_scatter(const uint32_t *__restrict__ hash, const uint32_t *__restrict__ ticket, const uint32_t *__restrict__ cellStart,
+               uint32_t *__restrict__ hash_by_slot, uint32_t *__restrict__ index_by_slot, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t h = hash[i];
+  const uint32_t slot = __ldg(cellStart + h) + ticket[i];
+  hash_by_slot[slot] = h;
+  index_by_slot[slot] = i;
+}
+
+/* K3 of the binned route: stable order inside each cell + the packed sorted copy.
+ * Slot k holds some robot `a` of cell h; its place in the stable order is cellStart[h] + (number
+ * of robots of the cell with a smaller original index). */
+__global__ void __launch_bounds__(256)
+k_reorder_binned(const uint32_t *__restrict__ hash_by_slot, const uint32_t *__restrict__ index_by_slot,
+                 const uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ cellEnd, uint32_t *__restrict__ hash,
+                 uint32_t *__restrict__ index, float4 *__restrict__ sortedPR, float2 *__restrict__ sortedVel,
+                 const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad, uint32_t n,
+                 uint32_t *scratch) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t h = hash_by_slot[k];
+  const uint32_t a = index_by_slot[k];
+  const float2 p = pos[a];
+  const float2 v = vel[a];
+  const float r = rad[a];
+  const uint32_t s = __ldg(cellStart + h), e = __ldg(cellEnd + h);
+  uint32_t below = 0;
+  if (e - s <= MAX_RANKED_CELL) {
+    for (uint32_t j = s; j < e; j++) below += (index_by_slot[j] < a) ? 1u : 0u;
+  } else {
+    atomicOr(&scratch[2], 1u); /* crowded beyond what the guard admits: the host fails loudly */
+    below = k - s;
+  }
+  const uint32_t dst = s + below;
+  hash[k] = h; /* every slot of the cell carries the cell's key */
+  index[dst] = a;
+  sortedPR[dst] = make_float4(p.x, p.y, r, __uint_as_float(a));
+  sortedVel[dst] = v;
+}
+
+inline size_t scan_scratch_words(uint32_t C) { return 4 + (size_t)(C + SCAN_TILE - 1) / SCAN_TILE; }
+
+}  // namespace prs_bin

@@ -9,6 +9,19 @@
 #include "prs_onesweep.cuh"
 #include <vector>
 
+/* guard state of the binned (counting-sort) route of the fused step, see prs_fused_step */
+struct PrsBinState {
+  uint32_t *cellCount = nullptr, *scratch = nullptr;
+  size_t cap_cells = 0;
+  int mode = 0;               /* 0 auto, 1 never, 2 always */
+  bool admitted = false;      /* the swarm is known to be sparse enough */
+  unsigned generation = 0;    /* bumped whenever positions are rewritten behind the library's back */
+  uint32_t *h_report = nullptr; /* pinned: [0] largest cell population, [1] error flag */
+  cudaEvent_t report_event = nullptr;
+  bool report_pending = false;
+  unsigned report_generation = 0;
+};
+
 struct PrsHostState {
   cudaStream_t stream = 0;            /* legacy default stream, like the reference */
   unsigned long long launches = 0;    /* kernels launched by this library */
@@ -17,6 +30,7 @@ struct PrsHostState {
   float world_half = 64.0f;           /* reference wall (kernel_impl.cuh:75-97) */
   int collide_mode = 0;               /* 0 exact, 1 fast */
   prs_sort::Workspace sort_ws;
+  PrsBinState bin;
   int sort_threads = 0;               /* tile shape of k_onesweep: 512 / 1024 threads, 0 = by size */
   unsigned long long *sort_timeline = nullptr; /* tuning aid, see prs_sort_set_timeline */
   /* optional per-stage CUDA-event timing of the fused step (bench.py's roofline numbers) */

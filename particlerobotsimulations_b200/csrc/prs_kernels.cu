@@ -25,6 +25,7 @@
 #include "prs_host_state.h"
 
 #include "prs_collide.cuh"
+#include "prs_cellbin.cuh"
 
 using namespace prs;
 
@@ -242,13 +243,15 @@ k_update_rad(const float *__restrict__ fa, const float *__restrict__ fr, float *
 }
 
 /* Fused K1: controller -> integrate -> (hash) with one read and one write of each robot
- * (north_star (4); SURVEY.md §8d K1: 60 B per robot on sort steps). */
-template <bool DO_SORT>
+ * (north_star (4); SURVEY.md §8d K1: 60 B per robot on sort steps).  COUNT: the robot also takes
+ * its arrival ticket in its cell (cell binning, prs_cellbin.cuh) — index[i] then holds the ticket. */
+template <bool DO_SORT, bool COUNT = false>
 __global__ void __launch_bounds__(256)
 k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, float *__restrict__ rad,
                          const float *__restrict__ phase, const float *__restrict__ fa, const float *__restrict__ fr,
                          const int *__restrict__ dead, uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
-                         float time, float dt, int run_controller, uint32_t n, const uint32_t *__restrict__ n_dev) {
+                         float time, float dt, int run_controller, uint32_t n, const uint32_t *__restrict__ n_dev,
+                         uint32_t *__restrict__ cellCount = nullptr) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
   if (i >= n) return;
@@ -267,8 +270,31 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
   if (v.x != v0.x || v.y != v0.y) vel[i] = v;
   if (DO_SORT) {
     const int2 g = cell_of(p.x, p.y);
-    hash[i] = cell_hash(g.x, g.y);
-    index[i] = i;
+    const uint32_t h = cell_hash(g.x, g.y);
+    hash[i] = h;
+    index[i] = COUNT ? atomicAdd(&cellCount[h], 1u) : i;
+  }
+}
+
+/* largest cell population of a sorted key array (guard of the binned route, see prs_fused_step) */
+__global__ void __launch_bounds__(256)
+k_max_population(const uint32_t *__restrict__ hash, const uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ cellEnd,
+                 uint32_t n, uint32_t *__restrict__ out_max) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t m = 0;
+  if (k < n) {
+    const uint32_t h = hash[k];
+    if (k == 0 || hash[k - 1] != h) m = cellEnd[h] - cellStart[h];
+  }
+  __shared__ uint32_t s_m[8];
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) m = max(m, s_m[w]);
+    /* one atomic per block at most, none once the running maximum is reached */
+    if (m > *reinterpret_cast<volatile uint32_t *>(out_max)) atomicMax(out_max, m);
   }
 }
 
@@ -589,6 +615,9 @@ void freeArray(void *devPtr) { PRS_CUDA(cudaFree(devPtr)); }
 void threadSync(void) { PRS_CUDA(cudaDeviceSynchronize()); }
 
 void copyArrayToDevice(void *device, const void *host, int offset, int size) {
+  /* state may change behind the fused step's back: the binned route re-earns its admission */
+  g_prs.bin.admitted = false;
+  g_prs.bin.generation++;
   PRS_CUDA(cudaMemcpyAsync((char *)device + offset, host, (size_t)size, cudaMemcpyHostToDevice, g_prs.stream));
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
 }
@@ -767,10 +796,99 @@ void prs_sort_pairs(const unsigned *in_keys, const unsigned *in_vals, unsigned *
   sort_pairs(in_keys, in_vals, out_keys, out_vals, n, key_bits, false);
 }
 
+/* ---- guard of the binned route ----
+ * The in-cell ranking of prs_cellbin.cuh is quadratic in the cell population, so the route is only
+ * taken while the swarm is known to be sparse enough.  The largest population of every sort step
+ * (binned or not) is copied to pinned host memory asynchronously and looked at when it has
+ * arrived — the host never waits for it; anything that rewrites positions behind the library's
+ * back (setArray, reset, ...) calls prs_bin_invalidate().  Both routes give identical results. */
+static void bin_poll_report() {
+  PrsBinState &B = g_prs.bin;
+  if (!B.report_pending || cudaEventQuery(B.report_event) != cudaSuccess) return;
+  B.report_pending = false;
+  if (B.h_report[1]) {
+    fprintf(stderr, "prs_fused_step: a cell held more than %u robots on the binned route\n", prs_bin::MAX_RANKED_CELL);
+    exit(EXIT_FAILURE);
+  }
+  const uint32_t pop = B.h_report[0];
+  if (B.admitted) { if (pop > 64u) B.admitted = false; }
+  else if (B.report_generation == B.generation && pop <= 48u) B.admitted = true;
+}
+static void bin_send_report(const uint32_t *d_two_words) {
+  PrsBinState &B = g_prs.bin;
+  if (B.report_pending) return; /* one report in flight at a time */
+  if (!B.h_report) {
+    PRS_CUDA(cudaMallocHost(&B.h_report, 2 * sizeof(uint32_t)));
+    PRS_CUDA(cudaEventCreateWithFlags(&B.report_event, cudaEventDisableTiming));
+  }
+  PRS_CUDA(cudaMemcpyAsync(B.h_report, d_two_words, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_prs.stream));
+  PRS_CUDA(cudaEventRecord(B.report_event, g_prs.stream));
+  B.report_pending = true;
+  B.report_generation = B.generation;
+}
+static void bin_ensure(uint32_t n, uint32_t C) {
+  PrsBinState &B = g_prs.bin;
+  if (B.cap_cells < C) {
+    if (B.cellCount) PRS_CUDA(cudaFree(B.cellCount));
+    if (B.scratch) PRS_CUDA(cudaFree(B.scratch));
+    PRS_CUDA(cudaMalloc(&B.cellCount, (size_t)C * 4));
+    PRS_CUDA(cudaMemsetAsync(B.cellCount, 0, (size_t)C * 4, g_prs.stream));
+    PRS_CUDA(cudaMalloc(&B.scratch, prs_bin::scan_scratch_words(C) * 4));
+    B.cap_cells = C;
+  }
+  ensure_sort_workspace(n, 1, 4096);
+}
+void prs_bin_invalidate(void) {
+  g_prs.bin.admitted = false;
+  g_prs.bin.generation++;
+}
+void prs_bin_set_mode(int mode) { g_prs.bin.mode = mode; } /* 0 auto (default), 1 never (always onesweep), 2 always */
+int prs_bin_active(void) { return g_prs.bin.admitted ? 1 : 0; }
+
 void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort) {
   const uint32_t n = b->nCells;
   if (!n) return;
   const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
+  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
+  PrsBinState &B = g_prs.bin;
+  bool binned = false;
+  if (do_sort && b->sortedPR) {
+    bin_poll_report();
+    const bool shape_ok = (unsigned long long)b->numCells <= 16ull * n && n < (1u << 30);
+    binned = shape_ok && (B.mode == 2 || (B.mode == 0 && B.admitted));
+  }
+  if (binned) {
+    /* K1 + tickets -> scan (= cell table) -> scatter -> in-cell order + gather */
+    bin_ensure(n, b->numCells);
+    prs_sort::Workspace &w = g_prs.sort_ws;
+    uint32_t *ticket = w.vals[0], *hash_by_slot = w.keys[0], *index_by_slot = w.vals[1];
+    {
+      StageScope t(PRS_STAGE_K1);
+      PRS_LAUNCH((k_control_integrate_hash<true, true>), div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
+                 b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
+                 (const uint32_t *)nullptr, B.cellCount);
+    }
+    {
+      StageScope t(PRS_STAGE_SORT);
+      const unsigned tiles = div_up(b->numCells, prs_bin::SCAN_TILE);
+      PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
+      PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->numCells, B.scratch, tiles);
+      PRS_LAUNCH(prs_bin::k_cell_apply, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
+                 B.scratch);
+      PRS_LAUNCH(prs_bin::k_cell_scatter, div_up(n, 256), 256, 0, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
+    }
+    {
+      StageScope t(PRS_STAGE_REORDER);
+      PRS_LAUNCH(prs_bin::k_reorder_binned, div_up(n, 256), 256, 0, hash_by_slot, index_by_slot, b->cellStart, b->cellEnd,
+                 b->hash, b->index, (float4 *)b->sortedPR, (float2 *)b->sortedVel, (const float2 *)b->pos,
+                 (const float2 *)b->vel, b->rad, n, B.scratch);
+    }
+    bin_send_report(B.scratch + 1);
+    StageScope t(PRS_STAGE_COLLIDE);
+    prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
+    prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+    return;
+  }
   if (do_sort) {
     {
       StageScope t(PRS_STAGE_K1);
@@ -784,13 +902,19 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n, (const uint32_t *)nullptr);
   }
-  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
   if (b->sortedPR) {
     {
       StageScope t(PRS_STAGE_REORDER);
       PRS_CUDA(cudaMemsetAsync(b->cellStart, 0xff, (size_t)b->numCells * sizeof(unsigned), g_prs.stream));
       PRS_LAUNCH(k_reorder_packed, div_up(n, 256), 256, 0, b->cellStart, b->cellEnd, (float4 *)b->sortedPR,
                  (float2 *)b->sortedVel, b->hash, b->index, (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
+      if (do_sort && B.mode == 0 && !B.admitted && (unsigned long long)b->numCells <= 16ull * n) {
+        /* not on the binned route: report the largest cell population so that it can be taken */
+        bin_ensure(n, b->numCells);
+        PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
+        PRS_LAUNCH(k_max_population, div_up(n, 256), 256, 0, b->hash, b->cellStart, b->cellEnd, n, B.scratch + 1);
+        bin_send_report(B.scratch + 1);
+      }
     }
     StageScope t(PRS_STAGE_COLLIDE);
     prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};

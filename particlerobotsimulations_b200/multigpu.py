@@ -341,12 +341,13 @@ def bench_slabs(args, rank, world, local_rank):
     sort_interval = o.timestep if args.sort_interval is None else args.sort_interval
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = bench.ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         sim.step(o.timestep, sort_interval)
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = bench.ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     lib.prs_launch_count(1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
@@ -357,9 +358,9 @@ def bench_slabs(args, rank, world, local_rank):
         b.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
+    sampler.mark()
     launches = int(lib.prs_launch_count(0))
     total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
-    clocks = sampler.stop()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
@@ -379,6 +380,7 @@ def bench_slabs(args, rank, world, local_rank):
     cnt = (C.c_uint * 6)()
     lib.prs_stage_times(ms, cnt)
     lib.prs_stage_timing(0)
+    clocks = sampler.stop()
     per_bytes, b_alg, passes = bench.algorithmic_bytes(p, sort_interval <= o.timestep)
     peak, peak_src = bench.measured_peak()
     stages = {}

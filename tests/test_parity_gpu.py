@@ -537,3 +537,70 @@ def test_synthetic_hex_swarm_properties():
     ob.lib().prso_set_threads(1)
     assert util.rel_err(vel, v_o, max(float(np.abs(v_o).max()), 1e-3)) < TOL_ORACLE
     sim.close()
+
+
+def _hex_run(mode, steps, scramble=False, crowd=0):
+    """64k hex swarm through the fused path with the cell sort pinned to one route (prs_bin_set_mode)."""
+    p, o = util.cfg("example")
+    nx = ny = 256
+    p.nCells = nx * ny
+    L = prs.lib()
+    L.prs_params_set_world(C.byref(p), 512, 64.0)
+    L.prs_bin_set_mode(mode)
+    try:
+        sim = prs.Simulation(p, 64.0, prs.BACKEND_FUSED)
+        sim.init_hex(nx, ny, 0.17, 0.01 * p.max_radius, 5555)
+        if scramble or crowd:
+            pos = sim.get(prs.POSITION)
+            rng = np.random.default_rng(5)
+            if crowd:      # pile `crowd` robots into each of a few cells (stable order inside crowded cells)
+                for c in range(8):
+                    sel = rng.choice(p.nCells, crowd, replace=False)
+                    pos[sel] = pos[sel[0]] + (rng.random((crowd, 2), dtype=np.float32) - 0.5) * np.float32(0.2)
+            if scramble:   # robot order unrelated to position (arrival tickets far from index order)
+                pos = pos[rng.permutation(p.nCells)]
+            sim.set(prs.POSITION, pos)
+        out = []
+        for k in range(steps):
+            sim.update(o.timestep, o.timestep)
+            if k in (0, steps - 1):
+                out.append({key: sim.get(w) for key, w in (("hash", prs.HASH), ("index", prs.INDEX), ("cs", prs.CELLSTART),
+                                                           ("ce", prs.CELLEND), ("pos", prs.POSITION), ("vel", prs.VELOCITY),
+                                                           ("spos", prs.SORTEDPOS), ("srad", prs.SORTEDRAD), ("svel", prs.SORTEDVEL))})
+        sim.close()
+        return out
+    finally:
+        L.prs_bin_set_mode(0)
+
+
+@pytest.mark.parametrize("scramble,crowd,steps", [(False, 0, 12), (True, 0, 6), (True, 40, 1)])
+def test_cell_binning_route_equals_onesweep_route(scramble, crowd, steps):
+    """The fused step sorts by cell binning (counting sort whose scan is the cell table) when the swarm
+    is sparse, else by the onesweep radix sort: hashes, stable index order, cellStart/cellEnd (stale
+    cellEnd of emptied cells included), sorted copies and the trajectory must be identical bits."""
+    a = _hex_run(1, steps, scramble, crowd)   # onesweep only
+    b = _hex_run(2, steps, scramble, crowd)   # binning only
+    for x, y in zip(a, b):
+        for k in x:
+            assert np.array_equal(x[k].view(np.uint32), y[k].view(np.uint32)), k
+
+
+def test_cell_binning_is_taken_once_the_swarm_is_known_to_be_sparse():
+    """auto mode: the first sort steps go through onesweep and report the fullest cell; after the
+    report has arrived the binned route is used; an upload through the C-ABI withdraws the admission."""
+    p, o = util.cfg("example")
+    nx = ny = 128
+    p.nCells = nx * ny
+    L = prs.lib()
+    L.prs_params_set_world(C.byref(p), 256, 64.0)
+    sim = prs.Simulation(p, 64.0, prs.BACKEND_FUSED)
+    sim.init_hex(nx, ny, 0.17, 0.01 * p.max_radius, 5555)
+    assert L.prs_bin_active() == 0
+    for _ in range(3):
+        sim.update(o.timestep, o.timestep)
+        sim.sync()
+    sim.update(o.timestep, o.timestep)
+    assert L.prs_bin_active() == 1
+    sim.set(prs.VELOCITY, np.zeros((p.nCells, 2), np.float32))
+    assert L.prs_bin_active() == 0
+    sim.close()
