@@ -111,11 +111,11 @@ k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *s
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
-             const uint32_t *__restrict__ scratch) {
+             const uint32_t *__restrict__ scratch, uint32_t slot_offset) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c0 = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
-  const uint32_t tile_offset = scratch[4 + blockIdx.x];
+  const uint32_t tile_offset = slot_offset + scratch[4 + blockIdx.x]; /* slab ranks: slots start after the lower halo */
   uint32_t cnt[SCAN_ITEMS];
   load_counts(cellCount, c0, C, cnt);
   uint32_t sum = 0;

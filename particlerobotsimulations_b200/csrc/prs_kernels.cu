@@ -874,7 +874,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
       PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->numCells, B.scratch, tiles);
       PRS_LAUNCH(prs_bin::k_cell_apply, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                 B.scratch);
+                 B.scratch, 0u);
       PRS_LAUNCH(prs_bin::k_cell_scatter, div_up(n, 256), 256, 0, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
     }
     {

@@ -12,6 +12,11 @@
  *   K1 -> [sort steps: migrate_pack -> exchange -> migrate_unpack -> sort (+ ties by global id)]
  *      -> gather -> halo_pack -> exchange -> halo_unpack -> cell_table -> collide
  *
+ * The sort is the onesweep radix sort followed by an in-cell insertion sort by global id, or —
+ * while the swarm is known to be sparse (same asynchronous guard as the fused single-GPU step) —
+ * cell binning (prs_cellbin.cuh): tickets, a scan over the owned rows' cells that IS their cell
+ * table, scatter, and the in-cell order by global id folded into the gather.  Same results.
+ *
  * Migration record (23 words, structure-of-arrays with stride mig_cap after the count word):
  *   pos.xy vel.xy rad phase absForce_a absForce_r dead gid hash rng[12]
  * Halo record (7 words, stride halo_cap): sortedPR.xyzw sortedVel.xy hash
@@ -253,6 +258,87 @@ __global__ void __launch_bounds__(256) k_curand_setup_ids(curandState *__restric
   if (i < n) curand_init(c_prm.p.seed, gid[i], 0, &st[i]);
 }
 
+/* ---- binned route of the slab sort (prs_cellbin.cuh): tickets, scatter, in-cell order by GLOBAL id ---- */
+__global__ void __launch_bounds__(256) k_slab_tickets(prs_slab s, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ ticket) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ticket[i] = atomicAdd(&cellCount[s.hash[i]], 1u);
+}
+__global__ void __launch_bounds__(256)
+k_slab_scatter(prs_slab s, const uint32_t *__restrict__ ticket, uint32_t *__restrict__ index_by_slot) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t h = s.hash[i];
+  const uint32_t slot = __ldg(s.cellStart + h) + ticket[i]; /* absolute slot of [halo | owned | halo] */
+  s.hash_cat[slot] = h;
+  index_by_slot[slot - s.halo_cap] = i;
+}
+/* the robots of one cell in ascending GLOBAL id (= the single-GPU stable order) + packed sorted copy */
+__global__ void __launch_bounds__(256)
+k_slab_gather_binned(prs_slab s, const uint32_t *__restrict__ index_by_slot, uint32_t *scratch) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t h = s.hash_cat[s.halo_cap + k];
+  const uint32_t a = index_by_slot[k];
+  const uint32_t g = s.gid[a];
+  const float2 p = ((const float2 *)s.pos)[a];
+  const float2 v = ((const float2 *)s.vel)[a];
+  const float r = s.rad[a];
+  const uint32_t c0 = __ldg(s.cellStart + h), c1 = __ldg(s.cellEnd + h);
+  uint32_t below = 0;
+  if (c1 - c0 <= prs_bin::MAX_RANKED_CELL) {
+    for (uint32_t j = c0; j < c1; j++) below += (s.gid[index_by_slot[j - s.halo_cap]] < g) ? 1u : 0u;
+  } else {
+    atomicOr(&scratch[2], 1u);
+    below = s.halo_cap + k - c0;
+  }
+  const uint32_t dst = c0 + below;
+  s.index_sorted[dst - s.halo_cap] = a;
+  ((float4 *)s.sortedPR)[dst] = make_float4(p.x, p.y, r, __uint_as_float(a));
+  ((float2 *)s.sortedVel)[dst] = v;
+}
+/* fullest owned cell (guard of the binned route) from the sorted owned keys and the finished table */
+__global__ void __launch_bounds__(256) k_slab_max_population(prs_slab s, uint32_t *__restrict__ out_max) {
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t *hash = s.hash_cat + s.halo_cap;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t m = 0;
+  if (k < n) {
+    const uint32_t h = hash[k];
+    if (k == 0 || hash[k - 1] != h) m = s.cellEnd[h] - s.cellStart[h];
+  }
+  __shared__ uint32_t s_m[8];
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) m = max(m, s_m[w]);
+    if (m > *reinterpret_cast<volatile uint32_t *>(out_max)) atomicMax(out_max, m);
+  }
+}
+/* cell table entries of the two halo flanks only (the owned rows' entries come from the scan) */
+__global__ void __launch_bounds__(256) k_slab_halo_table(prs_slab s) {
+  const uint32_t n_lo = s.counts[PRS_SC_NLO], n = s.counts[PRS_SC_N], n_hi = s.counts[PRS_SC_NHI];
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_lo + n_hi) return;
+  const bool lower = q < n_lo;
+  const uint32_t first = lower ? s.halo_cap - n_lo : s.halo_cap + n;   /* first slot of the flank */
+  const uint32_t len = lower ? n_lo : n_hi;
+  const uint32_t r = lower ? q : q - n_lo;
+  const uint32_t *hash = s.hash_cat + first;
+  const uint32_t h = hash[r];
+  const uint32_t hp = (r > 0) ? hash[r - 1] : 0u;
+  if (r == 0 || h != hp) {
+    s.cellStart[h] = first + r;
+    if (r > 0) s.cellEnd[hp] = first + r;
+  }
+  if (r == len - 1) s.cellEnd[h] = first + r + 1;
+}
+
 /* -------------------------------------------------------------------------------------------- */
 /* C entry points                                                                                 */
 /* -------------------------------------------------------------------------------------------- */
@@ -302,12 +388,39 @@ void prs_slab_migrate_unpack(const prs_slab *s, const unsigned *recv_dn, const u
 /* (hash, local slot) of the owned robots sorted by hash into hash_cat[halo_cap ..] / index_sorted,
  * robots of one cell in ascending global id */
 void prs_slab_sort(const prs_slab *s) {
+  PrsBinState &B = g_prs.bin;
+  bin_poll_report();
+  const unsigned gx = g_prs.h_prm.p.gridSize.x;
+  const unsigned cells = (s->row_hi - s->row_lo) * gx; /* cells of the owned rows */
+  g_prs.slab_binned = (B.mode == 2 || (B.mode == 0 && B.admitted)) && (unsigned long long)cells <= 16ull * s->cap;
   StageScope t(PRS_STAGE_SORT);
+  if (g_prs.slab_binned) {
+    /* tickets -> scan of the owned rows' cells (= their cell table, slots offset by the lower halo)
+     * -> scatter; the in-cell order by global id is part of the gather */
+    bin_ensure(s->cap, g_prs.h_prm.p.numCells);
+    prs_sort::Workspace &w = g_prs.sort_ws;
+    const size_t c_lo = (size_t)s->row_lo * gx;
+    const unsigned tiles = div_up(cells, prs_bin::SCAN_TILE);
+    PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
+    PRS_LAUNCH(k_slab_tickets, div_up(s->cap, 256), 256, 0, *s, B.cellCount, w.vals[0]);
+    PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, cells, B.scratch, tiles);
+    PRS_LAUNCH(prs_bin::k_cell_apply, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
+               cells, B.scratch, s->halo_cap);
+    PRS_LAUNCH(k_slab_scatter, div_up(s->cap, 256), 256, 0, *s, w.vals[0], w.vals[1]);
+    g_prs.slab_table_fresh = true; /* consumed by this step's gather and cell_table */
+    return;
+  }
+  g_prs.slab_sorted_onesweep = true;
   sort_pairs(s->hash, nullptr, s->hash_cat + s->halo_cap, s->index_sorted, s->cap, key_bits_of_grid(), true, s->counts + PRS_SC_N);
   PRS_LAUNCH(k_fix_ties_by_gid, div_up(s->cap, 256), 256, 0, s->hash_cat + s->halo_cap, s->index_sorted, s->gid, s->counts + PRS_SC_N);
 }
 void prs_slab_gather(const prs_slab *s) {
   StageScope t(PRS_STAGE_REORDER);
+  if (g_prs.slab_binned && g_prs.slab_table_fresh) {
+    PRS_LAUNCH(k_slab_gather_binned, div_up(s->cap, 256), 256, 0, *s, g_prs.sort_ws.vals[1], g_prs.bin.scratch);
+    bin_send_report(g_prs.bin.scratch + 1);
+    return;
+  }
   PRS_LAUNCH(k_slab_gather, div_up(s->cap, 256), 256, 0, *s);
 }
 void prs_slab_halo_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up) {
@@ -318,14 +431,31 @@ void prs_slab_halo_unpack(const prs_slab *s, const unsigned *recv_dn, const unsi
   StageScope t(PRS_STAGE_EXCHANGE);
   PRS_LAUNCH(k_slab_halo_unpack, min(div_up(2 * s->halo_cap, 256), 592u), 256, 0, *s, recv_dn, recv_up);
 }
-/* clears cellStart for the rows this rank can see and builds the table over [halo | owned | halo] */
+/* cell table over [halo | owned | halo].  After a binned sort the owned rows' entries already exist
+ * (the scan wrote them): only the halo rows are cleared and filled.  Otherwise (onesweep route, or
+ * a step without sort: stale table) everything this rank can see is rebuilt. */
 void prs_slab_cell_table(const prs_slab *s) {
   StageScope t(PRS_STAGE_REORDER);
   const unsigned gx = g_prs.h_prm.p.gridSize.x, gy = g_prs.h_prm.p.gridSize.y;
   const unsigned r0 = s->row_lo > s->halo_rows ? s->row_lo - s->halo_rows : 0u;
   const unsigned r1 = min(s->row_hi + s->halo_rows, gy);
+  if (g_prs.slab_binned && g_prs.slab_table_fresh) {
+    if (s->row_lo > r0) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(s->row_lo - r0) * gx * sizeof(unsigned), g_prs.stream));
+    if (r1 > s->row_hi) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)s->row_hi * gx, 0xff, (size_t)(r1 - s->row_hi) * gx * sizeof(unsigned), g_prs.stream));
+    PRS_LAUNCH(k_slab_halo_table, div_up(2 * s->halo_cap, 256), 256, 0, *s);
+    g_prs.slab_table_fresh = false;
+    return;
+  }
   PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(r1 - r0) * gx * sizeof(unsigned), g_prs.stream));
   PRS_LAUNCH(k_slab_cell_table, div_up(s->cap + 2 * s->halo_cap, 256), 256, 0, *s);
+  if (g_prs.slab_sorted_onesweep && g_prs.bin.mode == 0 && !g_prs.bin.admitted) {
+    /* report the fullest cell so that the binned route can be admitted */
+    bin_ensure(s->cap, g_prs.h_prm.p.numCells);
+    PRS_CUDA(cudaMemsetAsync(g_prs.bin.scratch, 0, 16, g_prs.stream));
+    PRS_LAUNCH(k_slab_max_population, div_up(s->cap, 256), 256, 0, *s, g_prs.bin.scratch + 1);
+    bin_send_report(g_prs.bin.scratch + 1);
+  }
+  g_prs.slab_sorted_onesweep = false;
 }
 /* collide for the owned sorted slots [halo_cap, halo_cap + n); results go to the local slots */
 void prs_slab_collide(const prs_slab *s, float dt) {
