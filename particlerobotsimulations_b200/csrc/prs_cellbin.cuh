@@ -10,7 +10,7 @@
  *
  *   K1  (k_control_integrate_hash<.., COUNT>)  hash h of each robot + arrival ticket within its cell:
  *        ticket = atomicAdd(&cellCount[h], 1)                   (order of arrival: arbitrary)
- *   scan (k_cell_tile_sums, k_cell_apply)  over the C cells:
+ *   scan (k_cell_tile_sums, k_cell_scan_tiles, k_cell_apply)  over the C cells:
  *        cellStart[c] = exclusive sum (or 0xffffffff), cellEnd[c] = start + count (non-empty cells
  *        only), cellCount[c] = 0 for the next step — this replaces the cudaMemset of the table
  *   scatter (k_cell_scatter)  robot i -> slot cellStart[h] + ticket: arrival-ordered index list
@@ -34,14 +34,14 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr uint32_t MAX_RANKED_CELL = 1024; /* populations above this are not ranked (error flag) */
 
-/* The scan over the C cells is two kernels without any inter-block waiting (a single-pass chained
- * scan was tried first: with ~450 tiles in flight every tile spent most of its life waiting for
- * its predecessors' aggregates, 44 us for 4 M cells):
- *   k_cell_tile_sums  tile sums + fullest cell; the LAST block to finish scans the tile sums
- *   k_cell_apply      exclusive sums inside each tile + the tile's offset -> cellStart / cellEnd,
- *                     counters back to zero
- * scratch: [0] blocks done, [1] largest cell population, [2] error flag, [4..4+T) tile sums ->
- * exclusive tile offsets */
+/* The scan over the C cells has no inter-block waiting (a single-pass chained scan was tried first:
+ * with ~450 tiles in flight every tile spent most of its life waiting for its predecessors'
+ * aggregates, 44 us for 4 M cells):
+ *   k_cell_tile_sums   sums of tiles of 4096 cells
+ *   k_cell_scan_tiles  one block: exclusive scan of the tile sums
+ *   k_cell_apply       exclusive sums inside each tile + the tile's offset -> cellStart / cellEnd,
+ *                      counters back to zero
+ * scratch: [1] largest cell population, [2] error flag, [4..4+T) tile sums, [4+T..4+2T) tile offsets */
 __device__ __forceinline__ void load_counts(const uint32_t *cellCount, uint32_t c0, uint32_t C, uint32_t (&cnt)[SCAN_ITEMS]) {
   if (c0 + SCAN_ITEMS <= C) {
     const uint4 a = *reinterpret_cast<const uint4 *>(cellCount + c0), b = *reinterpret_cast<const uint4 *>(cellCount + c0 + 4);
@@ -52,39 +52,37 @@ __device__ __forceinline__ void load_counts(const uint32_t *cellCount, uint32_t 
   }
 }
 
+/* sums of the tiles of 4096 cells (no atomics: thousands of same-address atomics — a "last block
+ * done" counter, per-robot tile sums from K1, a running maximum — each cost 10-100 us in L2) */
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch, uint32_t num_tiles) {
-  __shared__ uint32_t s_sum[SCAN_THREADS / 32], s_max[SCAN_THREADS / 32];
-  __shared__ bool s_last;
+k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch) {
+  __shared__ uint32_t s_sum[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t cnt[SCAN_ITEMS];
   load_counts(cellCount, blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS, C, cnt);
-  uint32_t sum = 0, mx = 0;
+  uint32_t sum = 0;
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; i++) { sum += cnt[i]; mx = max(mx, cnt[i]); }
+  for (int i = 0; i < SCAN_ITEMS; i++) sum += cnt[i];
   sum = __reduce_add_sync(0xffffffffu, sum);
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if (lane == 0) { s_sum[warp] = sum; s_max[warp] = mx; }
+  if (lane == 0) s_sum[warp] = sum;
   __syncthreads();
   if (tid == 0) {
-    uint32_t total = 0, bmax = 0;
+    uint32_t total = 0;
 #pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; w++) { total += s_sum[w]; bmax = max(bmax, s_max[w]); }
+    for (int w = 0; w < SCAN_THREADS / 32; w++) total += s_sum[w];
     scratch[4 + blockIdx.x] = total;
-    /* fullest cell: one atomic per tile at most, none once the running maximum is reached */
-    if (bmax > *reinterpret_cast<volatile uint32_t *>(&scratch[1])) atomicMax(&scratch[1], bmax);
-    __threadfence();
-    s_last = atomicAdd(&scratch[0], 1u) == num_tiles - 1;
   }
-  __syncthreads();
-  if (!s_last) return;
-  /* last block: exclusive scan of the tile sums, in place */
-  __threadfence();
-  volatile uint32_t *sums = scratch + 4;
+}
+
+/* exclusive scan of the T tile sums (one block) */
+__global__ void __launch_bounds__(1024) k_cell_scan_tiles(uint32_t *scratch, uint32_t num_tiles) {
+  __shared__ uint32_t s_sum[32];
   __shared__ uint32_t s_carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *sums = scratch + 4, *offsets = scratch + 4 + num_tiles;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < num_tiles; base += SCAN_THREADS) {
+  for (uint32_t base = 0; base < num_tiles; base += 1024) {
     const uint32_t i = base + tid;
     const uint32_t v = (i < num_tiles) ? sums[i] : 0u;
     uint32_t inc = v;
@@ -97,12 +95,12 @@ k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *s
     __syncthreads();
     uint32_t before = s_carry, total = 0;
 #pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+    for (int w = 0; w < 32; w++) {
       const uint32_t t = s_sum[w];
       before += (w < (int)warp) ? t : 0u;
       total += t;
     }
-    if (i < num_tiles) sums[i] = before + inc - v;
+    if (i < num_tiles) offsets[i] = before + inc - v;
     __syncthreads();
     if (tid == 0) s_carry += total;
     __syncthreads();
@@ -111,16 +109,20 @@ k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *s
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
-             const uint32_t *__restrict__ scratch, uint32_t slot_offset) {
+             uint32_t *scratch, uint32_t slot_offset) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c0 = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
-  const uint32_t tile_offset = slot_offset + scratch[4 + blockIdx.x]; /* slab ranks: slots start after the lower halo */
+  const uint32_t tile_offset = slot_offset + scratch[4 + gridDim.x + blockIdx.x]; /* slab ranks: slots start after the lower halo */
   uint32_t cnt[SCAN_ITEMS];
   load_counts(cellCount, c0, C, cnt);
-  uint32_t sum = 0;
+  uint32_t sum = 0, mx = 0;
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; i++) sum += cnt[i];
+  for (int i = 0; i < SCAN_ITEMS; i++) { sum += cnt[i]; mx = max(mx, cnt[i]); }
+  /* fullest cell (guard of the in-cell ranking): one atomic per warp at most, none once the running
+   * maximum is reached — same-address traffic serialises in one L2 slice */
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0 && mx > 1u && mx > *reinterpret_cast<volatile const uint32_t *>(&scratch[1])) atomicMax(&scratch[1], mx);
   uint32_t inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -197,6 +199,8 @@ k_reorder_binned(const uint32_t *__restrict__ hash_by_slot, const uint32_t *__re
   sortedVel[dst] = v;
 }
 
-inline size_t scan_scratch_words(uint32_t C) { return 4 + (size_t)(C + SCAN_TILE - 1) / SCAN_TILE; }
+inline size_t scan_scratch_words(uint32_t C) { return 4 + 2 * ((size_t)(C + SCAN_TILE - 1) / SCAN_TILE); }
+constexpr int SCAN_TILE_LOG2 = 12;
+static_assert((1 << SCAN_TILE_LOG2) == SCAN_TILE, "tile size");
 
 }  // namespace prs_bin

@@ -22,10 +22,10 @@
 #include "prs_cabi.h"
 #include "prs_device.cuh"
 #include "prs_onesweep.cuh"
+#include "prs_cellbin.cuh"
 #include "prs_host_state.h"
 
 #include "prs_collide.cuh"
-#include "prs_cellbin.cuh"
 
 using namespace prs;
 
@@ -834,6 +834,7 @@ static void bin_ensure(uint32_t n, uint32_t C) {
     PRS_CUDA(cudaMalloc(&B.cellCount, (size_t)C * 4));
     PRS_CUDA(cudaMemsetAsync(B.cellCount, 0, (size_t)C * 4, g_prs.stream));
     PRS_CUDA(cudaMalloc(&B.scratch, prs_bin::scan_scratch_words(C) * 4));
+    PRS_CUDA(cudaMemsetAsync(B.scratch, 0, prs_bin::scan_scratch_words(C) * 4, g_prs.stream));
     B.cap_cells = C;
   }
   ensure_sort_workspace(n, 1, 4096);
@@ -864,6 +865,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     uint32_t *ticket = w.vals[0], *hash_by_slot = w.keys[0], *index_by_slot = w.vals[1];
     {
       StageScope t(PRS_STAGE_K1);
+      PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
       PRS_LAUNCH((k_control_integrate_hash<true, true>), div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                  b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
                  (const uint32_t *)nullptr, B.cellCount);
@@ -871,8 +873,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     {
       StageScope t(PRS_STAGE_SORT);
       const unsigned tiles = div_up(b->numCells, prs_bin::SCAN_TILE);
-      PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
-      PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->numCells, B.scratch, tiles);
+      PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->numCells, B.scratch);
+      PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
       PRS_LAUNCH(prs_bin::k_cell_apply, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
                  B.scratch, 0u);
       PRS_LAUNCH(prs_bin::k_cell_scatter, div_up(n, 256), 256, 0, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);

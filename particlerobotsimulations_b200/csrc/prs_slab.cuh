@@ -403,7 +403,8 @@ void prs_slab_sort(const prs_slab *s) {
     const unsigned tiles = div_up(cells, prs_bin::SCAN_TILE);
     PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
     PRS_LAUNCH(k_slab_tickets, div_up(s->cap, 256), 256, 0, *s, B.cellCount, w.vals[0]);
-    PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, cells, B.scratch, tiles);
+    PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, cells, B.scratch);
+    PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
     PRS_LAUNCH(prs_bin::k_cell_apply, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
                cells, B.scratch, s->halo_cap);
     PRS_LAUNCH(k_slab_scatter, div_up(s->cap, 256), 256, 0, *s, w.vals[0], w.vals[1]);

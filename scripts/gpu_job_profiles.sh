@@ -1,0 +1,6 @@
+# GPU job: the ncu evidence for profiles/: launch list of a short S1 bench run + one --set full capture of the step's kernels
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+bash scripts/gpu_job_launches.sh r1_s1 > gpurun_out/launches_r1_s1.txt 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"k_collide|k_control_integrate|k_cell_|k_reorder_binned" -s 40 -c 6 -f -o gpurun_out/prof_r1_step \
+  python bench.py --steps 6 --warmup 12 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_r1_step.log 2>&1
+cat gpurun_out/launches_r1_s1.txt | tail -16
