@@ -167,6 +167,13 @@ __global__ void k_selftest_div(const float *__restrict__ x, const float *__restr
   if (__float_as_uint(s) != __float_as_uint(__fsqrt_rn(d[i]))) atomicAdd(mismatches + 1, 1ull);
   const float g = prs::powf2_fast_path(d[i]);
   if (__float_as_uint(g) != __float_as_uint(__powf(d[i], 2.0f))) atomicAdd(mismatches + 2, 1ull);
+  /* x / sqrt(d) with the reciprocal seeded by rsqrt(d) instead of MUFU.RCP (collide's unit vector) */
+  float y;
+  const float sq = prs::sqrt_fast_path(d[i], &y);
+  const float r1s = fmaf(y, fmaf(y, -sq, 1.0f), y);
+  const float qs = prs::div_shared(x[i], sq, r1s);
+  const float ws = __fdiv_rn(x[i], sq);
+  if (__float_as_uint(qs) != __float_as_uint(ws) && !(qs == 0.0f && ws == 0.0f)) atomicAdd(mismatches + 3, 1ull);
 }
 
 /* Euler step + wall bounce for one robot (result of integrate_functor, :53-103) */
@@ -941,15 +948,16 @@ void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad
 }
 
 unsigned long long prs_selftest_div(const float *d_x, const float *d_d, unsigned n) {
-  unsigned long long *dm, h[3] = {0, 0, 0};
+  unsigned long long *dm, h[4] = {0, 0, 0, 0};
   PRS_CUDA(cudaMalloc(&dm, sizeof(h)));
   PRS_CUDA(cudaMemsetAsync(dm, 0, sizeof(h), g_prs.stream));
   PRS_LAUNCH(k_selftest_div, div_up(n, 256), 256, 0, d_x, d_d, n, dm);
   PRS_CUDA(cudaMemcpyAsync(h, dm, sizeof(h), cudaMemcpyDeviceToHost, g_prs.stream));
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
   PRS_CUDA(cudaFree(dm));
-  if (h[0] || h[1] || h[2]) fprintf(stderr, "prs_selftest_div: div %llu sqrt %llu powf2 %llu mismatches\n", h[0], h[1], h[2]);
-  return h[0] + h[1] + h[2];
+  if (h[0] || h[1] || h[2] || h[3])
+    fprintf(stderr, "prs_selftest_div: div %llu sqrt %llu powf2 %llu div-by-sqrt %llu mismatches\n", h[0], h[1], h[2], h[3]);
+  return h[0] + h[1] + h[2] + h[3];
 }
 
 void prs_stage_timing(int enable) {

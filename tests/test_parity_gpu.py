@@ -98,20 +98,21 @@ def test_fast_path_sequences_match_ieee_operators():
     reciprocal), sqrt and __powf(.,2) under ONE range test per pair (prs_collide.cuh).  Over the
     admitted operand ranges they must return the bits of __fdiv_rn / __fsqrt_rn / __powf."""
     L = prs.lib()
-    rng = np.random.default_rng(7)
     n = 1 << 22
-    # numerators: offsets / attraction*unit-vector, magnitudes 1e-20 .. 1e6 (and exact zeros)
-    x = (rng.choice([-1.0, 1.0], n) * np.exp(rng.uniform(np.log(1e-20), np.log(1e6), n))).astype(np.float32)
-    x[:64] = 0.0
-    x[64:128] = -0.0
-    # denominators: dist in [1e-10, 1e6], gap^2 in [3.6e-6, 1e12]; also used as sqrt / powf2 operands
-    d = np.exp(rng.uniform(np.log(1e-10), np.log(1e12), n)).astype(np.float32)
-    d[: n // 2] = np.exp(rng.uniform(np.log(1.9e-3), np.log(10.0), n // 2)).astype(np.float32)  # typical gaps / distances
-    # keep quotients inside the normal range, as they are in collide
-    q = np.abs(x.astype(np.float64)) / d.astype(np.float64)
-    x[(q > 1e30) | ((q < 1e-30) & (x != 0))] = 1.0
-    dx, dd = Dev(x), Dev(d)
-    assert L.prs_selftest_div(dx.ptr, dd.ptr, n) == 0
+    for seed in (7, 8, 9, 10):      # 16 M operand pairs; also x / sqrt(d) with the rsqrt-seeded reciprocal
+        rng = np.random.default_rng(seed)
+        # numerators: offsets / attraction*unit-vector, magnitudes 1e-20 .. 1e6 (and exact zeros)
+        x = (rng.choice([-1.0, 1.0], n) * np.exp(rng.uniform(np.log(1e-20), np.log(1e6), n))).astype(np.float32)
+        x[:64] = 0.0
+        x[64:128] = -0.0
+        # denominators: dist in [1e-10, 1e6], gap^2 in [3.6e-6, 1e12]; also used as sqrt / powf2 operands
+        d = np.exp(rng.uniform(np.log(1e-10), np.log(1e12), n)).astype(np.float32)
+        d[: n // 2] = np.exp(rng.uniform(np.log(1.9e-3), np.log(10.0), n // 2)).astype(np.float32)  # typical gaps / distances
+        # keep quotients inside the normal range, as they are in collide
+        q = np.abs(x.astype(np.float64)) / d.astype(np.float64)
+        x[(q > 1e30) | ((q < 1e-30) & (x != 0))] = 1.0
+        dx, dd = Dev(x), Dev(d)
+        assert L.prs_selftest_div(dx.ptr, dd.ptr, n) == 0
 
 
 def _grid_pipeline(L, p, pos, vel, rad):
