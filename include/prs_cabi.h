@@ -90,6 +90,9 @@ float prs_get_world_half_extent(void);
  * 1 = "fast" (one reciprocal per pair, shared-memory tiles); both are parity-tested */
 void prs_set_collide_mode(int mode);
 int prs_get_collide_mode(void);
+/* collide runs one WARP per robot for swarms of up to max_robots (latency-bound sizes; default 16384,
+ * 0 = always one thread per robot).  Same bits either way. */
+void prs_set_collide_warp_max(unsigned max_robots);
 /* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
 unsigned long long prs_launch_count(int reset);
 

@@ -112,6 +112,7 @@ SIGNATURES = {
     "prs_version": (C.c_char_p, []), "prs_set_stream": (None, [_VP]), "prs_get_stream": (_VP, []),
     "prs_set_world_half_extent": (None, [_F]), "prs_get_world_half_extent": (_F, []),
     "prs_set_collide_mode": (None, [_I]), "prs_get_collide_mode": (_I, []),
+    "prs_set_collide_warp_max": (None, [_U]),
     "prs_launch_count": (C.c_ulonglong, [_I]),
     "prs_stage_timing": (None, [_I]), "prs_stage_times": (None, [_VP, _VP]),
     "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),

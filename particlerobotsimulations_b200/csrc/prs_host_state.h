@@ -22,6 +22,12 @@ struct PrsBinState {
   unsigned report_generation = 0;
 };
 
+/* which cell table the fused step built last (steps without a sort reuse it: same keys, same table) */
+struct PrsTableState {
+  const void *cellStart = nullptr, *hash = nullptr;
+  unsigned n = 0, numCells = 0, generation = 0;
+};
+
 struct PrsHostState {
   cudaStream_t stream = 0;            /* legacy default stream, like the reference */
   unsigned long long launches = 0;    /* kernels launched by this library */
@@ -29,8 +35,10 @@ struct PrsHostState {
   bool params_set = false;
   float world_half = 64.0f;           /* reference wall (kernel_impl.cuh:75-97) */
   int collide_mode = 0;               /* 0 exact, 1 fast */
+  unsigned collide_warp_max = 16384;  /* swarms up to this size use the warp-per-robot collide kernel */
   prs_sort::Workspace sort_ws;
   PrsBinState bin;
+  PrsTableState table;
   bool slab_sorted_onesweep = false;
   bool slab_binned = false, slab_table_fresh = false; /* slab engine: route of the last sort / its table not consumed yet */
   int sort_threads = 0;               /* tile shape of k_onesweep: 512 / 1024 threads, 0 = by size */

@@ -141,6 +141,20 @@ k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEn
   sortedPR[k] = make_float4(p.x, p.y, r, __uint_as_float(src));
   sortedVel[k] = v;
 }
+/* Steps WITHOUT a sort (reference cadence: hash and sort only every sort_interval): hash and index are
+ * unchanged, so the cell table the reference rebuilds every step (cudaMemset + the same compares,
+ * particlebot_cuda.cu:301-309) comes out identical — only the sorted copy has to be refreshed. */
+__global__ void __launch_bounds__(256)
+k_gather_packed(float4 *__restrict__ sortedPR, float2 *__restrict__ sortedVel, const uint32_t *__restrict__ index,
+                const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t src = index[k];
+  const float2 p = pos[src];
+  sortedPR[k] = make_float4(p.x, p.y, rad[src], __uint_as_float(src));
+  sortedVel[k] = vel[src];
+}
+
 /* packed -> the reference's sortedPos / sortedRad arrays (only when a caller asks for them) */
 __global__ void __launch_bounds__(256) k_unpack_sorted(const float4 *__restrict__ pr, float2 *__restrict__ sortedPos,
                                                        float *__restrict__ sortedRad, uint32_t n) {
@@ -618,7 +632,10 @@ void cudaInit(int argc, char **argv) {
 void cudaGLInit(int argc, char **argv) { cudaInit(argc, argv); }
 
 void allocateArray(void **devPtr, size_t size) { PRS_CUDA(cudaMalloc(devPtr, size)); }
-void freeArray(void *devPtr) { PRS_CUDA(cudaFree(devPtr)); }
+void freeArray(void *devPtr) {
+  g_prs.table.cellStart = nullptr; /* a recycled address must not look like the cached table */
+  PRS_CUDA(cudaFree(devPtr));
+}
 void threadSync(void) { PRS_CUDA(cudaDeviceSynchronize()); }
 
 void copyArrayToDevice(void *device, const void *host, int offset, int size) {
@@ -672,17 +689,20 @@ void integrateSystem(float *pos, float *vel, float *rad, float deltaTime, unsign
 }
 
 void calcHash(unsigned *hash, unsigned *index, float *pos, int nCells) {
+  g_prs.table.cellStart = nullptr;
   if (nCells <= 0) return;
   PRS_LAUNCH(k_calc_hash, div_up(nCells, 256), 256, 0, hash, index, (const float2 *)pos, (uint32_t)nCells);
 }
 
 void sortParticlebots(unsigned *hash, unsigned *index, unsigned nCells) {
+  g_prs.table.cellStart = nullptr; /* the fused step's cached table no longer describes these keys */
   sort_pairs(hash, index, hash, index, nCells, key_bits_of_grid(), false);
 }
 
 void reorderDataAndFindCellStart(unsigned *cellStart, unsigned *cellEnd, float *sortedPos, float *sortedVel,
                                  float *sortedRad, unsigned *hash, unsigned *index, float *oldPos, float *oldVel,
                                  float *oldRad, unsigned nCells, unsigned numCells) {
+  g_prs.table.cellStart = nullptr;
   PRS_CUDA(cudaMemsetAsync(cellStart, 0xff, (size_t)numCells * sizeof(unsigned), g_prs.stream));
   if (!nCells) return;
   PRS_LAUNCH(k_reorder, div_up(nCells, 256), 256, 0, cellStart, cellEnd, (float2 *)sortedPos, (float2 *)sortedVel,
@@ -768,6 +788,8 @@ void prs_set_world_half_extent(float half) {
 float prs_get_world_half_extent(void) { return g_prs.world_half; }
 void prs_set_collide_mode(int mode) { g_prs.collide_mode = mode; }
 int prs_get_collide_mode(void) { return g_prs.collide_mode; }
+/* swarms of up to max_robots use the warp-per-robot collide kernel (0 = never); default 16384 */
+void prs_set_collide_warp_max(unsigned max_robots) { g_prs.collide_warp_max = max_robots; }
 unsigned long long prs_launch_count(int reset) {
   const unsigned long long v = g_prs.launches;
   if (reset) g_prs.launches = 0;
@@ -893,6 +915,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
                  (const float2 *)b->vel, b->rad, n, B.scratch);
     }
     bin_send_report(B.scratch + 1);
+    g_prs.table.cellStart = b->cellStart; g_prs.table.hash = b->hash; g_prs.table.n = n;
+    g_prs.table.numCells = b->numCells; g_prs.table.generation = B.generation;
     StageScope t(PRS_STAGE_COLLIDE);
     prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
     prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
@@ -914,9 +938,18 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
   if (b->sortedPR) {
     {
       StageScope t(PRS_STAGE_REORDER);
-      PRS_CUDA(cudaMemsetAsync(b->cellStart, 0xff, (size_t)b->numCells * sizeof(unsigned), g_prs.stream));
-      PRS_LAUNCH(k_reorder_packed, div_up(n, 256), 256, 0, b->cellStart, b->cellEnd, (float4 *)b->sortedPR,
-                 (float2 *)b->sortedVel, b->hash, b->index, (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
+      PrsTableState &T = g_prs.table;
+      const bool table_current = !do_sort && T.cellStart == b->cellStart && T.hash == b->hash && T.n == n &&
+                                 T.numCells == b->numCells && T.generation == B.generation;
+      if (table_current) {
+        PRS_LAUNCH(k_gather_packed, div_up(n, 256), 256, 0, (float4 *)b->sortedPR, (float2 *)b->sortedVel, b->index,
+                   (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
+      } else {
+        PRS_CUDA(cudaMemsetAsync(b->cellStart, 0xff, (size_t)b->numCells * sizeof(unsigned), g_prs.stream));
+        PRS_LAUNCH(k_reorder_packed, div_up(n, 256), 256, 0, b->cellStart, b->cellEnd, (float4 *)b->sortedPR,
+                   (float2 *)b->sortedVel, b->hash, b->index, (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
+        T.cellStart = b->cellStart; T.hash = b->hash; T.n = n; T.numCells = b->numCells; T.generation = B.generation;
+      }
       if (do_sort && B.mode == 0 && !B.admitted && (unsigned long long)b->numCells <= 16ull * n) {
         /* not on the binned route: report the largest cell population so that it can be taken */
         bin_ensure(n, b->numCells);

@@ -26,6 +26,17 @@ TOL_REF = 1e-5      # vs the reference's kernels (north_star)
 TOL_ORACLE = 5e-4   # vs the IEEE CPU restatement
 
 
+@pytest.fixture(autouse=True, params=["warp-per-robot", "thread-per-robot"])
+def collide_kernel(request):
+    """collide has two kernels with identical results: one warp per robot for small swarms (<= 16384
+    robots by default, i.e. every cfg-sized test here) and one thread per robot.  Every test of this
+    module runs with both."""
+    L = prs.lib()
+    L.prs_set_collide_warp_max(16384 if request.param == "warp-per-robot" else 0)
+    yield request.param
+    L.prs_set_collide_warp_max(16384)
+
+
 def _backends():
     b = [("percall", prs.BACKEND_PERCALL, None), ("fused", prs.BACKEND_FUSED, None)]
     return b
