@@ -9,7 +9,7 @@ bits = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 n = 1 << log2n
 L = prs.lib()
 L.prs_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
-nt = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+nt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 L.prs_sort_set_threads(nt)
 tile = L.prs_sort_tile_size()
 tiles = (n + tile - 1) // tile
