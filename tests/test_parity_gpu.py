@@ -616,3 +616,50 @@ def test_cell_binning_is_taken_once_the_swarm_is_known_to_be_sparse():
     sim.set(prs.VELOCITY, np.zeros((p.nCells, 2), np.float32))
     assert L.prs_bin_active() == 0
     sim.close()
+
+
+def _observables(params, opt, backend, ext, steps, sample_every):
+    """centroid track (and the object's track in object-transport mode) over a long horizon, reference cadence"""
+    sim = prs.Simulation(params, 64.0, backend, ext)
+    sim.srand(params.seed)
+    sim.reset()
+    cen, obj = [sim.get(prs.POSITION).astype(np.float64).mean(0)], []
+    if params.nDead == -1:
+        obj.append(sim.get(prs.POSITION)[-1].astype(np.float64))
+    for k in range(steps):
+        sim.update(opt.timestep, opt.sort_interval)
+        if (k + 1) % sample_every == 0:
+            pos = sim.get(prs.POSITION).astype(np.float64)
+            cen.append(pos.mean(0))
+            if params.nDead == -1:
+                obj.append(pos[-1])
+    sim.close()
+    return np.array(cen), np.array(obj)
+
+
+@pytest.mark.parametrize("name", ["example", "example_dead_cells", "example_object_transport"])
+def test_long_horizon_observables_vs_reference_kernels(name):
+    """north_star: over long horizons (chaotic divergence allowed) the swarm-level observables must agree
+    within 2 %: centroid velocity toward the light source and object-transport displacement.  24 000 steps
+    = 240 s of simulated time (20 controller periods, one re-sort at step 18002) on the reference's own
+    kernels and on the fused path."""
+    if not util.refcuda_available():
+        pytest.skip("oracle/_ref/libprs_refcuda.so not built (needs /root/reference at build time)")
+    p, o = util.cfg(name)
+    steps, every = 24000, 2000
+    c_ref, o_ref = _observables(p, o, prs.BACKEND_EXTERNAL, ob.REFCUDA_PATH, steps, every)
+    c_new, o_new = _observables(p, o, prs.BACKEND_FUSED, None, steps, every)
+    light = np.array([p.light_x, p.light_y], np.float64)
+    T = steps * float(o.timestep)
+
+    def toward_light(track):        # mean velocity of the point toward the light over the horizon
+        return (np.linalg.norm(track[0] - light) - np.linalg.norm(track[-1] - light)) / T
+
+    v_ref, v_new = toward_light(c_ref), toward_light(c_new)
+    assert abs(v_ref) > 1e-4, "the reference swarm did not move: the observable would be meaningless"
+    assert abs(v_new - v_ref) <= 0.02 * abs(v_ref), (v_new, v_ref)
+    if len(o_ref):
+        d_ref, d_new = np.linalg.norm(o_ref[-1] - o_ref[0]), np.linalg.norm(o_new[-1] - o_new[0])
+        assert abs(d_new - d_ref) <= 0.02 * max(d_ref, 1e-3), (d_new, d_ref)
+    # stronger than the bar: the path is bit-identical to the reference kernels, so the tracks coincide
+    assert np.array_equal(c_ref, c_new)
