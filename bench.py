@@ -460,6 +460,8 @@ def main():
     ap.add_argument("--collide-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-kernels-on-R1 comparison block")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: neighbour exchange by peer-to-peer stores into mapped mailboxes (default) or NCCL send/recv")
     ap.add_argument("--workload", default="s1", choices=["s1", "r1"],
                     help="s1: 2^robots_log2 hex swarm in its own world; r1: 640x640 swarm in the reference's +-64 world")
     args = ap.parse_args()

@@ -159,7 +159,8 @@ enum {
   PRS_SLAB_ERR_HALO_CAP = 2,   /* a halo longer than halo_cap */
   PRS_SLAB_ERR_CAPACITY = 4,   /* more robots than cap */
   PRS_SLAB_ERR_TWO_SLABS = 8,  /* a robot crossed more than one slab between two sorts */
-  PRS_SLAB_ERR_LEFT_WORLD = 16 /* a robot left the rows of the first / last slab (hash wrap-around) */
+  PRS_SLAB_ERR_LEFT_WORLD = 16, /* a robot left the rows of the first / last slab (hash wrap-around) */
+  PRS_SLAB_ERR_PEER_TIMEOUT = 32 /* peer-to-peer exchange: the neighbour's data did not arrive */
 };
 typedef struct {
   /* owned robots, local slots [0, cap) */
@@ -195,6 +196,18 @@ void prs_slab_collide(const prs_slab *s, float dt);
 void prs_slab_min_light_distance(const prs_slab *s, float *d_min_d);
 void prs_slab_update_phase(const prs_slab *s, float spacing, const float *d_min_d);
 void prs_slab_add_noise(const prs_slab *s, float std);
+/* peer-to-peer exchange (multigpu.py exchange="p2p"): the send buffers handed to the pack calls are
+ * the NEIGHBOUR's mailbox, mapped through CUDA IPC; prs_slab_signal publishes the sequence number
+ * in the neighbours' flag words after the pack kernel, prs_slab_wait holds the stream until both
+ * neighbours' flags have reached it (device-side spin, bounded) */
+size_t prs_ipc_handle_size(void);
+void *prs_slab_mailbox_alloc(size_t words);
+void prs_slab_mailbox_free(void *p);
+void prs_ipc_export(void *dev_ptr, void *handle_out);
+void *prs_ipc_open(const void *handle);
+void prs_ipc_close(void *p);
+void prs_slab_signal(unsigned *remote_flag_dn, unsigned *remote_flag_up, unsigned seq);
+void prs_slab_wait(const prs_slab *s, const unsigned *local_flag_dn, const unsigned *local_flag_up, unsigned seq);
 
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n);
 /* self-test: number of operand pairs for which the shared-reciprocal division used by collide

@@ -84,7 +84,8 @@ class Slab(C.Structure):
 # words of Slab.counts (PRS_SC_*) and error bits (PRS_SLAB_ERR_*)
 SC_N, SC_NLO, SC_NHI, SC_KDN, SC_KUP, SC_MIGDN, SC_MIGUP, SC_LEAVERS, SC_HOLES, SC_KEEPERS, SC_ERR, SC_STAT_MIG, SC_STAT_HALO = range(13)
 SLAB_ERRORS = {1: "more migrants than mig_cap in one step", 2: "a halo longer than halo_cap", 4: "more robots than the slab capacity",
-               8: "a robot crossed more than one slab between two sorts", 16: "a robot left the grid rows of the outermost slab"}
+               8: "a robot crossed more than one slab between two sorts", 16: "a robot left the grid rows of the outermost slab",
+               32: "peer-to-peer exchange timed out waiting for a neighbour"}
 SLAB_MIG_WORDS, SLAB_HALO_WORDS = 23, 7
 
 _lib = None
@@ -127,6 +128,9 @@ SIGNATURES = {
     "prs_slab_cell_table": (None, [_VP]), "prs_slab_collide": (None, [_VP, _F]),
     "prs_slab_min_light_distance": (None, [_VP, _VP]), "prs_slab_update_phase": (None, [_VP, _F, _VP]),
     "prs_slab_add_noise": (None, [_VP, _F]),
+    "prs_ipc_handle_size": (C.c_size_t, []), "prs_slab_mailbox_alloc": (_VP, [C.c_size_t]), "prs_slab_mailbox_free": (None, [_VP]),
+    "prs_ipc_export": (None, [_VP, _VP]), "prs_ipc_open": (_VP, [_VP]), "prs_ipc_close": (None, [_VP]),
+    "prs_slab_signal": (None, [_VP, _VP, _U]), "prs_slab_wait": (None, [_VP, _VP, _VP, _U]),
     "prs_unpack_sorted": (None, [_VP, _VP, _VP, _U]), "prs_selftest_div": (C.c_ulonglong, [_VP, _VP, _U]),
     "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
     "prs_bin_invalidate": (None, []), "prs_bin_set_mode": (None, [_I]), "prs_bin_active": (_I, []),

@@ -479,3 +479,60 @@ void prs_slab_update_phase(const prs_slab *s, float spacing, const float *d_min_
 void prs_slab_add_noise(const prs_slab *s, float std) {
   PRS_LAUNCH(k_add_normal_noise, div_up(s->cap, 256), 256, 0, (curandState *)s->rng, s->phase, std, s->cap, s->counts + PRS_SC_N);
 }
+
+/* -------------------------------------------------------------------------------------------- */
+/* peer-to-peer exchange: the pack kernels write straight into the NEIGHBOUR's mailbox over       */
+/* NVLink (peer-mapped memory), a flag word carries the sequence number, the consumer waits for   */
+/* it on the device — no NCCL call, no host involvement, nothing between the producing kernel     */
+/* and the neighbour's HBM.  Mailboxes are double-buffered by step parity: a rank can only be one */
+/* exchange ahead of its neighbour (it needs the neighbour's data of the current exchange to go   */
+/* on), so the buffer of exchange t+2 is free when t+2 is written.                                */
+/* -------------------------------------------------------------------------------------------- */
+__global__ void k_slab_signal(unsigned *remote_dn, unsigned *remote_up, unsigned seq) {
+  /* the pack kernel that ran before this one in the stream has completed: order its peer writes
+   * before the flag at system scope */
+  __threadfence_system();
+  if (remote_dn) *reinterpret_cast<volatile unsigned *>(remote_dn) = seq;
+  if (remote_up) *reinterpret_cast<volatile unsigned *>(remote_up) = seq;
+  __threadfence_system();
+}
+__global__ void k_slab_wait(const unsigned *local_dn, const unsigned *local_up, unsigned seq, unsigned *counts) {
+  const volatile unsigned *f = threadIdx.x == 0 ? local_dn : local_up;
+  if (threadIdx.x < 2 && f) {
+    unsigned long long spins = 0;
+    while ((int)(*f - seq) < 0) {
+      __nanosleep(64);
+      if (++spins > (1ull << 26)) { atomicOr(&counts[PRS_SC_ERR], PRS_SLAB_ERR_PEER_TIMEOUT); break; } /* ~10 s: never hang the GPU */
+    }
+  }
+  __threadfence_system();
+}
+
+size_t prs_ipc_handle_size(void) { return sizeof(cudaIpcMemHandle_t); }
+/* device memory that can be mapped by peers: plain cudaMalloc, zeroed */
+void *prs_slab_mailbox_alloc(size_t words) {
+  void *p = nullptr;
+  PRS_CUDA(cudaMalloc(&p, words * 4));
+  PRS_CUDA(cudaMemset(p, 0, words * 4));
+  return p;
+}
+void prs_slab_mailbox_free(void *p) { if (p) PRS_CUDA(cudaFree(p)); }
+void prs_ipc_export(void *dev_ptr, void *handle_out) {
+  PRS_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_out, dev_ptr));
+}
+void *prs_ipc_open(const void *handle) {
+  void *p = nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  PRS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return p;
+}
+void prs_ipc_close(void *p) { if (p) PRS_CUDA(cudaIpcCloseMemHandle(p)); }
+void prs_slab_signal(unsigned *remote_flag_dn, unsigned *remote_flag_up, unsigned seq) {
+  StageScope t(PRS_STAGE_EXCHANGE);
+  PRS_LAUNCH(k_slab_signal, 1, 1, 0, remote_flag_dn, remote_flag_up, seq);
+}
+void prs_slab_wait(const prs_slab *s, const unsigned *local_flag_dn, const unsigned *local_flag_up, unsigned seq) {
+  StageScope t(PRS_STAGE_EXCHANGE);
+  PRS_LAUNCH(k_slab_wait, 1, 32, 0, local_flag_dn, local_flag_up, seq, s->counts);
+}

@@ -123,7 +123,16 @@ class CudaBackend:
 
     @staticmethod
     def _p(t):
-        return C.c_void_p(t.data_ptr())
+        """device address of a tensor, or a raw address (peer-mapped mailbox), or None"""
+        if t is None:
+            return None
+        return C.c_void_p(t if isinstance(t, int) else t.data_ptr())
+
+    def signal(self, remote_flag_dn, remote_flag_up, seq):
+        self.lib.prs_slab_signal(self._p(remote_flag_dn), self._p(remote_flag_up), seq)
+
+    def wait(self, local_flag_dn, local_flag_up, seq):
+        self.lib.prs_slab_wait(self._ref, self._p(local_flag_dn), self._p(local_flag_up), seq)
 
     def rng_setup(self, n):
         self.lib.prs_slab_rng_setup(self._ref, n)
@@ -174,7 +183,7 @@ class SlabSim:
     stand-in); `group` is the torch.distributed process group (None = default)."""
 
     def __init__(self, params, opt, backend, rank, world, device, pos, gid, rows, capacity=None, halo_cap=None,
-                 mig_cap=None, group=None):
+                 mig_cap=None, group=None, exchange="nccl"):
         self.p, self.opt, self.be = params, opt, backend
         self.rank, self.world, self.dev, self.group = rank, world, device, group
         self.R_lo, self.R_hi = rows[rank], rows[rank + 1]
@@ -211,6 +220,69 @@ class SlabSim:
         self.sorted_once = False
         self.be.bind(self)
         self.be.rng_setup(n)
+        self.exchange = exchange
+        self.seq = {"halo": 0, "mig": 0}
+        if exchange == "p2p":
+            self._setup_p2p(mw, hw)
+        elif exchange != "nccl":
+            raise ValueError(exchange)
+
+    # ---- peer-to-peer mailboxes (exchange="p2p") ---------------------------------------------------
+    def _setup_p2p(self, mw, hw):
+        """One mailbox per rank, mapped by both neighbours through CUDA IPC.  Layout (uint32 words):
+        for source s in (0 = from the lower neighbour, 1 = from the upper): halo[2 parities][hw],
+        mig[2 parities][mw]; then the flag words halo_seq[s], mig_seq[s]."""
+        lib = self.be.lib
+        self._mw, self._hw = mw, hw
+        self._region = 2 * hw + 2 * mw
+        words = 2 * self._region + 16
+        self.mailbox = int(lib.prs_slab_mailbox_alloc(words))
+        handle = C.create_string_buffer(int(lib.prs_ipc_handle_size()))
+        lib.prs_ipc_export(C.c_void_p(self.mailbox), handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        self.peer = [None, None]     # [lower, upper] neighbour's mailbox in this process's address space
+        if self.rank > 0:
+            self.peer[0] = int(lib.prs_ipc_open(C.create_string_buffer(handles[self.rank - 1], len(handles[self.rank - 1]))))
+        if self.rank < self.world - 1:
+            self.peer[1] = int(lib.prs_ipc_open(C.create_string_buffer(handles[self.rank + 1], len(handles[self.rank + 1]))))
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def _mb_buf(self, base, src, kind, parity):
+        off = src * self._region + (parity * self._hw if kind == "halo" else 2 * self._hw + parity * self._mw)
+        return base + 4 * off
+
+    def _mb_flag(self, base, src, kind):
+        return base + 4 * (2 * self._region + (0 if kind == "halo" else 2) + src)
+
+    def _p2p_targets(self, kind, send):
+        """where this exchange's records go: the neighbour's mailbox (its "from the other side" region),
+        or the local scratch buffer when there is no neighbour; advances the sequence number"""
+        self.seq[kind] += 1
+        q = self.seq[kind]
+        par = q & 1
+        dn = self._mb_buf(self.peer[0], 1, kind, par) if self.peer[0] else send[0]   # I am the lower rank's UPPER neighbour
+        up = self._mb_buf(self.peer[1], 0, kind, par) if self.peer[1] else send[1]
+        return q, par, dn, up
+
+    def _p2p_publish_and_wait(self, kind, q):
+        be = self.be
+        be.signal(self._mb_flag(self.peer[0], 1, kind) if self.peer[0] else None,
+                  self._mb_flag(self.peer[1], 0, kind) if self.peer[1] else None, q)
+        be.wait(self._mb_flag(self.mailbox, 0, kind) if self.peer[0] else None,
+                self._mb_flag(self.mailbox, 1, kind) if self.peer[1] else None, q)
+
+    def close(self):
+        if self.exchange == "p2p" and getattr(self, "mailbox", None):
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            for pp in self.peer:
+                if pp:
+                    self.be.lib.prs_ipc_close(C.c_void_p(pp))
+            dist.barrier(group=self.group)
+            self.be.lib.prs_slab_mailbox_free(C.c_void_p(self.mailbox))
+            self.mailbox = None
 
     # ---- helpers ---------------------------------------------------------------------------------
     @staticmethod
@@ -266,16 +338,29 @@ class SlabSim:
             if p.phase_std:
                 be.add_noise(float(p.phase_std))
         be.k1(float(time), float(dt), sort_step)
+        p2p = self.exchange == "p2p"
         if sort_step:
-            be.migrate_pack(self.mig_send[0], self.mig_send[1])
-            self._exchange(self.mig_send, self.mig_recv)
-            be.migrate_unpack(self.mig_recv[0], self.mig_recv[1])
+            if p2p:
+                q, par, dn, up = self._p2p_targets("mig", self.mig_send)
+                be.migrate_pack(dn, up)                      # records land in the neighbours' HBM
+                self._p2p_publish_and_wait("mig", q)
+                be.migrate_unpack(self._mb_buf(self.mailbox, 0, "mig", par), self._mb_buf(self.mailbox, 1, "mig", par))
+            else:
+                be.migrate_pack(self.mig_send[0], self.mig_send[1])
+                self._exchange(self.mig_send, self.mig_recv)
+                be.migrate_unpack(self.mig_recv[0], self.mig_recv[1])
             be.sort()
             self.sorted_once = True
         be.gather()
-        be.halo_pack(self.halo_send[0], self.halo_send[1])
-        self._exchange(self.halo_send, self.halo_recv)
-        be.halo_unpack(self.halo_recv[0], self.halo_recv[1])
+        if p2p:
+            q, par, dn, up = self._p2p_targets("halo", self.halo_send)
+            be.halo_pack(dn, up)
+            self._p2p_publish_and_wait("halo", q)
+            be.halo_unpack(self._mb_buf(self.mailbox, 0, "halo", par), self._mb_buf(self.mailbox, 1, "halo", par))
+        else:
+            be.halo_pack(self.halo_send[0], self.halo_send[1])
+            self._exchange(self.halo_send, self.halo_recv)
+            be.halo_unpack(self.halo_recv[0], self.halo_recv[1])
         be.cell_table()
         be.collide(float(dt))
         self.time = np.float32(time + np.float32(dt))
@@ -298,7 +383,7 @@ class SlabSim:
         return out
 
 
-def make_hex_slab(params, opt, geom, backend_factory, rank, world, device, seed, jitter, group=None):
+def make_hex_slab(params, opt, geom, backend_factory, rank, world, device, seed, jitter, group=None, exchange="nccl"):
     """Builds rank `rank`'s slab of the nx*ny hex block: every rank generates only the lattice rows
     around its slab and keeps the robots whose grid row it owns."""
     nx, ny, pitch = geom["nx"], geom["ny"], geom["pitch"]
@@ -316,7 +401,7 @@ def make_hex_slab(params, opt, geom, backend_factory, rank, world, device, seed,
     halo_cap = int(1.6 * HALO_ROWS * per_grid_row) + 4096
     return SlabSim(params, opt, be, rank, world, device, pos[keep], ids[keep], rows,
                    capacity=int(n_expected * 1.25) + 65536, halo_cap=halo_cap,
-                   mig_cap=max(4096, int(0.5 * per_grid_row)), group=group)
+                   mig_cap=max(4096, int(0.5 * per_grid_row)), group=group, exchange=exchange)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -336,7 +421,8 @@ def bench_slabs(args, rank, world, local_rank):
     log2n = args.robots_log2 or 26
     p, o, geom = bench.swarm_config(prs, log2n)
     n_total = int(p.nCells)
-    sim = make_hex_slab(p, o, geom, CudaBackend, rank, world, dev, bench.SEED, bench.JITTER_FRAC * p.max_radius)
+    sim = make_hex_slab(p, o, geom, CudaBackend, rank, world, dev, bench.SEED, bench.JITTER_FRAC * p.max_radius,
+                        exchange=args.exchange)
     lib = prs.lib()
     sort_interval = o.timestep if args.sort_interval is None else args.sort_interval
     stream = torch.cuda.current_stream()
@@ -428,7 +514,9 @@ def bench_slabs(args, rank, world, local_rank):
             "config": {"workload": f"{geom['name']}: {n_total} robots, hex {geom['nx']}x{geom['ny']} pitch {geom['pitch']}, "
                                    f"world +-{geom['half']:g}, grid {geom['grid']}^2, {world} slabs of grid rows",
                        "sort_interval": "timestep (sort every step)", "collide_mode": "exact",
-                       "l2": "flushed between timed steps (256 MiB write)", "halo_rows": HALO_ROWS},
+                       "l2": "flushed between timed steps (256 MiB write)", "halo_rows": HALO_ROWS,
+                       "exchange": "peer-to-peer stores into the neighbour's mailbox (CUDA IPC over NVLink)" if args.exchange == "p2p"
+                                   else "NCCL send/recv of fixed-size buffers"},
             "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 20 * n_total,
                     "d2h_bytes_per_step": 20 * n_total, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "what": "per rank: pos/vel/rad of the owned robots from pinned host -> device, SlabSim.step, device -> pinned host"},
@@ -446,5 +534,6 @@ def bench_slabs(args, rank, world, local_rank):
             "state_finite": bool(finite.item()),
         }
         print(json.dumps(line))
+    sim.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -30,7 +30,7 @@ def _initial_velocity(gid):
     return v
 
 
-def _worker(rank, world, port, out_path, bin_mode):
+def _worker(rank, world, port, out_path, bin_mode, exchange):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -38,7 +38,7 @@ def _worker(rank, world, port, out_path, bin_mode):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     p, o, geom = _config()
     prs.lib().prs_bin_set_mode(bin_mode)      # 0 auto, 1 onesweep + in-cell insertion sort, 2 cell binning
-    sim = multigpu.make_hex_slab(p, o, geom, multigpu.CudaBackend, rank, world, dev, 5555, 0.01 * p.max_radius)
+    sim = multigpu.make_hex_slab(p, o, geom, multigpu.CudaBackend, rank, world, dev, 5555, 0.01 * p.max_radius, exchange=exchange)
     n0 = sim.n
     sim.s.vel[:n0] = torch.from_numpy(_initial_velocity(sim.s.gid[:n0].cpu().numpy())).to(dev)
     snaps = {}
@@ -51,6 +51,7 @@ def _worker(rank, world, port, out_path, bin_mode):
     dist.all_gather_object(stats, (sim.n, sim.stats["migrated"], sim.stats["halo"]))
     if rank == 0:
         np.savez(out_path, stats=np.array(stats), **{f"{key}_{k}": v for k, g in snaps.items() for key, v in g.items()})
+    sim.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,13 +62,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,bin_mode", [(2, 0), (2, 1), (2, 2), (4, 0), (8, 0), (8, 2)])
-def test_slabs_bit_equal_to_single_gpu(world, bin_mode, tmp_path):
+@pytest.mark.parametrize("world,bin_mode,exchange", [(2, 0, "p2p"), (2, 1, "nccl"), (2, 2, "p2p"), (2, 2, "nccl"), (4, 0, "p2p"),
+                                                     (8, 0, "p2p"), (8, 2, "nccl")])
+def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     out = str(tmp_path / "slabs.npz")
-    mp.spawn(_worker, args=(world, _free_port(), out, bin_mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, bin_mode, exchange), nprocs=world, join=True)
     got = np.load(out)
     p, o, geom = _config()
     torch.cuda.set_device(0)
