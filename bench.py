@@ -208,7 +208,7 @@ def hex_positions(p, geom):
 
 
 def timed_steps(torch, sim, dt, sort_interval, steps, warmup, flush):
-    """ms per step of sim.update over `steps` steps (CUDA events on the current stream, L2 flushed between steps)"""
+    """median ms per step of sim.update over `steps` steps (CUDA events on the current stream, L2 flushed between steps)"""
     stream = torch.cuda.current_stream()
     for _ in range(warmup):
         sim.update(dt, sort_interval)
@@ -220,7 +220,7 @@ def timed_steps(torch, sim, dt, sort_interval, steps, warmup, flush):
         sim.update(dt, sort_interval)
         b.record(stream)
     torch.cuda.synchronize()
-    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    return float(np.median([a.elapsed_time(b) for a, b in ev]))   # median: the reference's per-sort cudaMalloc/cudaFree makes outliers
 
 
 def ref_cuda_block(torch, prs, flush, steps=30, warmup=5):
