@@ -427,6 +427,16 @@ def run_gpu(args):
                "sample": f"same lattice at 2^{cpu_log2} robots, {done} steps after 1 warm-up, sort every step ({dt:.1f} s of "
                          f"{threads}-thread OpenMP work; oracle/prs_oracle.cpp)"}
 
+    # ---- secondary: the reference's cadence — hash + sort only every 180 s of simulated time ----
+    secondary = None
+    if not ref_cuda and sort_interval <= o.timestep:
+        sim2 = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
+        sim2.init_hex(geom["nx"], geom["ny"], geom["pitch"], JITTER_FRAC * p.max_radius, SEED)
+        ms2 = timed_steps(torch, sim2, o.timestep, 180.0, min(args.steps, 100), 10, flush)
+        sim2.close()
+        secondary = {"sort_interval": 180.0, "ms_per_step": ms2, "value": n / (ms2 * 1e-3), "unit": "particle-steps/s",
+                     "what": "same swarm, reference cadence: controller+integrate, gather, collide on the step-0 ordering (Q1)"}
+
     ref_cuda_cmp = None
     if not ref_cuda and not args.no_ref_cuda:
         ref_cuda_cmp = ref_cuda_block(torch, prs, flush)
@@ -441,7 +451,7 @@ def run_gpu(args):
                    "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)"},
         "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
-        "stages": stages, "cpu_baseline": cpu, "ref_cuda": ref_cuda_cmp, "state_finite": finite,
+        "stages": stages, "cpu_baseline": cpu, "ref_cuda": ref_cuda_cmp, "secondary": secondary, "state_finite": finite,
     }
     if ref_cuda:
         line["impl"] = "ref-cuda"

@@ -520,11 +520,18 @@ void prs_slab_mailbox_free(void *p) { if (p) PRS_CUDA(cudaFree(p)); }
 void prs_ipc_export(void *dev_ptr, void *handle_out) {
   PRS_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_out, dev_ptr));
 }
+/* returns NULL (and clears the error) if the peer's memory cannot be mapped — the caller then
+ * falls back to the NCCL exchange on every rank */
 void *prs_ipc_open(const void *handle) {
   void *p = nullptr;
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, sizeof(h));
-  PRS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "prs_ipc_open: %s — peer-to-peer exchange not available\n", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return nullptr;
+  }
   return p;
 }
 void prs_ipc_close(void *p) { if (p) PRS_CUDA(cudaIpcCloseMemHandle(p)); }

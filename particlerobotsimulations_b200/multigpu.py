@@ -242,11 +242,25 @@ class SlabSim:
         handles = [None] * self.world
         dist.all_gather_object(handles, handle.raw, group=self.group)
         self.peer = [None, None]     # [lower, upper] neighbour's mailbox in this process's address space
-        if self.rank > 0:
-            self.peer[0] = int(lib.prs_ipc_open(C.create_string_buffer(handles[self.rank - 1], len(handles[self.rank - 1]))))
-        if self.rank < self.world - 1:
-            self.peer[1] = int(lib.prs_ipc_open(C.create_string_buffer(handles[self.rank + 1], len(handles[self.rank + 1]))))
+        ok = 1
+        for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= nb < self.world:
+                ptr = lib.prs_ipc_open(C.create_string_buffer(handles[nb], len(handles[nb])))
+                self.peer[side] = int(ptr) if ptr else None
+                ok &= int(bool(ptr))
         torch.cuda.synchronize()
+        # every rank must use the same exchange: if any mapping failed, all fall back to NCCL
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            for pp in self.peer:
+                if pp:
+                    lib.prs_ipc_close(C.c_void_p(pp))
+            lib.prs_slab_mailbox_free(C.c_void_p(self.mailbox))
+            self.mailbox, self.peer, self.exchange = None, [None, None], "nccl"
+            if self.rank == 0:
+                import sys
+                print("multigpu: peer-to-peer mapping unavailable, using the NCCL exchange", file=sys.stderr, flush=True)
         dist.barrier(group=self.group)
 
     def _mb_buf(self, base, src, kind, parity):
@@ -515,7 +529,7 @@ def bench_slabs(args, rank, world, local_rank):
                                    f"world +-{geom['half']:g}, grid {geom['grid']}^2, {world} slabs of grid rows",
                        "sort_interval": "timestep (sort every step)", "collide_mode": "exact",
                        "l2": "flushed between timed steps (256 MiB write)", "halo_rows": HALO_ROWS,
-                       "exchange": "peer-to-peer stores into the neighbour's mailbox (CUDA IPC over NVLink)" if args.exchange == "p2p"
+                       "exchange": "peer-to-peer stores into the neighbour's mailbox (CUDA IPC over NVLink)" if sim.exchange == "p2p"
                                    else "NCCL send/recv of fixed-size buffers"},
             "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 20 * n_total,
                     "d2h_bytes_per_step": 20 * n_total, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
