@@ -107,13 +107,28 @@ __global__ void __launch_bounds__(1024) k_cell_scan_tiles(uint32_t *scratch, uin
   }
 }
 
+template <bool SELF_PREFIX>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
              uint32_t *scratch, uint32_t slot_offset) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c0 = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
-  const uint32_t tile_offset = slot_offset + scratch[4 + gridDim.x + blockIdx.x]; /* slab ranks: slots start after the lower halo */
+  /* offset of this tile: from k_cell_scan_tiles, or — few tiles (SELF_PREFIX) — summed here from the
+   * tile sums, which saves the one-block scan kernel and its launch (5 us at 2^20 robots) */
+  uint32_t tile_offset = slot_offset; /* slab ranks: slots start after the lower halo */
+  if (SELF_PREFIX) {
+    uint32_t part = 0;
+    for (uint32_t t = tid; t < blockIdx.x; t += SCAN_THREADS) part += scratch[4 + t];
+    part = __reduce_add_sync(0xffffffffu, part);
+    __shared__ uint32_t s_part[SCAN_THREADS / 32];
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) tile_offset += s_part[w];
+  } else {
+    tile_offset += scratch[4 + gridDim.x + blockIdx.x];
+  }
   uint32_t cnt[SCAN_ITEMS];
   load_counts(cellCount, c0, C, cnt);
   uint32_t sum = 0, mx = 0;
@@ -199,6 +214,7 @@ k_reorder_binned(const uint32_t *__restrict__ hash_by_slot, const uint32_t *__re
   sortedVel[dst] = v;
 }
 
+constexpr uint32_t SELF_PREFIX_MAX_TILES = 2048; /* up to 8 M cells: every apply block sums the tile sums before it */
 inline size_t scan_scratch_words(uint32_t C) { return 4 + 2 * ((size_t)(C + SCAN_TILE - 1) / SCAN_TILE); }
 constexpr int SCAN_TILE_LOG2 = 12;
 static_assert((1 << SCAN_TILE_LOG2) == SCAN_TILE, "tile size");

@@ -903,9 +903,14 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       StageScope t(PRS_STAGE_SORT);
       const unsigned tiles = div_up(b->numCells, prs_bin::SCAN_TILE);
       PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->numCells, B.scratch);
-      PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
-      PRS_LAUNCH(prs_bin::k_cell_apply, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                 B.scratch, 0u);
+      if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
+        PRS_LAUNCH(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
+                   B.scratch, 0u);
+      } else {
+        PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
+        PRS_LAUNCH(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
+                   B.scratch, 0u);
+      }
       PRS_LAUNCH(prs_bin::k_cell_scatter, div_up(n, 256), 256, 0, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
     }
     {

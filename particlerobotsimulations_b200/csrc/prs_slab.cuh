@@ -404,9 +404,14 @@ void prs_slab_sort(const prs_slab *s) {
     PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
     PRS_LAUNCH(k_slab_tickets, div_up(s->cap, 256), 256, 0, *s, B.cellCount, w.vals[0]);
     PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, cells, B.scratch);
-    PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
-    PRS_LAUNCH(prs_bin::k_cell_apply, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-               cells, B.scratch, s->halo_cap);
+    if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
+      PRS_LAUNCH(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
+                 cells, B.scratch, s->halo_cap);
+    } else {
+      PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
+      PRS_LAUNCH(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
+                 cells, B.scratch, s->halo_cap);
+    }
     PRS_LAUNCH(k_slab_scatter, div_up(s->cap, 256), 256, 0, *s, w.vals[0], w.vals[1]);
     g_prs.slab_table_fresh = true; /* consumed by this step's gather and cell_table */
     return;
