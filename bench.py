@@ -323,6 +323,10 @@ def run_gpu(args):
         sim = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
     sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], JITTER_FRAC * p.max_radius, SEED)
     pos0 = sim.get(prs.POSITION)
+    if args.scramble:   # robot index unrelated to position (the reference's aggregation placement is like that)
+        pos0 = pos0[np.random.default_rng(SEED).permutation(n)]
+        sim.set(prs.POSITION, pos0)
+        geom["name"] += " (robot order scrambled)"
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -470,6 +474,7 @@ def main():
     ap.add_argument("--collide-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-kernels-on-R1 comparison block")
+    ap.add_argument("--scramble", action="store_true", help="N = 1: permute the robots so that index order is unrelated to position")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: neighbour exchange by peer-to-peer stores into mapped mailboxes (default) or NCCL send/recv")
     ap.add_argument("--workload", default="s1", choices=["s1", "r1"],
