@@ -10,6 +10,7 @@ for c in example example_dead_cells example_obstacle example_gap example_object_
 done
 python bench.py --robots-log2 23 --steps 20 --warmup 5 --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_2p23.json 2> gpurun_out/bench_2p23.err
 python bench.py --robots-log2 26 --steps 8 --warmup 4 --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_2p26.json 2> gpurun_out/bench_2p26.err
+python scripts/cpu_oracle_cfgs.py 2>/dev/null | tail -5 >> gpurun_out/small_n.log
 grep -A1 "fused\|ext:" gpurun_out/small_n.log | grep ParticleBot | head -12
 python - <<'PY'
 import json
