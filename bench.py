@@ -76,32 +76,71 @@ def algorithmic_bytes(p, sort_every_step=True):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  Started before the warm-up (the tool
-    needs ~0.1 s to come up), polled every 20 ms; `mark()` brackets the timed region and the report
-    uses the samples inside it (all samples under load if the region was shorter than the polling)."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line), polled
+    through NVML every 5 ms from a thread (nvidia-smi as a fallback: it needs a second or more to come
+    up on an 8-GPU box, longer than a short timed region).  `mark()` brackets the timed region; the
+    report uses the samples inside it (all samples taken under load if the region was too short)."""
 
-    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (time, sm_mhz, max_mhz, reasons bitmask)
         self.t0 = self.t1 = None
+        self._stop = False
+        self.thread = None
+        self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].strip().isdigit() else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def poll():
+                while not self._stop:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), float(sm), float(mx), int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.source = "nvidia-smi"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+
+            def read():
+                bits = (0x8, 0x40, 0x20, 0x4)
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    try:
+                        rs = sum(b for b, v in zip(bits, f[2:6]) if v.lower().startswith("active"))
+                        self.samples.append((time.time(), float(f[0]), float(f[1]), rs))
+                    except (ValueError, IndexError):
+                        pass
+
+            self.thread = threading.Thread(target=read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
 
     def mark(self):
         """call at the start and at the end of the timed region"""
@@ -111,33 +150,21 @@ class ClockSampler:
             self.t1 = time.time()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-
-        def parse(rows):
-            sm, mx, reasons = [], [], set()
-            for _, ln in rows:
-                f = [x.strip() for x in ln.split(",")]
-                if len(f) < 10:
-                    continue
-                try:
-                    sm.append(float(f[2])); mx.append(float(f[3]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            return sm, mx, reasons
-
-        inside = [r for r in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.02]
+        self._stop = True
+        if self.proc:
+            self.proc.terminate()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"], "samples": 0}
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1 + 0.005]
         scope = "timed region"
         if len(inside) < 2:
-            inside, scope = self.lines, "warm-up + timed region + stage timing (timed region shorter than the polling interval)"
-        sm, mx, reasons = parse(inside)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
+            inside, scope = self.samples, "warm-up + timed region + stage timing (timed region shorter than two polls)"
+        mask = 0
+        for x in inside:
+            mask |= x[3]
+        return {"sm_mhz": float(np.median([x[1] for x in inside])), "sm_max_mhz": max(x[2] for x in inside),
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(inside), "scope": scope,
+                "source": self.source}
 
 
 def ncu_traffic(kernel):
