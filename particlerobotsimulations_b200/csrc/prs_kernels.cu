@@ -836,8 +836,13 @@ static void bin_poll_report() {
   if (!B.report_pending || cudaEventQuery(B.report_event) != cudaSuccess) return;
   B.report_pending = false;
   if (B.h_report[1]) {
-    fprintf(stderr, "prs_fused_step: a cell held more than %u robots on the binned route\n", prs_bin::MAX_RANKED_CELL);
-    exit(EXIT_FAILURE);
+    /* a cell outgrew the in-cell ranking between two reports (in practice: a swarm that blew up to NaN,
+     * every NaN position hashes to cell 0).  Those cells were filed in arrival order for the steps in
+     * between; from here on the onesweep route is taken, as the pop > 64 test below would also decide. */
+    static bool warned = false;
+    if (!warned) fprintf(stderr, "prs_fused_step: a cell held more than %u robots; cell binning switched off\n", prs_bin::MAX_RANKED_CELL);
+    warned = true;
+    B.admitted = false;
   }
   const uint32_t pop = B.h_report[0];
   if (B.admitted) { if (pop > 64u) B.admitted = false; }
