@@ -445,6 +445,21 @@ def run_gpu(args):
            "what": "copyArrayToDevice(pos,vel,rad from pinned host) -> Particlebot::update -> copyArrayFromDevice(pos,vel,rad)"}
 
     finite = bool(np.isfinite(sim.get(prs.POSITION)).all())
+    # ---- the dominant kernel against the unit that actually binds it (informational, next to the HBM roofline) ----
+    roofline_compute = None
+    if not ref_cuda and stages and "collide" in stages:
+        h = sim.get(prs.HASH).astype(np.int64)
+        gdim = int(p.gridSize.x)
+        cnt = np.bincount(h, minlength=gdim * gdim).reshape(gdim, gdim).astype(np.int64)
+        box = sum(np.roll(np.roll(cnt, dy, 0), dx, 1) for dy in range(-2, 3) for dx in range(-2, 3))   # 5x5 stencil, wrapped
+        pairs = int((cnt * box).sum() - n)                     # ordered neighbour pairs evaluated per step
+        sm_clock_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
+        xu_peak = 148 * 16 * sm_clock_hz / 4.0                 # 16 MUFU lanes per SM and clock, 4 MUFU ops per far pair
+        rate = pairs / (stages["collide"]["avg_us"] * 1e-6)
+        roofline_compute = {"kernel": "collide", "bound": "xu (MUFU) pipe", "pairs_per_step": pairs, "achieved": rate, "peak": xu_peak,
+                            "unit": "neighbour pairs/s", "frac": rate / xu_peak,
+                            "what": "4 MUFU ops (rsqrt, lg2, ex2, rcp) per far pair are what the reference's formulas need after sharing; "
+                                    "peak = 148 SMs x 16 MUFU lanes x SM clock / 4"}
     sim.close()
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port, all threads, a few steps of the same swarm ----
@@ -481,7 +496,7 @@ def run_gpu(args):
                    "sort_interval": "timestep (sort every step)" if sort_interval <= o.timestep else sort_interval,
                    "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)"},
         "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step, "roofline_compute": roofline_compute,
         "stages": stages, "cpu_baseline": cpu, "ref_cuda": ref_cuda_cmp, "secondary": secondary, "state_finite": finite,
     }
     if ref_cuda:
