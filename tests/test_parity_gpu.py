@@ -663,3 +663,21 @@ def test_long_horizon_observables_vs_reference_kernels(name):
         assert abs(d_new - d_ref) <= 0.02 * max(d_ref, 1e-3), (d_new, d_ref)
     # stronger than the bar: the path is bit-identical to the reference kernels, so the tracks coincide
     assert np.array_equal(c_ref, c_new)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 33])
+def test_tiny_swarms_vs_reference_kernels(n):
+    """Degenerate sizes: a single robot (no pair at all), two robots (one pair, in contact), three, and one
+    robot more than a warp — 60 steps, sort every step, against the reference's own kernels."""
+    if not util.refcuda_available():
+        pytest.skip("oracle/_ref/libprs_refcuda.so not built (needs /root/reference at build time)")
+    p, o = util.cfg("example")
+    p.nCells = n
+    ref = _run(p, o, prs.BACKEND_EXTERNAL, 60, ob.REFCUDA_PATH, o.timestep)
+    for bname, kind, _ in _backends():
+        got = _run(p, o, kind, 60, None, o.timestep)
+        for a, b in zip(got, ref):
+            for k in ("hash", "index", "pos", "vel", "rad", "phase"):
+                assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (bname, k, a["step"])
+            occupied = np.unique(b["hash"])
+            assert np.array_equal(a["cs"][occupied], b["cs"][occupied]) and np.array_equal(a["ce"][occupied], b["ce"][occupied])
