@@ -66,6 +66,12 @@ def swarm_config(prs, log2n, world64=False, nx=None, ny=None, pitch=None):
     return p, o, dict(name=name, nx=nx, ny=ny, half=half, grid=grid, light=light, pitch=pitch)
 
 
+def workload_text(geom, n):
+    """the `config.workload` string, shared by both arms"""
+    return (f"{geom['name']}: {n} robots, hex {geom['nx']}x{geom['ny']} pitch {geom['pitch']}, "
+            f"world +-{geom['half']:g}, grid {geom['grid']}^2, light {geom['light']}")
+
+
 def algorithmic_bytes(p, sort_every_step=True):
     """B_alg = 158 + 16*P + 4*C/N per particle-step (146 + 4*C/N without the sort)."""
     bits = int(np.ceil(np.log2(p.numCells)))
@@ -281,8 +287,8 @@ def run_reference_cpu(args):
     p, o, geom = swarm_config(prs, 14)
     rate, _, _ = cpu_oracle_throughput(p, o, geom, hex_positions(p, geom), 3, threads)
     sample = 14
-    while sample + 2 <= log2n and (1 << (sample + 2)) * (args.steps + args.warmup) / rate < budget_s:
-        sample += 2
+    while sample + 2 <= min(log2n, 22) and (1 << (sample + 2)) * (args.steps + args.warmup) / rate < budget_s:
+        sample += 2            # at most 2^22 robots: bounded host memory and time whatever K and W are
     p, o, geom = swarm_config(prs, sample)
     pos0 = hex_positions(p, geom)
     L = ob.lib()
@@ -302,7 +308,8 @@ def run_reference_cpu(args):
         "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"S1 synthetic hex swarm (2^{log2n} robots), CPU sample 2^{sample}", "sort_interval": "timestep"},
+        "config": {"workload": workload_text(swarm_config(prs, log2n)[2], 1 << log2n),
+                   "sort_interval": "timestep (sort every step)", "cpu_sample": f"2^{sample} robots of the same lattice"},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -491,8 +498,7 @@ def run_gpu(args):
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{geom['name']}: {n} robots, hex {geom['nx']}x{geom['ny']} pitch {geom['pitch']}, "
-                               f"world +-{geom['half']:g}, grid {geom['grid']}^2, light {geom['light']}",
+        "config": {"workload": workload_text(geom, n),
                    "sort_interval": "timestep (sort every step)" if sort_interval <= o.timestep else sort_interval,
                    "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)"},
         "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},

@@ -525,8 +525,7 @@ def bench_slabs(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{geom['name']}: {n_total} robots, hex {geom['nx']}x{geom['ny']} pitch {geom['pitch']}, "
-                                   f"world +-{geom['half']:g}, grid {geom['grid']}^2, {world} slabs of grid rows",
+            "config": {"workload": bench.workload_text(geom, n_total), "decomposition": f"{world} slabs of grid rows",
                        "sort_interval": "timestep (sort every step)", "collide_mode": "exact",
                        "l2": "flushed between timed steps (256 MiB write)", "halo_rows": HALO_ROWS,
                        "exchange": "peer-to-peer stores into the neighbour's mailbox (CUDA IPC over NVLink)" if sim.exchange == "p2p"
