@@ -251,6 +251,8 @@ void prs_sim_get(prs_sim *s, int which, void *host, size_t bytes);
 void prs_sim_set(prs_sim *s, int which, const void *host, size_t offset_bytes, size_t bytes);
 /* dumpParticlebot (particlebot.cpp:303-367): CSV row when the dump gate fires */
 void prs_sim_dump(prs_sim *s, void *FILE_ptr, float dump_interval, unsigned testing);
+/* loadFromFile (particlebot.cpp:369-411): time, positions, velocities, radii from the LAST row of a testing=1 CSV */
+void prs_sim_load(prs_sim *s, void *FILE_ptr);
 
 #ifdef __cplusplus
 }

@@ -144,7 +144,7 @@ SIGNATURES = {
     "prs_sim_update": (_I, [_VP, _F, _F]), "prs_sim_time": (_F, [_VP]), "prs_sim_sync": (None, [_VP]),
     "prs_sim_device_ptr": (_VP, [_VP, _I]), "prs_sim_get": (None, [_VP, _I, _VP, C.c_size_t]),
     "prs_sim_set": (None, [_VP, _I, _VP, C.c_size_t, C.c_size_t]),
-    "prs_sim_dump": (None, [_VP, _VP, _F, _U]),
+    "prs_sim_dump": (None, [_VP, _VP, _F, _U]), "prs_sim_load": (None, [_VP, _VP]),
 }
 
 

@@ -596,4 +596,8 @@ void prs_sim_dump(prs_sim *s, void *fp, float dump_interval, unsigned testing) {
   const SimParams &P = s->bot->getParams();
   s->bot->dumpParticlebot(0, P.nCells, (FILE *)fp, dump_interval, testing, P.light_x, P.light_y);
 }
+void prs_sim_load(prs_sim *s, void *fp) {
+  const SimParams &P = s->bot->getParams();
+  s->bot->loadFromFile(0, P.nCells, (FILE *)fp, 0.0f);
+}
 }

@@ -681,3 +681,72 @@ def test_tiny_swarms_vs_reference_kernels(n):
                 assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (bname, k, a["step"])
             occupied = np.unique(b["hash"])
             assert np.array_equal(a["cs"][occupied], b["cs"][occupied]) and np.array_equal(a["ce"][occupied], b["ce"][occupied])
+
+
+def _c_file(path, mode):
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    return libc, libc.fopen(str(path).encode(), mode.encode())
+
+
+def test_csv_dump_format_and_resume(tmp_path):
+    """dumpParticlebot (particlebot.cpp:303-367): "Seed" line, header, one row per dump gate with %f fields —
+    time, [x, y per robot | vx, vy per robot | radius per robot when testing], centroid (sequential fp32 host
+    sum) and its distance to the light.  loadFromFile (:369-411) resumes time / pos / vel / rad from the last
+    row (lossy by design: six decimals)."""
+    p, o = util.cfg("example_dead_cells")
+    L = prs.lib()
+    sim = prs.Simulation(p, 64.0, prs.BACKEND_FUSED)
+    sim.srand(p.seed)
+    sim.reset()
+    libc, fp = _c_file(tmp_path / "run.csv", "w+")
+    interval = 0.05                                   # dump gate: time mod 0.05 <= 0.01 -> steps 0, 1, 5, 6, 10, ...
+    rows_expected, n = [], p.nCells
+    for k in range(12):
+        t = sim.time
+        if np.float32(t) - np.float32(interval) * np.floor(np.float32(t) / np.float32(interval)) <= np.float32(0.01):
+            pos, vel, rad = sim.get(prs.POSITION), sim.get(prs.VELOCITY), sim.get(prs.RADII)
+            sx = sy = np.float32(0.0)
+            for i in range(n):
+                sx = np.float32(sx + pos[i, 0]); sy = np.float32(sy + pos[i, 1])
+            cx, cy = np.float32(sx / np.float32(n)), np.float32(sy / np.float32(n))
+            row = "%f," % t + "".join("%f, %f," % (x, y) for x, y in pos) + "".join("%f, %f," % (x, y) for x, y in vel)
+            row += "".join("%f," % r for r in rad)
+            dist = np.float32(np.power(np.float32(np.power(np.float32(cx - np.float32(p.light_x)), np.float32(2.0)) +
+                                                  np.power(np.float32(cy - np.float32(p.light_y)), np.float32(2.0))), np.float32(0.5)))
+            rows_expected.append((row, cx, cy, dist))
+        L.prs_sim_dump(sim._h, fp, interval, 1)
+        sim.update(o.timestep, o.sort_interval)
+    libc.fclose(fp)
+    lines = open(tmp_path / "run.csv").read().split("\n")
+    assert lines[0] == "Seed, %u" % p.seed
+    header = "Time," + "".join("Particlebot_%d_xpos, Particlebot_%d_ypos," % (i, i) for i in range(n))
+    header += "".join("Particlebot_%d_xvel, Particlebot_%d_yvel," % (i, i) for i in range(n))
+    header += "".join("Particlebot_%d_rad," % i for i in range(n)) + "Centroid X, Centroid Y, Distance"
+    assert lines[1] == header
+    body = [ln for ln in lines[2:] if ln]
+    assert len(body) == len(rows_expected) >= 3
+    for ln, (row, cx, cy, dist) in zip(body, rows_expected):
+        assert ln.startswith(row)
+        tail = [float(x) for x in ln[len(row):].rstrip(",").split(",")]
+        assert abs(tail[0] - cx) < 2e-6 and abs(tail[1] - cy) < 2e-6 and abs(tail[2] - dist) < 2e-5 * max(1.0, dist)
+    # resume: a fresh simulation picks up the last row
+    last_time = float(body[-1].split(",")[0])
+    state = dict(pos=sim.get(prs.POSITION), vel=sim.get(prs.VELOCITY))
+    sim.close()
+    sim2 = prs.Simulation(p, 64.0, prs.BACKEND_FUSED)
+    sim2.srand(p.seed)
+    sim2.reset()
+    libc, fp = _c_file(tmp_path / "run.csv", "r")
+    L.prs_sim_load(sim2._h, fp)
+    libc.fclose(fp)
+    assert abs(sim2.time - last_time) < 1e-6
+    row_vals = [float(x) for x in body[-1].split(",")[1:1 + 5 * n]]
+    assert np.allclose(sim2.get(prs.POSITION).ravel(), np.array(row_vals[:2 * n], np.float32), atol=1e-6)
+    assert np.allclose(sim2.get(prs.VELOCITY).ravel(), np.array(row_vals[2 * n:4 * n], np.float32), atol=1e-6)
+    assert np.allclose(sim2.get(prs.RADII), np.array(row_vals[4 * n:5 * n], np.float32), atol=1e-6)
+    sim2.update(o.timestep, o.sort_interval)
+    assert np.all(np.isfinite(sim2.get(prs.POSITION)))
+    sim2.close()
