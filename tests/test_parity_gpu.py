@@ -750,3 +750,64 @@ def test_csv_dump_format_and_resume(tmp_path):
     sim2.update(o.timestep, o.sort_interval)
     assert np.all(np.isfinite(sim2.get(prs.POSITION)))
     sim2.close()
+
+
+@pytest.mark.parametrize("n", [1, 64, 65, 300, 5000, 100_000])
+def test_calc_cog_bit_equal_to_reference(n):
+    """calcCOG (particlebot_cuda.cu:241-281, kernel_impl.cuh:295-349): 64-wide tree levels, result scaled by
+    1/N, y tagged +2000, stored in the trail slot pos[N + ind]."""
+    if not util.refcuda_available():
+        pytest.skip("oracle/_ref/libprs_refcuda.so not built (needs /root/reference at build time)")
+    p, o = util.cfg("example")
+    p.nCells = n
+    rng = np.random.default_rng(n)
+    hist = 16
+    pos = np.zeros((n + hist + 1, 2), np.float32)
+    pos[:n] = (rng.random((n, 2), dtype=np.float32) - 0.5) * 30.0
+    out = []
+    for lib in (prs.lib(), util.refcuda()):
+        lib.setParameters(C.byref(p))
+        d_pos, t1, t2 = Dev(pos, lib=lib), Dev(np.zeros((n + 64, 2), np.float32), lib=lib), Dev(np.zeros((n + 64, 2), np.float32), lib=lib)
+        for time in (0.0, 30.0, 70.0):
+            lib.calcCOG(d_pos.ptr, t1.ptr, t2.ptr, n, time, hist, 10.0)
+        lib.threadSync()
+        out.append(d_pos.get(np.float32, (n + hist + 1, 2)))
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
+    slot = out[0][n + 3]                      # time 30 / interval 10 -> slot 3
+    assert abs(slot[0] - pos[:n, 0].astype(np.float64).mean()) < 1e-3 and abs(slot[1] - 2000.0 - pos[:n, 1].astype(np.float64).mean()) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["example_dead_cells", "example_obstacle", "example_gap"])
+def test_update_col_matches_reference(name):
+    """updateCol (kernel_impl.cuh:401-443): radius -> RGB, dead robots black, optional shadow darkening."""
+    if not util.refcuda_available():
+        pytest.skip("oracle/_ref/libprs_refcuda.so not built (needs /root/reference at build time)")
+    p, o = util.cfg(name)
+    p.display_shadow = 1
+    n = p.nCells
+    rng = np.random.default_rng(3)
+    pos = ((rng.random((n, 2), dtype=np.float32) - 0.5) * 12.0).astype(np.float32)
+    rad = (p.min_radius + rng.random(n, dtype=np.float32) * (p.max_radius - p.min_radius)).astype(np.float32)
+    dead = (rng.random(n) < 0.2).astype(np.int32)
+    col0 = rng.random((n, 4), dtype=np.float32)
+    out = []
+    for lib in (prs.lib(), util.refcuda()):
+        lib.setParameters(C.byref(p))
+        d = [Dev(rad, lib=lib), Dev(col0, lib=lib), Dev(pos, lib=lib), Dev(np.zeros(n, np.float32), lib=lib), Dev(dead, lib=lib)]
+        lib.updateCol(d[0].ptr, d[1].ptr, n, d[2].ptr, d[3].ptr, d[4].ptr)
+        lib.threadSync()
+        out.append(d[1].get(np.float32, (n, 4)))
+    assert np.allclose(out[0], out[1], rtol=0, atol=2e-6)       # double-precision HSL round trip: last-bit freedom
+    assert np.all(out[0][dead == 1, :3] == 0.0) and np.array_equal(out[0][:, 3], col0[:, 3])
+
+
+def test_centroid_observable():
+    """prs_centroid: device-side swarm centroid (double accumulation) for the observables of SURVEY §8f."""
+    L = prs.lib()
+    rng = np.random.default_rng(5)
+    for n in (1, 1000, 300_001):
+        pos = ((rng.random((n, 2), dtype=np.float32) - 0.5) * 200.0).astype(np.float32)
+        d_pos, scratch, out = Dev(pos), Dev(np.zeros(256 * 2, np.float64)), Dev(np.zeros(2, np.float32))
+        L.prs_centroid(d_pos.ptr, n, scratch.ptr, out.ptr)
+        L.threadSync()
+        assert np.allclose(out.get(), pos.astype(np.float64).mean(0).astype(np.float32), rtol=0, atol=1e-5)

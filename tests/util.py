@@ -31,7 +31,7 @@ def refcuda():
         L = C.CDLL(ob.REFCUDA_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
         names = ["allocateArray", "freeArray", "threadSync", "copyArrayToDevice", "copyArrayFromDevice",
                  "setParameters", "integrateSystem", "calcHash", "sortParticlebots", "reorderDataAndFindCellStart",
-                 "collide", "updateRad_light_wave", "updatePhase", "curand_setup", "add_normal_noise", "calcCOG"]
+                 "collide", "updateRad_light_wave", "updatePhase", "curand_setup", "add_normal_noise", "calcCOG", "updateCol"]
         prs.bind_signatures(L, names)
         _ref = L
     return _ref
