@@ -811,3 +811,20 @@ def test_centroid_observable():
         L.prs_centroid(d_pos.ptr, n, scratch.ptr, out.ptr)
         L.threadSync()
         assert np.allclose(out.get(), pos.astype(np.float64).mean(0).astype(np.float32), rtol=0, atol=1e-5)
+
+
+def test_error_convention_exit_failure(tmp_path):
+    """Errors follow the reference's convention (include/helper_cuda.h:999-1031): message on stderr and
+    exit(EXIT_FAILURE).  More obstacles than the reference's 10-entry constant arrays is refused (the
+    reference overruns them); the GL interop entry points of the headless build abort when called."""
+    import subprocess, sys
+    code = (
+        "import ctypes as C, particlerobotsimulations_b200 as prs\n"
+        "p, o = prs.load_cfg('examples/example_obstacle.cfg')\n"
+        "p.n_cir_obstacles = 11\n"
+        "prs.lib().setParameters(C.byref(p))\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=util.ROOT, capture_output=True, text=True)
+    assert r.returncode == 1 and "obstacles" in r.stderr
+    code = "import particlerobotsimulations_b200 as prs\nprs.lib().mapGLBufferObject(None)\n"
+    r = subprocess.run([sys.executable, "-c", code], cwd=util.ROOT, capture_output=True, text=True)
+    assert r.returncode == 1 and "headless" in r.stderr
