@@ -339,10 +339,38 @@ class SlabSim:
         if err:
             raise RuntimeError(f"rank {self.rank}: " + "; ".join(m for bit, m in prs.SLAB_ERRORS.items() if err & bit))
 
+    # ---- dead-cell draw (particlebot.cpp:178-194) and observables ------------------------------------
+    def _dead_draw(self):
+        """nDead distinct robots, `rand() % remaining` with erase, on the glibc stream seeded with the cfg's
+        seed (main.cpp:929) — every rank draws the same GLOBAL ids and marks the ones it owns.  (The
+        reference's placement consumes the stream first; swarms set up by a generator start it fresh.)"""
+        n_dead, n_total = int(self.p.nDead), int(self.p.nCells)
+        if n_dead <= 0:
+            return
+        libc = C.CDLL(None)
+        libc.srand(C.c_uint(int(self.p.seed)))
+        alive = list(range(n_total))
+        ids = []
+        for _ in range(min(n_dead, n_total)):
+            ids.append(alive.pop(libc.rand() % len(alive)))
+        dead_ids = torch.tensor(ids, dtype=self.s.gid.dtype, device=self.dev)
+        self.s.dead[torch.isin(self.s.gid, dead_ids) & (torch.arange(self.cap, device=self.dev) < self.n)] = 1
+
+    def centroid(self):
+        """swarm centroid over all ranks (observable; one all_reduce of three doubles, not part of a step)"""
+        n = self.n
+        acc = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        acc[:2] = self.s.pos[:n].double().sum(0)
+        acc[2] = n
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        return (acc[:2] / acc[2]).cpu().numpy()
+
     # ---- one step (Particlebot::update, particlebot.cpp:170-300, cut at the exchanges) ----------------
     def step(self, dt, sort_interval):
         p, be = self.p, self.be
         time = self.time
+        if np.float32(time) >= np.float32(p.time_to_dead) and np.float32(time) < np.float32(p.time_to_dead) + np.float32(dt):
+            self._dead_draw()
         phase_step = self._gate(time, p.phase_update_interval, dt)
         sort_step = self._gate(time, sort_interval, dt) or not self.sorted_once
         if phase_step:

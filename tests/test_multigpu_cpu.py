@@ -207,6 +207,7 @@ class OracleBackend:
 def _config():
     p, o = util.cfg("example")
     p.nCells = NX * NY
+    p.nDead = 200                  # dead-cell draw on step 0: every rank draws the same global ids
     p.light_x, p.light_y = -6.0, 0.0
     geom = dict(nx=NX, ny=NY, pitch=PITCH, half=64.0)
     return p, o, geom
@@ -231,9 +232,16 @@ def _worker(rank, world, port, out_path, sort_every):
         sim.step(o.timestep, sort_every * o.timestep)
         if k in (1, 5, STEPS):
             snaps[k] = sim.gather_global(NX * NY)
+    cen = sim.centroid()
+    n_own = sim.n
+    dead_parts = [None] * world
+    dist.all_gather_object(dead_parts, (sim.s.gid[:n_own].numpy().copy(), sim.s.dead[:n_own].numpy().copy()))
     if rank == 0:
         sim.check()
-        np.savez(out_path, migrated=sim.stats["migrated"], halo=sim.stats["halo"],
+        dead = np.zeros(NX * NY, np.int32)
+        for g, d in dead_parts:
+            dead[g] = d
+        np.savez(out_path, centroid=cen, dead=dead, migrated=sim.stats["migrated"], halo=sim.stats["halo"],
                  **{f"{key}_{k}": v for k, g in snaps.items() for key, v in g.items()})
     stats = [None] * world
     dist.all_gather_object(stats, (sim.n, sim.stats["migrated"], sim.stats["halo"]))
@@ -254,6 +262,7 @@ def _single_process_reference(sort_every=1):
     ids = np.arange(NX * NY)
     pos0 = multigpu.hex_block_positions(ids, NX, NY, PITCH, 0.01 * p.max_radius, 5555)
     s = ob.OracleSim(p, 64.0)
+    s.srand(p.seed)                # the dead draw continues the glibc stream seeded with the cfg's seed
     s.view("pos")[:] = pos0
     s.view("rad")[:] = p.min_radius
     s.view("vel")[:] = _initial_velocity(ids)
@@ -262,6 +271,7 @@ def _single_process_reference(sort_every=1):
         s.update(o.timestep, sort_every * o.timestep)
         if k in (1, 5, STEPS):
             snaps[k] = dict(pos=s.get("pos"), vel=s.get("vel"), rad=s.get("rad"), phase=s.get("phase"))
+    snaps["dead"] = s.get("dead")
     return snaps, p
 
 
@@ -277,6 +287,8 @@ def test_slabs_match_single_process(world, sort_every, tmp_path):
     assert stats[:, 0].sum() == NX * NY                   # every robot owned exactly once
     assert stats[:, 2].sum() > 0                          # halos were exchanged
     assert stats[:, 1].sum() > 0                          # robots migrated between slabs
+    assert got["dead"].sum() == 200 and np.array_equal(got["dead"], ref["dead"])      # same draw on every rank
+    assert np.allclose(got["centroid"], ref[STEPS]["pos"].astype(np.float64).mean(0), atol=1e-9)
     for k in (1, 5, STEPS):
         assert np.all(got[f"owner_{k}"] >= 0)
         # the phase noise stream belongs to the robot (seeded by global id): bit-equal at any time

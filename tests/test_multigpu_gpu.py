@@ -20,6 +20,7 @@ NX, NY, PITCH, STEPS = 256, 192, 0.17, 60
 def _config():
     p, o = util.cfg("example")
     p.nCells = NX * NY
+    p.nDead = 150                    # dead-cell draw on step 0 (every rank draws the same global ids)
     p.light_x, p.light_y = -30.0, 0.0
     return p, o, dict(nx=NX, ny=NY, pitch=PITCH, half=64.0)
 
@@ -76,6 +77,7 @@ def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, tmp_path):
     lib = prs.lib()
     lib.prs_set_stream(None)
     sim = prs.Simulation(p, 64.0, prs.BACKEND_FUSED)
+    sim.srand(p.seed)                # main.cpp:929 — the dead draw continues this stream
     sim.init_hex(NX, NY, PITCH, 0.01 * p.max_radius, 5555)
     sim.set(prs.VELOCITY, _initial_velocity(np.arange(NX * NY)))
     stats = got["stats"]
