@@ -95,6 +95,29 @@ def slab_rows(params, ny, pitch, world):
     return R
 
 
+def balanced_rows(params, y_local, world, group=None):
+    """Row boundaries R[0..world] that give every rank about the same number of robots, for ANY swarm:
+    each rank histograms the grid rows of the robots it currently holds (`y_local`), the histograms are
+    summed over the ranks, and the cuts are placed on the cumulative count (slabs by equal
+    robot count).  Needs an initialised process group when world > 1."""
+    gy = int(params.gridSize.y)
+    rows = np.clip(grid_row_of(y_local, params), 0, gy - 1)
+    hist = torch.from_numpy(np.bincount(rows, minlength=gy).astype(np.int64))
+    if world > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        hist = hist.to(dev)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        hist = hist.cpu()
+    cum = np.cumsum(hist.numpy())
+    total = int(cum[-1])
+    R = [0]
+    for b in range(1, world):
+        cut = int(np.searchsorted(cum, total * b / world, "left")) + 1     # first row AFTER the b/world quantile
+        R.append(min(max(cut, R[-1] + 1), gy - (world - b)))
+    R.append(gy)
+    return R
+
+
 # --------------------------------------------------------------------------------------------------
 class CudaBackend:
     """The slab engine of libparticlebot_b200.so on CUDA tensors (current torch stream)."""

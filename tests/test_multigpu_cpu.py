@@ -320,3 +320,22 @@ def test_hex_generator_matches_library_and_rows_partition():
         owner = np.searchsorted(np.array(rows[1:]), r, "right")
         counts = np.bincount(owner, minlength=world)
         assert counts.min() > 0.5 * NX * NY / world
+
+
+def test_balanced_rows_single_process():
+    """slab boundaries by equal robot count for a lopsided swarm (two blobs of very different size)"""
+    p, o, geom = _config()
+    rng = np.random.default_rng(1)
+    y = np.concatenate([rng.normal(-20.0, 1.0, 9000), rng.normal(15.0, 3.0, 1000)]).astype(np.float32)
+    # world > 1 needs a process group; the cut logic itself is exercised with a one-rank group
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1)
+    try:
+        for world in (2, 4, 8):
+            R = multigpu.balanced_rows(p, y, world)
+            assert R[0] == 0 and R[-1] == p.gridSize.y and all(b > a for a, b in zip(R, R[1:]))
+            owner = np.searchsorted(np.array(R[1:]), multigpu.grid_row_of(y, p), "right")
+            counts = np.bincount(owner, minlength=world)
+            assert counts.max() <= 1.35 * len(y) / world + 64, (world, counts)      # grid rows are the granularity
+    finally:
+        dist.destroy_process_group()
