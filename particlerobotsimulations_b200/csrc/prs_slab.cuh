@@ -507,7 +507,7 @@ __global__ void k_slab_wait(const unsigned *local_dn, const unsigned *local_up, 
     unsigned long long spins = 0;
     while ((int)(*f - seq) < 0) {
       __nanosleep(64);
-      if (++spins > (1ull << 26)) { atomicOr(&counts[PRS_SC_ERR], PRS_SLAB_ERR_PEER_TIMEOUT); break; } /* ~10 s: never hang the GPU */
+      if (++spins > (1ull << 24)) { atomicOr(&counts[PRS_SC_ERR], PRS_SLAB_ERR_PEER_TIMEOUT); break; } /* ~15 s: never hang the GPU */
     }
   }
   __threadfence_system();
