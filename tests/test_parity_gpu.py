@@ -828,3 +828,29 @@ def test_error_convention_exit_failure(tmp_path):
     code = "import particlerobotsimulations_b200 as prs\nprs.lib().mapGLBufferObject(None)\n"
     r = subprocess.run([sys.executable, "-c", code], cwd=util.ROOT, capture_output=True, text=True)
     assert r.returncode == 1 and "headless" in r.stderr
+
+
+def test_large_swarm_bit_equal_to_reference_kernels():
+    """Full-size check against the reference itself: 409 600 robots (the largest hex block the reference's
+    hard-coded +-64 world and 512^2 grid hold), sort every step, 300 steps — the fused path (cell binning,
+    thread-per-robot collide with packed arithmetic) must reproduce the reference kernels bit for bit."""
+    if not util.refcuda_available():
+        pytest.skip("oracle/_ref/libprs_refcuda.so not built (needs /root/reference at build time)")
+    import bench
+    out = {}
+    for name, backend, ext in (("ref", prs.BACKEND_EXTERNAL, ob.REFCUDA_PATH), ("new", prs.BACKEND_FUSED, None)):
+        p, o, geom = bench.swarm_config(prs, 0, world64=True, nx=640, ny=640)
+        sim = prs.Simulation(p, geom["half"], backend, ext)
+        sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], bench.JITTER_FRAC * p.max_radius, bench.SEED)
+        for k in range(300):
+            sim.update(o.timestep, o.timestep)
+            if k == 3:
+                sim.sync()       # lets the density report arrive: the binned route is taken from here on
+        out[name] = {key: sim.get(w) for key, w in (("pos", prs.POSITION), ("vel", prs.VELOCITY), ("rad", prs.RADII),
+                                                    ("phase", prs.PHASE), ("hash", prs.HASH), ("index", prs.INDEX))}
+        if name == "new":
+            assert prs.lib().prs_bin_active() == 1
+        sim.close()
+    assert np.all(np.isfinite(out["ref"]["pos"]))
+    for key in out["ref"]:
+        assert np.array_equal(out["ref"][key].view(np.uint32), out["new"][key].view(np.uint32)), key
