@@ -98,6 +98,7 @@ class Particlebot {
   void _finalize();
   void uploadInitialState();
 
+  bool sorted_once_ = false;
   float *hPos, *hVel, *hRad;
   int *hDead;
   float *hphase, *hfreq;

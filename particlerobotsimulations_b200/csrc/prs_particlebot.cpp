@@ -214,7 +214,10 @@ bool Particlebot::update(float deltaTime, float sort_interval) {
   }
 
   const bool phase_step = params.control == LIGHT_WAVE && gate(time, params.phase_update_interval, deltaTime);
-  const bool sort_step = gate(time, sort_interval, deltaTime);
+  /* the first update always hashes and sorts: at time 0 the gate fires anyway; after loadFromFile (time > 0)
+   * the reference would build its table from never-written hash/index arrays */
+  const bool sort_step = gate(time, sort_interval, deltaTime) || !sorted_once_;
+  sorted_once_ = true;
   const float spacing = 2.0f * params.min_radius;
 
   if (backend_kind_ == PRS_BACKEND_FUSED) {
