@@ -346,6 +346,10 @@ def run_gpu(args):
     stream = torch.cuda.current_stream()
     lib.prs_set_stream(C.c_void_p(stream.cuda_stream))
     lib.prs_set_collide_mode(args.collide_mode)
+    if args.collide_tile is not None:
+        lib.prs_set_collide_tile(args.collide_tile)
+    if args.pdl is not None:
+        lib.prs_set_pdl(args.pdl)
 
     if ref_cuda:
         from oracle import binding as ob
@@ -500,7 +504,9 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(geom, n),
                    "sort_interval": "timestep (sort every step)" if sort_interval <= o.timestep else sort_interval,
-                   "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)"},
+                   "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)",
+                   "collide_neighbours": "shared-memory windows staged by TMA bulk copies" if lib.prs_get_collide_tile() else "L1/L2",
+                   "programmatic_dependent_launch": bool(lib.prs_get_pdl())},
         "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step, "roofline_compute": roofline_compute,
         "stages": stages, "cpu_baseline": cpu, "ref_cuda": ref_cuda_cmp, "secondary": secondary, "state_finite": finite,
@@ -520,6 +526,8 @@ def main():
     ap.add_argument("--robots-log2", type=int, default=None)
     ap.add_argument("--sort-interval", type=float, default=None)
     ap.add_argument("--collide-mode", type=int, default=0)
+    ap.add_argument("--collide-tile", type=int, default=None, help="1: collide stages neighbour windows in shared memory by TMA; 0: L1/L2 (default: library default)")
+    ap.add_argument("--pdl", type=int, default=None, help="1: programmatic dependent launch between the kernels of the fused step (default: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-kernels-on-R1 comparison block")
     ap.add_argument("--scramble", action="store_true", help="N = 1: permute the robots so that index order is unrelated to position")

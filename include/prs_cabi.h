@@ -93,6 +93,15 @@ int prs_get_collide_mode(void);
 /* collide runs one WARP per robot for swarms of up to max_robots (latency-bound sizes; default 16384,
  * 0 = always one thread per robot).  Same bits either way. */
 void prs_set_collide_warp_max(unsigned max_robots);
+/* thread-per-robot collide on the packed sorted layout: 1 = each block stages the five stencil-row windows
+ * of its 256 slots in shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) and reads neighbours
+ * from there; 0 = neighbours through L1/L2.  Same bits either way. */
+void prs_set_collide_tile(int on);
+int prs_get_collide_tile(void);
+/* 1 = the kernels of prs_fused_step are launched with programmatic dependent launch (each kernel's blocks
+ * become resident while the previous kernel drains; griddepcontrol.wait orders the data).  Same results. */
+void prs_set_pdl(int on);
+int prs_get_pdl(void);
 /* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
 unsigned long long prs_launch_count(int reset);
 

@@ -114,6 +114,8 @@ SIGNATURES = {
     "prs_set_world_half_extent": (None, [_F]), "prs_get_world_half_extent": (_F, []),
     "prs_set_collide_mode": (None, [_I]), "prs_get_collide_mode": (_I, []),
     "prs_set_collide_warp_max": (None, [_U]),
+    "prs_set_collide_tile": (None, [_I]), "prs_get_collide_tile": (_I, []),
+    "prs_set_pdl": (None, [_I]), "prs_get_pdl": (_I, []),
     "prs_launch_count": (C.c_ulonglong, [_I]),
     "prs_stage_timing": (None, [_I]), "prs_stage_times": (None, [_VP, _VP]),
     "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),

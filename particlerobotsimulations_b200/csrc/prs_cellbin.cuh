@@ -56,6 +56,7 @@ __device__ __forceinline__ void load_counts(const uint32_t *cellCount, uint32_t 
  * done" counter, per-robot tile sums from K1, a running maximum — each cost 10-100 us in L2) */
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch) {
+  prs::pdl_sync();
   __shared__ uint32_t s_sum[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t cnt[SCAN_ITEMS];
@@ -76,6 +77,7 @@ k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *s
 
 /* exclusive scan of the T tile sums (one block) */
 __global__ void __launch_bounds__(1024) k_cell_scan_tiles(uint32_t *scratch, uint32_t num_tiles) {
+  prs::pdl_sync();
   __shared__ uint32_t s_sum[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,6 +113,7 @@ template <bool SELF_PREFIX>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
              uint32_t *scratch, uint32_t slot_offset) {
+  prs::pdl_sync();
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c0 = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
@@ -175,6 +178,7 @@ k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart,
 __global__ void __launch_bounds__(256)
 k_cell_scatter(const uint32_t *__restrict__ hash, const uint32_t *__restrict__ ticket, const uint32_t *__restrict__ cellStart,
                uint32_t *__restrict__ hash_by_slot, uint32_t *__restrict__ index_by_slot, uint32_t n) {
+  prs::pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t h = hash[i];
@@ -192,6 +196,7 @@ k_reorder_binned(const uint32_t *__restrict__ hash_by_slot, const uint32_t *__re
                  uint32_t *__restrict__ index, float4 *__restrict__ sortedPR, float2 *__restrict__ sortedVel,
                  const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad, uint32_t n,
                  uint32_t *scratch) {
+  prs::pdl_sync();
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t h = hash_by_slot[k];

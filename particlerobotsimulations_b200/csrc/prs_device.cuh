@@ -21,6 +21,16 @@ __constant__ PrsDevParams c_prm;
 
 namespace prs {
 
+/* Programmatic dependent launch (sm_90+): first statement of every kernel of the fused step.  When the
+ * kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization its blocks may become resident
+ * while the previous kernel of the stream drains; `wait` holds them until that kernel has completed and its
+ * writes are visible, `launch_dependents` lets the NEXT kernel's blocks do the same behind this one.  Without
+ * the attribute both are no-ops. */
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct v2 { float x, y; };
 __device__ __forceinline__ v2 mk(float x, float y) { v2 r; r.x = x; r.y = y; return r; }
 __device__ __forceinline__ v2 operator+(v2 a, v2 b) { return mk(a.x + b.x, a.y + b.y); }

@@ -50,6 +50,25 @@ void prs_fail(const char *what, cudaError_t e, const char *file, int line) {
     if (e_ != cudaSuccess) prs_fail(#kernel, e_, __FILE__, __LINE__);                \
   } while (0)
 
+/* launch with the programmatic-dependent-launch attribute (see prs::pdl_sync): the kernel's blocks may become
+ * resident while the previous kernel of the stream drains.  Only kernels that start with pdl_sync() may be
+ * launched this way. */
+#define PRS_LAUNCH_PDL(kernel, grid, block, ...)                                       \
+  do {                                                                               \
+    cudaLaunchConfig_t cfg_ = {};                                                    \
+    cfg_.gridDim = dim3(grid);                                                       \
+    cfg_.blockDim = dim3(block);                                                     \
+    cfg_.stream = g_prs.stream;                                                      \
+    cudaLaunchAttribute at_[1];                                                      \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                  \
+    at_[0].val.programmaticStreamSerializationAllowed = g_prs.pdl ? 1 : 0;           \
+    cfg_.attrs = at_;                                                                \
+    cfg_.numAttrs = 1;                                                               \
+    cudaError_t e_ = cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                 \
+    g_prs.launches++;                                                                \
+    if (e_ != cudaSuccess) prs_fail(#kernel, e_, __FILE__, __LINE__);                \
+  } while (0)
+
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 /* stage timing: an event pair per stage and step on the launching stream, read after a sync */
@@ -125,6 +144,7 @@ k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEn
                  float2 *__restrict__ sortedVel, const uint32_t *__restrict__ hash, const uint32_t *__restrict__ index,
                  const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad,
                  uint32_t n) {
+  prs::pdl_sync();
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t h = hash[k];
@@ -147,6 +167,7 @@ k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEn
 __global__ void __launch_bounds__(256)
 k_gather_packed(float4 *__restrict__ sortedPR, float2 *__restrict__ sortedVel, const uint32_t *__restrict__ index,
                 const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad, uint32_t n) {
+  prs::pdl_sync();
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t src = index[k];
@@ -273,6 +294,7 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
                          const int *__restrict__ dead, uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
                          float time, float dt, int run_controller, uint32_t n, const uint32_t *__restrict__ n_dev,
                          uint32_t *__restrict__ cellCount = nullptr) {
+  prs::pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
   if (i >= n) return;
@@ -790,6 +812,10 @@ void prs_set_collide_mode(int mode) { g_prs.collide_mode = mode; }
 int prs_get_collide_mode(void) { return g_prs.collide_mode; }
 /* swarms of up to max_robots use the warp-per-robot collide kernel (0 = never); default 16384 */
 void prs_set_collide_warp_max(unsigned max_robots) { g_prs.collide_warp_max = max_robots; }
+void prs_set_collide_tile(int on) { g_prs.collide_tile = on ? 1 : 0; }
+void prs_set_pdl(int on) { g_prs.pdl = on ? 1 : 0; }
+int prs_get_pdl(void) { return g_prs.pdl; }
+int prs_get_collide_tile(void) { return g_prs.collide_tile; }
 unsigned long long prs_launch_count(int reset) {
   const unsigned long long v = g_prs.launches;
   if (reset) g_prs.launches = 0;
@@ -900,36 +926,40 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     {
       StageScope t(PRS_STAGE_K1);
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
-      PRS_LAUNCH((k_control_integrate_hash<true, true>), div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
-                 b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
-                 (const uint32_t *)nullptr, B.cellCount);
+      PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
+                     b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
+                     (const uint32_t *)nullptr, B.cellCount);
     }
     {
       StageScope t(PRS_STAGE_SORT);
       const unsigned tiles = div_up(b->numCells, prs_bin::SCAN_TILE);
-      PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->numCells, B.scratch);
+      PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch);
       if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
-        PRS_LAUNCH(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                   B.scratch, 0u);
+        PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
+                       B.scratch, 0u);
       } else {
-        PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
-        PRS_LAUNCH(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                   B.scratch, 0u);
+        PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
+        PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
+                       B.scratch, 0u);
       }
-      PRS_LAUNCH(prs_bin::k_cell_scatter, div_up(n, 256), 256, 0, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
+      PRS_LAUNCH_PDL(prs_bin::k_cell_scatter, div_up(n, 256), 256, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
     }
     {
       StageScope t(PRS_STAGE_REORDER);
-      PRS_LAUNCH(prs_bin::k_reorder_binned, div_up(n, 256), 256, 0, hash_by_slot, index_by_slot, b->cellStart, b->cellEnd,
-                 b->hash, b->index, (float4 *)b->sortedPR, (float2 *)b->sortedVel, (const float2 *)b->pos,
-                 (const float2 *)b->vel, b->rad, n, B.scratch);
+      PRS_LAUNCH_PDL(prs_bin::k_reorder_binned, div_up(n, 256), 256, hash_by_slot, index_by_slot, b->cellStart, b->cellEnd,
+                     b->hash, b->index, (float4 *)b->sortedPR, (float2 *)b->sortedVel, (const float2 *)b->pos,
+                     (const float2 *)b->vel, b->rad, n, B.scratch);
     }
-    bin_send_report(B.scratch + 1);
     g_prs.table.cellStart = b->cellStart; g_prs.table.hash = b->hash; g_prs.table.n = n;
     g_prs.table.numCells = b->numCells; g_prs.table.generation = B.generation;
-    StageScope t(PRS_STAGE_COLLIDE);
-    prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
-    prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+    {
+      StageScope t(PRS_STAGE_COLLIDE);
+      prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
+      prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+    }
+    /* fullest cell of this sort -> pinned host memory (nobody touches the two words before the next step's
+     * memset); issued after collide so that the kernels of the step stay adjacent in the stream */
+    bin_send_report(B.scratch + 1);
     return;
   }
   if (do_sort) {
@@ -942,8 +972,9 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     sort_pairs(b->hash, b->index, b->hash, b->index, n, key_bits_of_grid(), true);
   } else {
     StageScope t(PRS_STAGE_K1);
-    PRS_LAUNCH(k_control_integrate_hash<false>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
-               b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n, (const uint32_t *)nullptr);
+    PRS_LAUNCH_PDL((k_control_integrate_hash<false, false>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
+                   b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n,
+                   (const uint32_t *)nullptr, (uint32_t *)nullptr);
   }
   if (b->sortedPR) {
     {
@@ -952,8 +983,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       const bool table_current = !do_sort && T.cellStart == b->cellStart && T.hash == b->hash && T.n == n &&
                                  T.numCells == b->numCells && T.generation == B.generation;
       if (table_current) {
-        PRS_LAUNCH(k_gather_packed, div_up(n, 256), 256, 0, (float4 *)b->sortedPR, (float2 *)b->sortedVel, b->index,
-                   (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
+        PRS_LAUNCH_PDL(k_gather_packed, div_up(n, 256), 256, (float4 *)b->sortedPR, (float2 *)b->sortedVel, b->index,
+                       (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
       } else {
         PRS_CUDA(cudaMemsetAsync(b->cellStart, 0xff, (size_t)b->numCells * sizeof(unsigned), g_prs.stream));
         PRS_LAUNCH(k_reorder_packed, div_up(n, 256), 256, 0, b->cellStart, b->cellEnd, (float4 *)b->sortedPR,

@@ -26,15 +26,25 @@ TOL_REF = 1e-5      # vs the reference's kernels (north_star)
 TOL_ORACLE = 5e-4   # vs the IEEE CPU restatement
 
 
-@pytest.fixture(autouse=True, params=["warp-per-robot", "thread-per-robot"])
+@pytest.fixture(autouse=True, params=["warp-per-robot", "thread-per-robot-nopdl", "tile-staged"])
 def collide_kernel(request):
-    """collide has two kernels with identical results: one warp per robot for small swarms (<= 16384
-    robots by default, i.e. every cfg-sized test here) and one thread per robot.  Every test of this
-    module runs with both."""
+    """collide has three kernels with identical results: one warp per robot for small swarms (<= 16384
+    robots by default, i.e. every cfg-sized test here), one thread per robot reading neighbours through
+    L1/L2, and one thread per robot with the neighbour windows staged in shared memory by TMA bulk copies
+    (the fused step runs with programmatic dependent launch, the default, except in the second variant).
+    Every test of this module runs with all three."""
     L = prs.lib()
     L.prs_set_collide_warp_max(16384 if request.param == "warp-per-robot" else 0)
+    L.prs_set_collide_tile(1 if request.param == "tile-staged" else 0)
+    L.prs_set_pdl(0 if request.param == "thread-per-robot-nopdl" else 1)   # programmatic dependent launch: on by default
     yield request.param
     L.prs_set_collide_warp_max(16384)
+    L.prs_set_collide_tile(TILE_DEFAULT)
+    L.prs_set_pdl(PDL_DEFAULT)
+
+
+TILE_DEFAULT = prs.lib().prs_get_collide_tile()
+PDL_DEFAULT = prs.lib().prs_get_pdl()
 
 
 def _backends():
