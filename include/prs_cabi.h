@@ -101,6 +101,9 @@ int prs_get_collide_tile(void);
 /* 1 = the kernels of prs_fused_step are launched with programmatic dependent launch (each kernel's blocks
  * become resident while the previous kernel drains; griddepcontrol.wait orders the data).  Same results. */
 void prs_set_pdl(int on);
+/* steps without a sort: swarms of up to max_robots run controller+integrate and the gather into the sorted
+ * copy as ONE kernel (one launch less per step; default 65536, 0 = never).  Same bits. */
+void prs_set_fuse_gather_max(unsigned max_robots);
 int prs_get_pdl(void);
 /* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
 unsigned long long prs_launch_count(int reset);

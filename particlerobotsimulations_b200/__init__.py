@@ -116,6 +116,7 @@ SIGNATURES = {
     "prs_set_collide_warp_max": (None, [_U]),
     "prs_set_collide_tile": (None, [_I]), "prs_get_collide_tile": (_I, []),
     "prs_set_pdl": (None, [_I]), "prs_get_pdl": (_I, []),
+    "prs_set_fuse_gather_max": (None, [_U]),
     "prs_launch_count": (C.c_ulonglong, [_I]),
     "prs_stage_timing": (None, [_I]), "prs_stage_times": (None, [_VP, _VP]),
     "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),

@@ -35,6 +35,7 @@ struct PrsHostState {
   bool params_set = false;
   float world_half = 64.0f;           /* reference wall (kernel_impl.cuh:75-97) */
   int collide_mode = 0;               /* 0 exact, 1 fast */
+  unsigned fuse_gather_max = 65536;   /* steps without a sort: swarms up to this size run K1 and the gather as one kernel */
   int pdl = 1;                        /* 1: the fused step's kernels are launched with programmatic dependent launch */
   int collide_tile = 0;               /* 1: thread-per-robot collide stages its neighbours in shared memory by TMA */
   unsigned collide_warp_max = 16384;  /* swarms up to this size use the warp-per-robot collide kernel */

@@ -319,6 +319,36 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
   }
 }
 
+/* Steps WITHOUT a sort, small swarms: K1 and the gather in ONE launch.  Thread k owns sorted slot k, runs
+ * controller + integrate for the robot in that slot (every robot sits in exactly one slot; same arithmetic
+ * as k_control_integrate_hash) and writes both its state and its packed sorted record.  One launch less per
+ * step, which is what a 300-robot step is made of. */
+__global__ void __launch_bounds__(256)
+k_control_integrate_gather(float2 *__restrict__ pos, float2 *__restrict__ vel, float *__restrict__ rad,
+                           const float *__restrict__ phase, const float *__restrict__ fa, const float *__restrict__ fr,
+                           const int *__restrict__ dead, const uint32_t *__restrict__ index, float4 *__restrict__ sortedPR,
+                           float2 *__restrict__ sortedVel, float time, float dt, int run_controller, uint32_t n) {
+  prs::pdl_sync();
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = index[k];
+  float2 p = pos[i];
+  float2 v = vel[i];
+  float r = rad[i];
+  if (run_controller && !dead[i]) {
+    float rn;
+    if (c_prm.p.constrained_contraction) rn = controller_one<true>(r, phase[i], fr[i], fa[i], time, dt);
+    else rn = controller_one<false>(r, phase[i], fr[i], 0.0f, time, dt);
+    if (rn != r) { rad[i] = rn; r = rn; }
+  }
+  const float2 v0 = v;
+  integrate_one(p, v, r, dt);
+  pos[i] = p;
+  if (v.x != v0.x || v.y != v0.y) vel[i] = v;
+  sortedPR[k] = make_float4(p.x, p.y, r, __uint_as_float(i));
+  sortedVel[k] = v;
+}
+
 /* largest cell population of a sorted key array (guard of the binned route, see prs_fused_step) */
 __global__ void __launch_bounds__(256)
 k_max_population(const uint32_t *__restrict__ hash, const uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ cellEnd,
@@ -814,6 +844,7 @@ int prs_get_collide_mode(void) { return g_prs.collide_mode; }
 void prs_set_collide_warp_max(unsigned max_robots) { g_prs.collide_warp_max = max_robots; }
 void prs_set_collide_tile(int on) { g_prs.collide_tile = on ? 1 : 0; }
 void prs_set_pdl(int on) { g_prs.pdl = on ? 1 : 0; }
+void prs_set_fuse_gather_max(unsigned max_robots) { g_prs.fuse_gather_max = max_robots; }
 int prs_get_pdl(void) { return g_prs.pdl; }
 int prs_get_collide_tile(void) { return g_prs.collide_tile; }
 unsigned long long prs_launch_count(int reset) {
@@ -961,6 +992,22 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
      * memset); issued after collide so that the kernels of the step stay adjacent in the stream */
     bin_send_report(B.scratch + 1);
     return;
+  }
+  if (!do_sort && b->sortedPR && n <= g_prs.fuse_gather_max) {
+    const PrsTableState &T = g_prs.table;
+    if (T.cellStart == b->cellStart && T.hash == b->hash && T.n == n && T.numCells == b->numCells && T.generation == B.generation) {
+      /* the table of the last sort is current (nothing was rewritten since): K1 + gather in one launch, then collide */
+      {
+        StageScope t(PRS_STAGE_K1);
+        PRS_LAUNCH_PDL(k_control_integrate_gather, div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad, b->phase,
+                       b->absForce_a, b->absForce_r, b->dead, b->index, (float4 *)b->sortedPR, (float2 *)b->sortedVel, time, dt,
+                       run_controller, n);
+      }
+      StageScope t(PRS_STAGE_COLLIDE);
+      prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
+      prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+      return;
+    }
   }
   if (do_sort) {
     {

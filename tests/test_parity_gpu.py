@@ -37,7 +37,10 @@ def collide_kernel(request):
     L.prs_set_collide_warp_max(16384 if request.param == "warp-per-robot" else 0)
     L.prs_set_collide_tile(1 if request.param == "tile-staged" else 0)
     L.prs_set_pdl(0 if request.param == "thread-per-robot-nopdl" else 1)   # programmatic dependent launch: on by default
+    # steps without a sort: K1 + gather as one kernel (default) / as two kernels in the second variant
+    L.prs_set_fuse_gather_max(0 if request.param == "thread-per-robot-nopdl" else 65536)
     yield request.param
+    L.prs_set_fuse_gather_max(65536)
     L.prs_set_collide_warp_max(16384)
     L.prs_set_collide_tile(TILE_DEFAULT)
     L.prs_set_pdl(PDL_DEFAULT)
