@@ -265,6 +265,10 @@ void prs_sim_set(prs_sim *s, int which, const void *host, size_t offset_bytes, s
 void prs_sim_dump(prs_sim *s, void *FILE_ptr, float dump_interval, unsigned testing);
 /* loadFromFile (particlebot.cpp:369-411): time, positions, velocities, radii from the LAST row of a testing=1 CSV */
 void prs_sim_load(prs_sim *s, void *FILE_ptr);
+/* full binary checkpoint (Particlebot::saveCheckpoint / loadCheckpoint): a restored simulation of the same
+ * shape continues bit for bit, on either sort cadence.  0 on success, -1 on I/O error or shape mismatch. */
+int prs_sim_checkpoint_save(prs_sim *s, const char *path);
+int prs_sim_checkpoint_load(prs_sim *s, const char *path);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,8 @@ class PrsRand {
   PrsRand() { seed(1); }
   void seed(unsigned s);
   int next();
+  void getState(int out[33]) const { for (int i = 0; i < 31; i++) out[i] = r_[i]; out[31] = f_; out[32] = b_; }
+  void setState(const int in[33]) { for (int i = 0; i < 31; i++) r_[i] = in[i]; f_ = in[31]; b_ = in[32]; }
  private:
   int r_[31];
   int f_, b_;
@@ -82,6 +84,14 @@ class Particlebot {
   void dumpParticlebot(unsigned start, unsigned count, FILE *fp, float dump_interval, unsigned testing, float light_x,
                        float light_y);
   void loadFromFile(unsigned start, unsigned count, FILE *fp, float dump_interval);
+  /* Full checkpoint (the reference's loadFromFile restores only time, positions, velocities
+   * and radii from 6-digit CSV text).  Binary image of everything the next update() depends on: time, the
+   * host rand() stream, positions (with the centroid trail), velocities, radii, phases, both |force| sums,
+   * dead flags, the cuRAND states of the phase noise, and the frozen sort order (hash, index) that steps
+   * between two sorts walk.  A restored simulation continues bit for bit.  Return 0, or -1 on I/O or
+   * shape mismatch (nothing is modified then). */
+  int saveCheckpoint(FILE *fp);
+  int loadCheckpoint(FILE *fp);
 
   void getWorldOrigin(float *xy) const { xy[0] = params.worldOrigin.x; xy[1] = params.worldOrigin.y; }
   void getCellSize(float *xy) const { xy[0] = params.cellSize.x; xy[1] = params.cellSize.y; }

@@ -148,6 +148,7 @@ SIGNATURES = {
     "prs_sim_device_ptr": (_VP, [_VP, _I]), "prs_sim_get": (None, [_VP, _I, _VP, C.c_size_t]),
     "prs_sim_set": (None, [_VP, _I, _VP, C.c_size_t, C.c_size_t]),
     "prs_sim_dump": (None, [_VP, _VP, _F, _U]), "prs_sim_load": (None, [_VP, _VP]),
+    "prs_sim_checkpoint_save": (_I, [_VP, C.c_char_p]), "prs_sim_checkpoint_load": (_I, [_VP, C.c_char_p]),
 }
 
 
@@ -191,7 +192,7 @@ def load_cfg(path):
 _DTYPES = {POSITION: (np.float32, 2), VELOCITY: (np.float32, 2), RADII: (np.float32, 1), PHASE: (np.float32, 1),
            FREQUENCY: (np.float32, 1), DEAD: (np.int32, 1), ABSFORCE_A: (np.float32, 1), ABSFORCE_R: (np.float32, 1),
            HASH: (np.uint32, 1), INDEX: (np.uint32, 1), SORTEDPOS: (np.float32, 2), SORTEDVEL: (np.float32, 2),
-           SORTEDRAD: (np.float32, 1)}
+           SORTEDRAD: (np.float32, 1), RNGSTATE: (np.uint32, 12)}   # 48-byte curandStateXORWOW per robot
 
 
 class Simulation:
@@ -229,6 +230,16 @@ class Simulation:
 
     def sync(self):
         self._lib.prs_sim_sync(self._h)
+
+    def save_checkpoint(self, path):
+        """full binary checkpoint (Particlebot::saveCheckpoint); raises OSError on failure"""
+        if self._lib.prs_sim_checkpoint_save(self._h, os.fsencode(path)) != 0:
+            raise OSError(f"cannot write checkpoint {path}")
+
+    def load_checkpoint(self, path):
+        """restore a checkpoint of a swarm of the same shape; the run continues bit for bit"""
+        if self._lib.prs_sim_checkpoint_load(self._h, os.fsencode(path)) != 0:
+            raise OSError(f"cannot restore checkpoint {path}")
 
     @property
     def time(self):

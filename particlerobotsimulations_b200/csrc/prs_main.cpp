@@ -1,6 +1,6 @@
 /*
  * prs_main.cpp — headless runner `ParticleBot <cfg> [--steps N] [--backend fused|percall|ext:<lib>]
- * [--no-csv] [--quiet]`: the reference's main() (main.cpp:823-967) without GLUT/GL/OpenCV.  The
+ * [--no-csv] [--quiet] [--save-checkpoint FILE] [--resume-checkpoint FILE]`: the reference's main() (main.cpp:823-967) without GLUT/GL/OpenCV.  The
  * GLUT display callback that drives the reference (dumpParticlebot, then update, main.cpp:360-361)
  * becomes a plain loop; rendering and video are optional components that are not built here
  * (north_star (5)).
@@ -22,6 +22,7 @@ int main(int argc, char **argv) {
   int backend = PRS_BACKEND_FUSED;
   const char *ext = 0;
   bool csv = true, quiet = false;
+  const char *ck_out = 0, *ck_in = 0;
   int positional = 0;
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--steps") && i + 1 < argc) max_steps = atol(argv[++i]);
@@ -31,7 +32,9 @@ int main(int argc, char **argv) {
       else if (!strcmp(b, "percall")) backend = PRS_BACKEND_PERCALL;
       else if (!strncmp(b, "ext:", 4)) { backend = PRS_BACKEND_EXTERNAL; ext = b + 4; }
       else { fprintf(stderr, "unknown backend %s\n", b); return 2; }
-    } else if (!strcmp(argv[i], "--no-csv")) csv = false;
+    } else if (!strcmp(argv[i], "--save-checkpoint") && i + 1 < argc) ck_out = argv[++i];
+    else if (!strcmp(argv[i], "--resume-checkpoint") && i + 1 < argc) ck_in = argv[++i];
+    else if (!strcmp(argv[i], "--no-csv")) csv = false;
     else if (!strcmp(argv[i], "--quiet")) quiet = true;
     else if (!strcmp(argv[i], "--headless")) { /* default */ }
     else if (argv[i][0] != '-' && positional++ == 0) cfg = argv[i];
@@ -47,6 +50,11 @@ int main(int argc, char **argv) {
   Particlebot bot(params, 64.0f, backend, ext);
   bot.srand(params.seed); /* main.cpp:929 */
   bot.reset();
+  if (ck_in) {
+    FILE *ck = fopen(ck_in, "rb");
+    if (!ck || bot.loadCheckpoint(ck) != 0) { fprintf(stderr, "cannot restore %s\n", ck_in); return 1; }
+    fclose(ck);
+  }
 
   const auto t0 = std::chrono::steady_clock::now();
   long steps = 0;
@@ -56,6 +64,11 @@ int main(int argc, char **argv) {
     steps++;
   }
   bot.sync();
+  if (ck_out) {
+    FILE *ck = fopen(ck_out, "wb");
+    if (!ck || bot.saveCheckpoint(ck) != 0) { fprintf(stderr, "cannot write %s\n", ck_out); return 1; }
+    fclose(ck);
+  }
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   fclose(fp);
   fprintf(stderr, "ParticleBot: %ld steps, %u robots, %.3f s, %.1f steps/s, %.3e particle-steps/s\n", steps,

@@ -527,6 +527,83 @@ void Particlebot::loadFromFile(unsigned start, unsigned count, FILE *fp, float /
   printf("Time = %f\n", time);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * checkpoint
+ * ------------------------------------------------------------------------------------------ */
+namespace {
+struct CheckpointHeader {
+  char magic[8];            /* "PRSCKPT1" */
+  uint32_t version, nCells, numCells, trail;
+  float time;
+  uint32_t sorted_once;
+  int32_t rand_state[33];
+  uint32_t seed, reserved[5];
+};
+struct CheckpointArray { int which; size_t bytes; };
+}  // namespace
+
+int Particlebot::saveCheckpoint(FILE *fp) {
+  const size_t n = params.nCells, trail = (size_t)params.centroid_steps + 1;
+  CheckpointHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "PRSCKPT1", 8);
+  h.version = 1; h.nCells = (uint32_t)n; h.numCells = params.numCells; h.trail = (uint32_t)trail;
+  h.time = time; h.sorted_once = sorted_once_ ? 1u : 0u; h.seed = (uint32_t)params.seed;
+  rng_.getState(h.rand_state);
+  if (fwrite(&h, sizeof(h), 1, fp) != 1) return -1;
+  be_.threadSync();
+  const struct { void *dev; size_t bytes; } arrays[] = {
+      {dPos, (n + trail) * 8}, {dVel, n * 8}, {dRad, (n + trail) * 4}, {dphase, n * 4}, {dAbsForce_a, n * 4},
+      {dAbsForce_r, n * 4}, {dDead, n * 4}, {dState, n * 48}, {dGridParticleHash, n * 4}, {dGridParticleIndex, n * 4}};
+  std::vector<char> buf;
+  for (const auto &a : arrays) {
+    buf.resize(a.bytes);
+    for (size_t done = 0; done < a.bytes;) { /* the reference ABI counts bytes in int */
+      const size_t chunk = std::min<size_t>(a.bytes - done, (size_t)1 << 30);
+      be_.copyArrayFromDevice(buf.data() + done, (const char *)a.dev + done, 0, (int)chunk);
+      done += chunk;
+    }
+    if (a.bytes && fwrite(buf.data(), 1, a.bytes, fp) != a.bytes) return -1;
+  }
+  return fflush(fp) == 0 ? 0 : -1;
+}
+
+int Particlebot::loadCheckpoint(FILE *fp) {
+  const size_t n = params.nCells, trail = (size_t)params.centroid_steps + 1;
+  CheckpointHeader h;
+  if (fread(&h, sizeof(h), 1, fp) != 1) return -1;
+  if (memcmp(h.magic, "PRSCKPT1", 8) != 0 || h.version != 1 || h.nCells != n || h.numCells != params.numCells || h.trail != trail) {
+    fprintf(stderr, "loadCheckpoint: not a checkpoint of this swarm (robots %u/%zu, cells %u/%u)\n", h.nCells, n, h.numCells, params.numCells);
+    return -1;
+  }
+  const struct { void *dev; size_t bytes; } arrays[] = {
+      {dPos, (n + trail) * 8}, {dVel, n * 8}, {dRad, (n + trail) * 4}, {dphase, n * 4}, {dAbsForce_a, n * 4},
+      {dAbsForce_r, n * 4}, {dDead, n * 4}, {dState, n * 48}, {dGridParticleHash, n * 4}, {dGridParticleIndex, n * 4}};
+  /* read everything before touching the simulation */
+  std::vector<std::vector<char>> data;
+  for (const auto &a : arrays) {
+    data.emplace_back(a.bytes);
+    if (a.bytes && fread(data.back().data(), 1, a.bytes, fp) != a.bytes) return -1;
+  }
+  for (size_t k = 0; k < data.size(); k++) {
+    const size_t bytes = arrays[k].bytes;
+    for (size_t done = 0; done < bytes;) {
+      const size_t chunk = std::min<size_t>(bytes - done, (size_t)1 << 30);
+      be_.copyArrayToDevice((char *)arrays[k].dev + done, data[k].data() + done, 0, (int)chunk);
+      done += chunk;
+    }
+  }
+  memcpy(hPos, data[0].data(), n * 8);
+  memcpy(hVel, data[1].data(), n * 8);
+  memcpy(hRad, data[2].data(), n * 4);
+  memcpy(hphase, data[3].data(), n * 4);
+  memcpy(hDead, data[6].data(), n * 4);
+  time = h.time;
+  sorted_once_ = h.sorted_once != 0; /* the frozen order came along: the next update only sorts if its gate says so */
+  rng_.setState(h.rand_state);
+  return 0;
+}
+
 void *Particlebot::devicePtr(int which) {
   switch (which) {
     case POSITION: return dPos;      case VELOCITY: return dVel;   case RADII: return dRad;
@@ -598,6 +675,19 @@ void prs_sim_set(prs_sim *s, int which, const void *host, size_t offset_bytes, s
 void prs_sim_dump(prs_sim *s, void *fp, float dump_interval, unsigned testing) {
   const SimParams &P = s->bot->getParams();
   s->bot->dumpParticlebot(0, P.nCells, (FILE *)fp, dump_interval, testing, P.light_x, P.light_y);
+}
+int prs_sim_checkpoint_save(prs_sim *s, const char *path) {
+  FILE *fp = fopen(path, "wb");
+  if (!fp) return -1;
+  const int rc = s->bot->saveCheckpoint(fp);
+  return fclose(fp) == 0 ? rc : -1;
+}
+int prs_sim_checkpoint_load(prs_sim *s, const char *path) {
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return -1;
+  const int rc = s->bot->loadCheckpoint(fp);
+  fclose(fp);
+  return rc;
 }
 void prs_sim_load(prs_sim *s, void *fp) {
   const SimParams &P = s->bot->getParams();

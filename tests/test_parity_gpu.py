@@ -11,6 +11,9 @@ the approximate __powf which IEEE host arithmetic cannot reproduc
 is applied against the reference kernels themselves.
 """
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -564,7 +567,7 @@ def test_synthetic_hex_swarm_properties():
     sim.close()
 
 
-def _hex_run(mode, steps, scramble=False, crowd=0):
+def _hex_run(mode, steps, scramble=False, crowd=0, drift=0.0):
     """64k hex swarm through the fused path with the cell sort pinned to one route (prs_bin_set_mode)."""
     p, o = util.cfg("example")
     nx = ny = 256
@@ -585,6 +588,10 @@ def _hex_run(mode, steps, scramble=False, crowd=0):
             if scramble:   # robot order unrelated to position (arrival tickets far from index order)
                 pos = pos[rng.permutation(p.nCells)]
             sim.set(prs.POSITION, pos)
+        if drift:          # the whole swarm flies upwards: scan tiles empty out behind it and fill up ahead of it
+            vel = np.zeros((p.nCells, 2), np.float32)
+            vel[:, 1] = drift
+            sim.set(prs.VELOCITY, vel)
         out = []
         for k in range(steps):
             sim.update(o.timestep, o.timestep)
@@ -598,13 +605,13 @@ def _hex_run(mode, steps, scramble=False, crowd=0):
         L.prs_bin_set_mode(0)
 
 
-@pytest.mark.parametrize("scramble,crowd,steps", [(False, 0, 12), (True, 0, 6), (True, 40, 1)])
-def test_cell_binning_route_equals_onesweep_route(scramble, crowd, steps):
+@pytest.mark.parametrize("scramble,crowd,steps,drift", [(False, 0, 12, 0.0), (True, 0, 6, 0.0), (True, 40, 1, 0.0), (False, 0, 14, 60.0)])
+def test_cell_binning_route_equals_onesweep_route(scramble, crowd, steps, drift):
     """The fused step sorts by cell binning (counting sort whose scan is the cell table) when the swarm
     is sparse, else by the onesweep radix sort: hashes, stable index order, cellStart/cellEnd (stale
     cellEnd of emptied cells included), sorted copies and the trajectory must be identical bits."""
-    a = _hex_run(1, steps, scramble, crowd)   # onesweep only
-    b = _hex_run(2, steps, scramble, crowd)   # binning only
+    a = _hex_run(1, steps, scramble, crowd, drift)   # onesweep only
+    b = _hex_run(2, steps, scramble, crowd, drift)   # binning only (scan tiles without robots are skipped)
     for x, y in zip(a, b):
         for k in x:
             assert np.array_equal(x[k].view(np.uint32), y[k].view(np.uint32)), k
@@ -702,6 +709,67 @@ def _c_file(path, mode):
     libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
     libc.fclose.argtypes = [C.c_void_p]
     return libc, libc.fopen(str(path).encode(), mode.encode())
+
+
+@pytest.mark.parametrize("backend", [prs.BACKEND_FUSED, prs.BACKEND_PERCALL])
+@pytest.mark.parametrize("cfg,sort_every_step", [("example", False), ("example", True), ("example_dead_cells", False),
+                                                 ("example_object_transport", False)])
+def test_checkpoint_resume_continues_bit_for_bit(tmp_path, cfg, sort_every_step, backend):
+    """Particlebot::saveCheckpoint / loadCheckpoint (SURVEY.md §8f-1): a checkpoint taken BETWEEN two sorts and
+    two phase updates, restored into a simulation that started from a different seed, continues exactly like
+    the uninterrupted run — through a later sort, a phase update with cuRAND noise and (dead cells) the
+    rand() draw of the dead robots."""
+    p, o = util.cfg(cfg)
+    p.phase_update_interval = 0.25          # phase update + noise every 25 steps
+    if cfg == "example_dead_cells":
+        p.time_to_dead = 0.5                # the dead draw (host rand()) happens after the checkpoint
+    sort_interval = o.timestep if sort_every_step else 0.4   # sorts at steps 0, 40, 80
+    a = prs.Simulation(p, 64.0, backend)
+    a.srand(p.seed)
+    a.reset()
+    for _ in range(30):
+        a.update(o.timestep, sort_interval)
+    a.save_checkpoint(tmp_path / "ck.bin")
+    for _ in range(45):
+        a.update(o.timestep, sort_interval)
+    b = prs.Simulation(p, 64.0, backend)
+    b.srand(p.seed + 1)                     # another placement, another rand() stream: everything must come from the file
+    b.reset()
+    b.load_checkpoint(tmp_path / "ck.bin")
+    assert b.time == pytest.approx(30 * o.timestep, rel=1e-5)
+    for _ in range(45):
+        b.update(o.timestep, sort_interval)
+    assert a.time == b.time
+    for name, which in (("pos", prs.POSITION), ("vel", prs.VELOCITY), ("rad", prs.RADII), ("phase", prs.PHASE),
+                        ("dead", prs.DEAD), ("absForce_a", 100), ("absForce_r", 101), ("hash", prs.HASH), ("index", prs.INDEX),
+                        ("rng", 109)):
+        x, y = a.get(which), b.get(which)
+        assert np.array_equal(np.ascontiguousarray(x).view(np.uint8), np.ascontiguousarray(y).view(np.uint8)), name
+    if cfg == "example_dead_cells":
+        assert int(a.get(prs.DEAD).sum()) == p.nDead
+    # a checkpoint of another swarm is refused and leaves the simulation untouched
+    q, _ = util.cfg("example_obstacle")
+    c = prs.Simulation(q, 64.0, backend)
+    c.srand(q.seed)
+    c.reset()
+    before = c.get(prs.POSITION)
+    with pytest.raises(OSError):
+        c.load_checkpoint(tmp_path / "ck.bin")
+    assert np.array_equal(before, c.get(prs.POSITION))
+    for s_ in (a, b, c):
+        s_.close()
+
+
+def test_runner_checkpoint_files_identical(tmp_path):
+    """headless runner: 75 steps in one go and 30 + (resume) 45 steps leave byte-identical checkpoints"""
+    exe = os.path.join(util.ROOT, "particlerobotsimulations_b200", "ParticleBot")
+    cfg = os.path.join(util.ROOT, "examples", "example_obstacle.cfg")
+    base = [exe, cfg, "--no-csv", "--quiet"]
+    run = lambda extra: subprocess.run(base + extra, cwd=tmp_path, check=True, capture_output=True)
+    run(["--steps", "75", "--save-checkpoint", "full.bin"])
+    run(["--steps", "30", "--save-checkpoint", "part.bin"])
+    run(["--steps", "45", "--resume-checkpoint", "part.bin", "--save-checkpoint", "resumed.bin"])
+    assert open(tmp_path / "full.bin", "rb").read() == open(tmp_path / "resumed.bin", "rb").read()
 
 
 def test_csv_dump_format_and_resume(tmp_path):
