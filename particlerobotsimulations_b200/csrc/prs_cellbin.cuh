@@ -33,6 +33,14 @@ constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr uint32_t MAX_RANKED_CELL = 1024; /* populations above this are not ranked (error flag) */
+/* tile marks ("a robot hashed into this scan tile in this step"): MARK_WAYS words per tile, the writer picks
+ * one by its block number, so that the stores of a step spread over many L2 addresses (thousands of stores
+ * to ONE word serialise in its L2 slice: measured +4 us on K1 at 2^20 robots) */
+constexpr uint32_t MARK_WAYS = 32;
+__device__ __forceinline__ bool tile_marked(const uint32_t *marks, uint32_t tile) {
+  const uint32_t lane = threadIdx.x & 31u;
+  return __any_sync(0xffffffffu, marks[tile * MARK_WAYS + lane] != 0u);
+}
 
 /* The scan over the C cells has no inter-block waiting (a single-pass chained scan was tried first:
  * with ~450 tiles in flight every tile spent most of its life waiting for its predecessors'
@@ -55,10 +63,14 @@ __device__ __forceinline__ void load_counts(const uint32_t *cellCount, uint32_t 
 /* sums of the tiles of 4096 cells (no atomics: thousands of same-address atomics — a "last block
  * done" counter, per-robot tile sums from K1, a running maximum — each cost 10-100 us in L2) */
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch) {
+k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch, const uint32_t *marks = nullptr) {
   prs::pdl_sync();
   __shared__ uint32_t s_sum[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (marks && !tile_marked(marks, blockIdx.x)) { /* no robot hashed into this tile in this step: nothing to read */
+    if (tid == 0) scratch[4 + blockIdx.x] = 0u;
+    return;
+  }
   uint32_t cnt[SCAN_ITEMS];
   load_counts(cellCount, blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS, C, cnt);
   uint32_t sum = 0;
@@ -112,11 +124,30 @@ __global__ void __launch_bounds__(1024) k_cell_scan_tiles(uint32_t *scratch, uin
 template <bool SELF_PREFIX>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
-             uint32_t *scratch, uint32_t slot_offset) {
+             uint32_t *scratch, uint32_t slot_offset, uint32_t *marks = nullptr, uint32_t *prev_marks = nullptr) {
   prs::pdl_sync();
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c0 = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
+  if (marks) {
+    /* Tiles no robot hashed into (K1 marks the tile of every hash): their counters are all zero.  If the
+     * tile was also empty in the previous step its cellStart words are 0xffffffff already and nothing is
+     * touched; if it held robots then, only the empty markers are written.  (A world much larger than the
+     * swarm — S1: 4 M cells, a third of the tiles occupied — otherwise pays for the whole table.) */
+    const bool now = tile_marked(marks, blockIdx.x);
+    const uint32_t before_ = prev_marks[blockIdx.x];
+    __syncthreads(); /* every thread has read the words before they are rewritten */
+    if (tid < MARK_WAYS) marks[blockIdx.x * MARK_WAYS + tid] = 0u;
+    if (tid == 0) prev_marks[blockIdx.x] = now ? 1u : 0u;
+    if (!now) {
+      if (before_) {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++)
+          if (c0 + i < C) cellStart[c0 + i] = 0xffffffffu;
+      }
+      return;
+    }
+  }
   /* offset of this tile: from k_cell_scan_tiles, or — few tiles (SELF_PREFIX) — summed here from the
    * tile sums, which saves the one-block scan kernel and its launch (5 us at 2^20 robots) */
   uint32_t tile_offset = slot_offset; /* slab ranks: slots start after the lower halo */

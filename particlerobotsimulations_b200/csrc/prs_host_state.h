@@ -12,6 +12,9 @@
 /* guard state of the binned (counting-sort) route of the fused step, see prs_fused_step */
 struct PrsBinState {
   uint32_t *cellCount = nullptr, *scratch = nullptr;
+  uint32_t *marks = nullptr;     /* per scan tile: a robot hashed into it this step / the previous step (prs_cellbin.cuh) */
+  const void *marks_table = nullptr; /* the cellStart array the previous-step marks describe */
+  unsigned marks_cells = 0, marks_generation = 0;
   size_t cap_cells = 0;
   int mode = 0;               /* 0 auto, 1 never, 2 always */
   bool admitted = false;      /* the swarm is known to be sparse enough */

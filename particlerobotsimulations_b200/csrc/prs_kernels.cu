@@ -293,7 +293,7 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
                          const float *__restrict__ phase, const float *__restrict__ fa, const float *__restrict__ fr,
                          const int *__restrict__ dead, uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
                          float time, float dt, int run_controller, uint32_t n, const uint32_t *__restrict__ n_dev,
-                         uint32_t *__restrict__ cellCount = nullptr) {
+                         uint32_t *__restrict__ cellCount = nullptr, uint32_t *__restrict__ tileMark = nullptr) {
   prs::pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
@@ -316,6 +316,13 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
     const uint32_t h = cell_hash(g.x, g.y);
     hash[i] = h;
     index[i] = COUNT ? atomicAdd(&cellCount[h], 1u) : i;
+    if (COUNT && tileMark) {
+      /* the scan skips tiles nobody marked: the first lane of a run of equal tiles stores, into the way of its block */
+      const uint32_t tile = h / prs_bin::SCAN_TILE;
+      const unsigned act = __activemask();
+      const uint32_t left = __shfl_up_sync(act, tile, 1);
+      if ((threadIdx.x & 31u) == 0 || left != tile) tileMark[tile * prs_bin::MARK_WAYS + (blockIdx.x % prs_bin::MARK_WAYS)] = 1u;
+    }
   }
 }
 
@@ -686,6 +693,7 @@ void cudaGLInit(int argc, char **argv) { cudaInit(argc, argv); }
 void allocateArray(void **devPtr, size_t size) { PRS_CUDA(cudaMalloc(devPtr, size)); }
 void freeArray(void *devPtr) {
   g_prs.table.cellStart = nullptr; /* a recycled address must not look like the cached table */
+  g_prs.bin.marks_table = nullptr;
   PRS_CUDA(cudaFree(devPtr));
 }
 void threadSync(void) { PRS_CUDA(cudaDeviceSynchronize()); }
@@ -755,6 +763,7 @@ void reorderDataAndFindCellStart(unsigned *cellStart, unsigned *cellEnd, float *
                                  float *sortedRad, unsigned *hash, unsigned *index, float *oldPos, float *oldVel,
                                  float *oldRad, unsigned nCells, unsigned numCells) {
   g_prs.table.cellStart = nullptr;
+  g_prs.bin.marks_table = nullptr;
   PRS_CUDA(cudaMemsetAsync(cellStart, 0xff, (size_t)numCells * sizeof(unsigned), g_prs.stream));
   if (!nCells) return;
   PRS_LAUNCH(k_reorder, div_up(nCells, 256), 256, 0, cellStart, cellEnd, (float2 *)sortedPos, (float2 *)sortedVel,
@@ -926,11 +935,18 @@ static void bin_ensure(uint32_t n, uint32_t C) {
     PRS_CUDA(cudaMemsetAsync(B.cellCount, 0, (size_t)C * 4, g_prs.stream));
     PRS_CUDA(cudaMalloc(&B.scratch, prs_bin::scan_scratch_words(C) * 4));
     PRS_CUDA(cudaMemsetAsync(B.scratch, 0, prs_bin::scan_scratch_words(C) * 4, g_prs.stream));
+    if (B.marks) PRS_CUDA(cudaFree(B.marks));
+    const size_t tiles = (C + prs_bin::SCAN_TILE - 1) / prs_bin::SCAN_TILE;
+    /* [0, tiles * MARK_WAYS) marks of this step, then one word per tile for the previous step */
+    PRS_CUDA(cudaMalloc(&B.marks, (tiles * prs_bin::MARK_WAYS + tiles) * 4));
+    PRS_CUDA(cudaMemsetAsync(B.marks, 0, (tiles * prs_bin::MARK_WAYS + tiles) * 4, g_prs.stream));
+    B.marks_table = nullptr;
     B.cap_cells = C;
   }
   ensure_sort_workspace(n, 1, 4096);
 }
 void prs_bin_invalidate(void) {
+  g_prs.bin.marks_table = nullptr;
   g_prs.bin.admitted = false;
   g_prs.bin.generation++;
 }
@@ -954,24 +970,31 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     bin_ensure(n, b->numCells);
     prs_sort::Workspace &w = g_prs.sort_ws;
     uint32_t *ticket = w.vals[0], *hash_by_slot = w.keys[0], *index_by_slot = w.vals[1];
+    const unsigned tiles = div_up(b->numCells, prs_bin::SCAN_TILE);
+    uint32_t *marks = B.marks, *prev_marks = B.marks + (size_t)tiles * prs_bin::MARK_WAYS;
+    if (B.marks_table != (const void *)b->cellStart || B.marks_cells != b->numCells || B.marks_generation != B.generation) {
+      /* this table was last written by somebody else (other route, other buffers, an upload): every tile
+       * counts as "held robots before", i.e. gets its empty markers rewritten */
+      PRS_CUDA(cudaMemsetAsync(prev_marks, 0xff, (size_t)tiles * 4, g_prs.stream));
+      B.marks_table = b->cellStart; B.marks_cells = b->numCells; B.marks_generation = B.generation;
+    }
     {
       StageScope t(PRS_STAGE_K1);
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
       PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                      b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
-                     (const uint32_t *)nullptr, B.cellCount);
+                     (const uint32_t *)nullptr, B.cellCount, marks);
     }
     {
       StageScope t(PRS_STAGE_SORT);
-      const unsigned tiles = div_up(b->numCells, prs_bin::SCAN_TILE);
-      PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch);
+      PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch, (const uint32_t *)marks);
       if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u);
+                       B.scratch, 0u, marks, prev_marks);
       } else {
         PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u);
+                       B.scratch, 0u, marks, prev_marks);
       }
       PRS_LAUNCH_PDL(prs_bin::k_cell_scatter, div_up(n, 256), 256, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
     }
@@ -1021,7 +1044,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     StageScope t(PRS_STAGE_K1);
     PRS_LAUNCH_PDL((k_control_integrate_hash<false, false>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                    b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n,
-                   (const uint32_t *)nullptr, (uint32_t *)nullptr);
+                   (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr);
   }
   if (b->sortedPR) {
     {
@@ -1033,6 +1056,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
         PRS_LAUNCH_PDL(k_gather_packed, div_up(n, 256), 256, (float4 *)b->sortedPR, (float2 *)b->sortedVel, b->index,
                        (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
       } else {
+        B.marks_table = nullptr; /* the table is rebuilt from scratch here: the binned route's tile marks no longer describe it */
         PRS_CUDA(cudaMemsetAsync(b->cellStart, 0xff, (size_t)b->numCells * sizeof(unsigned), g_prs.stream));
         PRS_LAUNCH(k_reorder_packed, div_up(n, 256), 256, 0, b->cellStart, b->cellEnd, (float4 *)b->sortedPR,
                    (float2 *)b->sortedVel, b->hash, b->index, (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);

@@ -1,7 +1,6 @@
-# GPU job: parity tests, then the S1 line with the library defaults (no CPU baseline / reference-kernel block)
+# GPU job: the binning / large-swarm parity tests, then the S1 line with the library defaults (no CPU baseline / reference-kernel block)
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "not multigpu" 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
-cat gpurun_out/pytest_gpu.log
+timeout 600 python -m pytest tests -m gpu -x -q -k "binning or large_swarm" 2>&1 | tail -5
 timeout 300 python bench.py --steps 200 --warmup 50 --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_s1_quick.json 2> gpurun_out/bench_s1_quick.err
 python - <<'PY'
 import json
