@@ -105,6 +105,13 @@ void prs_set_pdl(int on);
  * copy as ONE kernel (one launch less per step; default 65536, 0 = never).  Same bits. */
 void prs_set_fuse_gather_max(unsigned max_robots);
 int prs_get_pdl(void);
+/* building blocks of the host-buffer step (Particlebot::updateHost / prs_sim_update_host): asynchronous copies
+ * between PINNED host memory and the device around prs_fused_step; the device-to-host copies of positions and
+ * radii wait only for K1 (controller + integrate) and run under the sort and collide kernels on a second stream */
+void prs_h2d_async(void *device, const void *host, size_t bytes);
+void prs_arm_k1_event(int on);
+void prs_d2h_async(void *host, const void *device, size_t bytes, int after_k1);
+void prs_host_step_sync(void);
 /* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
 unsigned long long prs_launch_count(int reset);
 
@@ -254,6 +261,12 @@ void prs_sim_srand(prs_sim *s, unsigned seed);            /* main.cpp:929 */
 void prs_sim_reset(prs_sim *s);                           /* Particlebot::reset */
 void prs_sim_init_hex(prs_sim *s, unsigned nx, unsigned ny, float pitch, float jitter, unsigned seed); /* synthetic swarms */
 int prs_sim_update(prs_sim *s, float dt, float sort_interval); /* Particlebot::update; returns 1 when time > max_time */
+/* One step with the state held by the HOST: positions, velocities and radii (original robot order, the layouts of
+ * getArray/setArray) go up from the in buffers, Particlebot::update runs, the new values come back in the out
+ * buffers (may alias the in buffers).  Same results as setArray x3, update, getArray x3; the copies are
+ * asynchronous and the downloads of positions and radii overlap the sort and collide kernels (pinned buffers). */
+int prs_sim_update_host(prs_sim *s, const float *pos_in, const float *vel_in, const float *rad_in, float *pos_out,
+                        float *vel_out, float *rad_out, float dt, float sort_interval);
 float prs_sim_time(const prs_sim *s);
 void prs_sim_sync(prs_sim *s);
 /* which: ParticlebotArray values, plus 100 absForce_a, 101 absForce_r, 102 hash, 103 index,

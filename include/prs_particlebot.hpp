@@ -66,6 +66,9 @@ class Particlebot {
   ~Particlebot();
 
   bool update(float deltaTime, float sort_interval); /* true once time > max_time */
+  /* update() for a caller that keeps the state on the host (see prs_sim_update_host in prs_cabi.h) */
+  bool updateHost(const float *pos_in, const float *vel_in, const float *rad_in, float *pos_out, float *vel_out,
+                  float *rad_out, float deltaTime, float sort_interval);
   void reset();
   void srand(unsigned seed) { rng_.seed(seed); }
   /* synthetic swarms: nx*ny hex lattice centred on the origin */

@@ -148,6 +148,9 @@ SIGNATURES = {
     "prs_sim_device_ptr": (_VP, [_VP, _I]), "prs_sim_get": (None, [_VP, _I, _VP, C.c_size_t]),
     "prs_sim_set": (None, [_VP, _I, _VP, C.c_size_t, C.c_size_t]),
     "prs_sim_dump": (None, [_VP, _VP, _F, _U]), "prs_sim_load": (None, [_VP, _VP]),
+    "prs_sim_update_host": (_I, [_VP] * 7 + [_F, _F]),
+    "prs_h2d_async": (None, [_VP, _VP, C.c_size_t]), "prs_arm_k1_event": (None, [_I]),
+    "prs_d2h_async": (None, [_VP, _VP, C.c_size_t, _I]), "prs_host_step_sync": (None, []),
     "prs_sim_checkpoint_save": (_I, [_VP, C.c_char_p]), "prs_sim_checkpoint_load": (_I, [_VP, C.c_char_p]),
 }
 
@@ -230,6 +233,11 @@ class Simulation:
 
     def sync(self):
         self._lib.prs_sim_sync(self._h)
+
+    def update_host(self, pos, vel, rad, dt, sort_interval):
+        """one step with the state in host arrays (float32, C-contiguous, ideally pinned): updated in place"""
+        return bool(self._lib.prs_sim_update_host(self._h, pos.ctypes.data, vel.ctypes.data, rad.ctypes.data,
+                                                  pos.ctypes.data, vel.ctypes.data, rad.ctypes.data, dt, sort_interval))
 
     def save_checkpoint(self, path):
         """full binary checkpoint (Particlebot::saveCheckpoint); raises OSError on failure"""

@@ -39,6 +39,11 @@ struct PrsHostState {
   float world_half = 64.0f;           /* reference wall (kernel_impl.cuh:75-97) */
   int collide_mode = 0;               /* 0 exact, 1 fast */
   unsigned fuse_gather_max = 65536;   /* steps without a sort: swarms up to this size run K1 and the gather as one kernel */
+  /* host-buffer step (prs_sim_update_host): second stream for the device-to-host copies that may start as soon
+   * as K1 has written positions and radii, and the event K1's completion is recorded in */
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t k1_event = nullptr;
+  bool k1_event_armed = false;
   int pdl = 1;                        /* 1: the fused step's kernels are launched with programmatic dependent launch */
   int collide_tile = 0;               /* 1: thread-per-robot collide stages its neighbours in shared memory by TMA */
   unsigned collide_warp_max = 16384;  /* swarms up to this size use the warp-per-robot collide kernel */

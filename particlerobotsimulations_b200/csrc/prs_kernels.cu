@@ -853,6 +853,37 @@ int prs_get_collide_mode(void) { return g_prs.collide_mode; }
 void prs_set_collide_warp_max(unsigned max_robots) { g_prs.collide_warp_max = max_robots; }
 void prs_set_collide_tile(int on) { g_prs.collide_tile = on ? 1 : 0; }
 void prs_set_pdl(int on) { g_prs.pdl = on ? 1 : 0; }
+
+/* ---- host-buffer step (Particlebot::updateHost): asynchronous copies around prs_fused_step ----
+ * prs_h2d_async: pinned host -> device on the launching stream (counts as an upload: the binned route re-earns
+ * its admission).  prs_arm_k1_event(1): the next fused step records an event once K1 (controller + integrate)
+ * is launched — positions and radii are final from there on.  prs_d2h_async(.., after_k1 = 1): device -> host on
+ * a second stream that waits for that event only, so the copy runs under the sort and collide kernels;
+ * after_k1 = 0: on the launching stream (after everything).  prs_host_step_sync waits for both streams. */
+void prs_h2d_async(void *device, const void *host, size_t bytes) {
+  g_prs.bin.admitted = false;
+  g_prs.bin.generation++;
+  PRS_CUDA(cudaMemcpyAsync(device, host, bytes, cudaMemcpyHostToDevice, g_prs.stream));
+}
+void prs_arm_k1_event(int on) {
+  if (on && !g_prs.k1_event) {
+    PRS_CUDA(cudaEventCreateWithFlags(&g_prs.k1_event, cudaEventDisableTiming));
+    PRS_CUDA(cudaStreamCreateWithFlags(&g_prs.copy_stream, cudaStreamNonBlocking));
+  }
+  g_prs.k1_event_armed = on != 0;
+}
+void prs_d2h_async(void *host, const void *device, size_t bytes, int after_k1) {
+  if (after_k1 && g_prs.k1_event) {
+    PRS_CUDA(cudaStreamWaitEvent(g_prs.copy_stream, g_prs.k1_event, 0));
+    PRS_CUDA(cudaMemcpyAsync(host, device, bytes, cudaMemcpyDeviceToHost, g_prs.copy_stream));
+  } else {
+    PRS_CUDA(cudaMemcpyAsync(host, device, bytes, cudaMemcpyDeviceToHost, g_prs.stream));
+  }
+}
+void prs_host_step_sync(void) {
+  if (g_prs.copy_stream) PRS_CUDA(cudaStreamSynchronize(g_prs.copy_stream));
+  PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+}
 void prs_set_fuse_gather_max(unsigned max_robots) { g_prs.fuse_gather_max = max_robots; }
 int prs_get_pdl(void) { return g_prs.pdl; }
 int prs_get_collide_tile(void) { return g_prs.collide_tile; }
@@ -953,6 +984,10 @@ void prs_bin_invalidate(void) {
 void prs_bin_set_mode(int mode) { g_prs.bin.mode = mode; } /* 0 auto (default), 1 never (always onesweep), 2 always */
 int prs_bin_active(void) { return g_prs.bin.admitted ? 1 : 0; }
 
+static inline void k1_done() {
+  if (g_prs.k1_event_armed) PRS_CUDA(cudaEventRecord(g_prs.k1_event, g_prs.stream));
+}
+
 void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort) {
   const uint32_t n = b->nCells;
   if (!n) return;
@@ -984,6 +1019,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                      b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
                      (const uint32_t *)nullptr, B.cellCount, marks);
+      k1_done();
     }
     {
       StageScope t(PRS_STAGE_SORT);
@@ -1025,6 +1061,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
         PRS_LAUNCH_PDL(k_control_integrate_gather, div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad, b->phase,
                        b->absForce_a, b->absForce_r, b->dead, b->index, (float4 *)b->sortedPR, (float2 *)b->sortedVel, time, dt,
                        run_controller, n);
+        k1_done();
       }
       StageScope t(PRS_STAGE_COLLIDE);
       prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
@@ -1037,6 +1074,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       StageScope t(PRS_STAGE_K1);
       PRS_LAUNCH(k_control_integrate_hash<true>, div_up(n, 256), 256, 0, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                  b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n, (const uint32_t *)nullptr);
+      k1_done();
     }
     StageScope t(PRS_STAGE_SORT);
     sort_pairs(b->hash, b->index, b->hash, b->index, n, key_bits_of_grid(), true);
@@ -1045,6 +1083,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     PRS_LAUNCH_PDL((k_control_integrate_hash<false, false>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                    b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n,
                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr);
+    k1_done();
   }
   if (b->sortedPR) {
     {

@@ -262,6 +262,34 @@ bool Particlebot::update(float deltaTime, float sort_interval) {
   return false;
 }
 
+bool Particlebot::updateHost(const float *pos_in, const float *vel_in, const float *rad_in, float *pos_out,
+                             float *vel_out, float *rad_out, float deltaTime, float sort_interval) {
+  const size_t n = params.nCells;
+  if (backend_kind_ != PRS_BACKEND_FUSED) {
+    /* per-call backends: the reference's own blocking copies */
+    setArray(POSITION, pos_in, 0, (int)n);
+    setArray(VELOCITY, vel_in, 0, (int)n);
+    setArray(RADII, rad_in, 0, (int)n);
+    const bool done = update(deltaTime, sort_interval);
+    be_.copyArrayFromDevice(pos_out, dPos, 0, (int)(n * 8));
+    be_.copyArrayFromDevice(vel_out, dVel, 0, (int)(n * 8));
+    be_.copyArrayFromDevice(rad_out, dRad, 0, (int)(n * 4));
+    return done;
+  }
+  prs_h2d_async(dPos, pos_in, n * 8);
+  prs_h2d_async(dVel, vel_in, n * 8);
+  prs_h2d_async(dRad, rad_in, n * 4);
+  prs_arm_k1_event(1);
+  const bool done = update(deltaTime, sort_interval);
+  prs_arm_k1_event(0);
+  /* positions and radii are final once K1 ran: their way back overlaps sort, reorder and collide */
+  prs_d2h_async(pos_out, dPos, n * 8, done ? 0 : 1);
+  prs_d2h_async(rad_out, dRad, n * 4, done ? 0 : 1);
+  prs_d2h_async(vel_out, dVel, n * 8, 0);
+  prs_host_step_sync();
+  return done;
+}
+
 /* ------------------------------------------------------------------------------------------
  * initial state
  * ------------------------------------------------------------------------------------------ */
@@ -647,6 +675,10 @@ void prs_sim_init_hex(prs_sim *s, unsigned nx, unsigned ny, float pitch, float j
   s->bot->initHexBlock(nx, ny, pitch, jitter, seed);
 }
 int prs_sim_update(prs_sim *s, float dt, float sort_interval) { return s->bot->update(dt, sort_interval) ? 1 : 0; }
+int prs_sim_update_host(prs_sim *s, const float *pos_in, const float *vel_in, const float *rad_in, float *pos_out,
+                        float *vel_out, float *rad_out, float dt, float sort_interval) {
+  return s->bot->updateHost(pos_in, vel_in, rad_in, pos_out, vel_out, rad_out, dt, sort_interval) ? 1 : 0;
+}
 float prs_sim_time(const prs_sim *s) { return s->bot->getTime(); }
 void prs_sim_sync(prs_sim *s) { s->bot->sync(); }
 void *prs_sim_device_ptr(prs_sim *s, int which) { return s->bot->devicePtr(which); }

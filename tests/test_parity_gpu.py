@@ -760,6 +760,33 @@ def test_checkpoint_resume_continues_bit_for_bit(tmp_path, cfg, sort_every_step,
         s_.close()
 
 
+@pytest.mark.parametrize("backend", [prs.BACKEND_FUSED, prs.BACKEND_PERCALL])
+@pytest.mark.parametrize("sort_every_step", [True, False])
+def test_update_host_equals_set_update_get(backend, sort_every_step):
+    """prs_sim_update_host (state kept by the host, asynchronous copies, downloads of positions and radii under the
+    sort and collide kernels) returns exactly what setArray x3 + update + getArray x3 returns, step after step."""
+    p, o = util.cfg("example_gap")
+    si = o.timestep if sort_every_step else o.sort_interval
+    sims = []
+    for _ in range(2):
+        s_ = prs.Simulation(p, 64.0, backend)
+        s_.srand(p.seed)
+        s_.reset()
+        sims.append(s_)
+    a, b = sims
+    pos, vel, rad = (np.ascontiguousarray(a.get(w)) for w in (prs.POSITION, prs.VELOCITY, prs.RADII))
+    hp, hv, hr = pos.copy(), vel.copy(), rad.copy()
+    for k in range(25):
+        a.set(prs.POSITION, pos); a.set(prs.VELOCITY, vel); a.set(prs.RADII, rad)
+        a.update(o.timestep, si)
+        pos, vel, rad = a.get(prs.POSITION), a.get(prs.VELOCITY), a.get(prs.RADII)
+        b.update_host(hp, hv, hr, o.timestep, si)
+        for x, y, name in ((pos, hp, "pos"), (vel, hv, "vel"), (rad, hr, "rad")):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (name, k)
+    assert np.abs(vel).max() > 0
+    a.close(); b.close()
+
+
 def test_runner_checkpoint_files_identical(tmp_path):
     """headless runner: 75 steps in one go and 30 + (resume) 45 steps leave byte-identical checkpoints"""
     exe = os.path.join(util.ROOT, "particlerobotsimulations_b200", "ParticleBot")
