@@ -505,10 +505,17 @@ def run_gpu(args):
     if not ref_cuda and sort_interval <= o.timestep:
         sim2 = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
         sim2.init_hex(geom["nx"], geom["ny"], geom["pitch"], JITTER_FRAC * p.max_radius, SEED)
+        if args.scramble:
+            sim2.set(prs.POSITION, pos0)
         ms2 = timed_steps(torch, sim2, o.timestep, 180.0, min(args.steps, 100), 10, flush)
-        sim2.close()
         secondary = {"sort_interval": 180.0, "ms_per_step": ms2, "value": n / (ms2 * 1e-3), "unit": "particle-steps/s",
                      "what": "same swarm, reference cadence: controller+integrate, gather, collide on the step-0 ordering (Q1)"}
+        if args.try_fused_gather:   # experiment: K1 + gather as one kernel also at this size
+            lib.prs_set_fuse_gather_max(1 << 30)
+            ms3 = timed_steps(torch, sim2, o.timestep, 180.0, min(args.steps, 100), 10, flush)
+            lib.prs_set_fuse_gather_max(65536)
+            secondary["ms_per_step_fused_gather"] = ms3
+        sim2.close()
 
     ref_cuda_cmp = None
     if not ref_cuda and not args.no_ref_cuda:
@@ -544,6 +551,7 @@ def main():
     ap.add_argument("--collide-mode", type=int, default=0)
     ap.add_argument("--collide-tile", type=int, default=None, help="1: collide stages neighbour windows in shared memory by TMA; 0: L1/L2 (default: library default)")
     ap.add_argument("--pdl", type=int, default=None, help="1: programmatic dependent launch between the kernels of the fused step (default: library default)")
+    ap.add_argument("--try-fused-gather", action="store_true", help="secondary: also time K1+gather as one kernel at this size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-kernels-on-R1 comparison block")
     ap.add_argument("--scramble", action="store_true", help="N = 1: permute the robots so that index order is unrelated to position")
