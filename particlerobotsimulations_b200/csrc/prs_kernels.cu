@@ -301,11 +301,18 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
   float2 p = pos[i];
   float2 v = vel[i];
   float r = rad[i];
-  if (run_controller && !dead[i]) {
-    float rn;
-    if (c_prm.p.constrained_contraction) rn = controller_one<true>(r, phase[i], fr[i], fa[i], time, dt);
-    else rn = controller_one<false>(r, phase[i], fr[i], 0.0f, time, dt);
-    if (rn != r) { rad[i] = rn; r = rn; }
+  if (run_controller) {
+    /* phase and the |force| sums are requested together with the dead flag, not after it has arrived: the
+     * kernel is one chain of memory round trips at 2^20 robots (reading them for a dead robot is harmless) */
+    const int is_dead = dead[i];
+    const float ph = phase[i], f_r = fr[i];
+    const float f_a = c_prm.p.constrained_contraction ? fa[i] : 0.0f;
+    if (!is_dead) {
+      float rn;
+      if (c_prm.p.constrained_contraction) rn = controller_one<true>(r, ph, f_r, f_a, time, dt);
+      else rn = controller_one<false>(r, ph, f_r, 0.0f, time, dt);
+      if (rn != r) { rad[i] = rn; r = rn; }
+    }
   }
   const float2 v0 = v;
   integrate_one(p, v, r, dt);
@@ -342,11 +349,18 @@ k_control_integrate_gather(float2 *__restrict__ pos, float2 *__restrict__ vel, f
   float2 p = pos[i];
   float2 v = vel[i];
   float r = rad[i];
-  if (run_controller && !dead[i]) {
-    float rn;
-    if (c_prm.p.constrained_contraction) rn = controller_one<true>(r, phase[i], fr[i], fa[i], time, dt);
-    else rn = controller_one<false>(r, phase[i], fr[i], 0.0f, time, dt);
-    if (rn != r) { rad[i] = rn; r = rn; }
+  if (run_controller) {
+    /* phase and the |force| sums are requested together with the dead flag, not after it has arrived: the
+     * kernel is one chain of memory round trips at 2^20 robots (reading them for a dead robot is harmless) */
+    const int is_dead = dead[i];
+    const float ph = phase[i], f_r = fr[i];
+    const float f_a = c_prm.p.constrained_contraction ? fa[i] : 0.0f;
+    if (!is_dead) {
+      float rn;
+      if (c_prm.p.constrained_contraction) rn = controller_one<true>(r, ph, f_r, f_a, time, dt);
+      else rn = controller_one<false>(r, ph, f_r, 0.0f, time, dt);
+      if (rn != r) { rad[i] = rn; r = rn; }
+    }
   }
   const float2 v0 = v;
   integrate_one(p, v, r, dt);
