@@ -86,8 +86,8 @@ void *prs_get_stream(void);
 /* wall position of integrate; the reference hard-codes 64 (kernel_impl.cuh:75-97) */
 void prs_set_world_half_extent(float half);
 float prs_get_world_half_extent(void);
-/* collide arithmetic: 0 = "exact" (operation order of the reference, IEEE div/sqrt),
- * 1 = "fast" (one reciprocal per pair, shared-memory tiles); both are parity-tested */
+/* kept for callers of earlier builds: every mode runs the exact arithmetic (operation order of the reference,
+ * IEEE div/sqrt); a reciprocal-multiply variant would break the 1e-5 @ 100 steps bar and is not built */
 void prs_set_collide_mode(int mode);
 int prs_get_collide_mode(void);
 /* collide runs one WARP per robot for swarms of up to max_robots (latency-bound sizes; default 16384,

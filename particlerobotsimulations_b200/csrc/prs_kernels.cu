@@ -6,8 +6,9 @@
  *   - one constant block instead of eight symbols, one stream, no per-call allocation, no host sync;
  *   - calcHash / integrate / controller are streaming kernels (and exist fused, k_control_integrate_hash);
  *   - sort is the onesweep radix sort of prs_onesweep.cuh;
- *   - collide exists in an "exact" variant (operation order of the reference) and a "fast" variant
- *     (shared-memory row tiles, one reciprocal per pair) — prs_collide.cuh.
+ *   - collide (prs_collide.cuh) keeps the operation order of the reference — bit-identical results — in
+ *     three kernels: thread per robot through L1/L2, thread per robot with TMA-staged shared-memory
+ *     windows, warp per robot for small swarms.
  *
  * Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo   (NO --use_fast_math: hashes
  * need IEEE divides, the reference is built without it, Makefile:78-84).
