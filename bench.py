@@ -527,7 +527,7 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(geom, n),
                    "sort_interval": "timestep (sort every step)" if sort_interval <= o.timestep else sort_interval,
-                   "collide_mode": "exact" if args.collide_mode == 0 else "fast", "l2": "flushed between timed steps (256 MiB write)",
+                   "collide_mode": "exact", "l2": "flushed between timed steps (256 MiB write)",
                    "collide_neighbours": "shared-memory windows staged by TMA bulk copies" if lib.prs_get_collide_tile() else "L1/L2",
                    "programmatic_dependent_launch": bool(lib.prs_get_pdl())},
         "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},
