@@ -1101,6 +1101,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     k1_done();
   }
   if (b->sortedPR) {
+    bool report = false;
     {
       StageScope t(PRS_STAGE_REORDER);
       PrsTableState &T = g_prs.table;
@@ -1121,12 +1122,17 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
         bin_ensure(n, b->numCells);
         PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
         PRS_LAUNCH(k_max_population, div_up(n, 256), 256, 0, b->hash, b->cellStart, b->cellEnd, n, B.scratch + 1);
-        bin_send_report(B.scratch + 1);
+        report = true;
       }
     }
-    StageScope t(PRS_STAGE_COLLIDE);
-    prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
-    prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+    {
+      StageScope t(PRS_STAGE_COLLIDE);
+      prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
+      prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+    }
+    /* the 8-byte report goes out AFTER collide: a device-to-host copy queued before it would sit behind whatever
+     * the copy engine is busy with (the host-buffer step downloads 12 MB right then) and hold collide back */
+    if (report) bin_send_report(B.scratch + 1);
     return;
   }
   {
