@@ -567,6 +567,47 @@ def test_synthetic_hex_swarm_properties():
     sim.close()
 
 
+def test_s1_full_size_fused_equals_percall_and_invariants():
+    """BASELINE.json's S1 at full size (bench.py's own workload: 2^20 robots, world +-128, 2048^2 cells): 40 steps of the
+    fused path (cell binning with tile skipping, packed thread-per-robot collide, programmatic dependent launch)
+    against the per-call path of this library (onesweep sort, reference array layout, one launch per reference
+    entry point) — identical bits — plus the size-independent invariants: keys sorted, index a permutation in
+    ascending order inside every cell (stable sort), table consistent with the keys, empty cells marked."""
+    import bench
+    out = {}
+    for name, backend in (("fused", prs.BACKEND_FUSED), ("percall", prs.BACKEND_PERCALL)):
+        p, o, geom = bench.swarm_config(prs, 20)
+        sim = prs.Simulation(p, geom["half"], backend)
+        sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], bench.JITTER_FRAC * p.max_radius, bench.SEED)
+        for k in range(40):
+            sim.update(o.timestep, o.timestep)
+            if k == 3:
+                sim.sync()       # the density report arrives: the binned route is taken from here on
+        out[name] = {key: sim.get(w) for key, w in (("pos", prs.POSITION), ("vel", prs.VELOCITY), ("rad", prs.RADII),
+                                                    ("hash", prs.HASH), ("index", prs.INDEX), ("cs", prs.CELLSTART),
+                                                    ("absForce_r", prs.ABSFORCE_R))}
+        if name == "fused":
+            assert prs.lib().prs_bin_active() == 1
+            out["ce"] = sim.get(prs.CELLEND)
+        sim.close()
+    a, b = out["fused"], out["percall"]
+    for key in a:
+        assert np.array_equal(a[key].view(np.uint32), b[key].view(np.uint32)), key
+    h, idx, cs, ce = a["hash"], a["index"], a["cs"], out["ce"]
+    n = h.size
+    assert np.all(h[1:] >= h[:-1])
+    assert np.array_equal(np.sort(idx), np.arange(n, dtype=np.uint32))
+    same_cell = h[1:] == h[:-1]
+    assert np.all(idx[1:][same_cell] > idx[:-1][same_cell])          # stable: ascending original index inside a cell
+    occ = np.unique(h)
+    assert np.array_equal(cs[occ], np.searchsorted(h, occ, "left").astype(np.uint32))
+    assert np.array_equal(ce[occ], np.searchsorted(h, occ, "right").astype(np.uint32))
+    empty = np.ones(cs.size, bool)
+    empty[occ] = False
+    assert np.all(cs[empty] == 0xFFFFFFFF)
+    assert np.all(np.isfinite(a["pos"])) and float(np.abs(a["vel"]).max()) > 0
+
+
 def _hex_run(mode, steps, scramble=False, crowd=0, drift=0.0):
     """64k hex swarm through the fused path with the cell sort pinned to one route (prs_bin_set_mode)."""
     p, o = util.cfg("example")
