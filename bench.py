@@ -15,8 +15,9 @@ collide) over the whole synthetic swarm.  Workloads (BASELINE.md
 Timing: W warm-up steps, then K steps each bracketed by CUDA events on the launching stream with
 an L2 flush (256 MiB write) between steps, outside the events; value = robots*K / sum(step times),
 max over ranks.  `back_to_back` is the same K steps without flushes (warm L2), for context.
-`e2e` runs the same steps through the C-ABI with HOST buffers: pinned-host -> device copies of
-pos/vel/rad before, device -> host copies of pos/vel/rad after every step, inside the timed region.
+`e2e` runs the same steps through the C-ABI with HOST buffers (prs_sim_update_host): pinned-host -> device copies of
+pos/vel/rad before, device -> host copies of pos/vel/rad after every step, inside the timed region (asynchronous; the
+downloads of pos and rad overlap sort + collide); `e2e.reference_api` is the same through the reference's blocking calls.
 `--impl reference` times the CPU oracle port (OpenMP, all host threads) — the reference ships no
 CPU path; `--impl ref-cuda` (extra) times the reference's OWN kernels compiled verbatim
 (oracle/_ref) on R1, the largest hex block its hard-coded +-64 world holds (640x640 robots);
