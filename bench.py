@@ -2,7 +2,7 @@
 """bench.py — particle-steps/s of the per-timestep particle-robot update (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference|ref-cuda]
-                    [--robots-log2 L] [--sort-interval S] [--collide-mode 0|1]
+                    [--robots-log2 L] [--sort-interval S]
 
 A "step" is one Particlebot::update() (controller -> integrate -> hash -> sort -> reorder ->
 collide) over the whole synthetic swarm.  Workloads:
@@ -41,12 +41,29 @@ PITCH = 0.17   # BASELINE.md S1 says 0.155 (= 2*min_radius): that crystal is num
 JITTER_FRAC = 0.01
 SEED = 5555
 STAGES = ["controller+integrate+hash", "sort", "reorder+celltable", "collide", "phase", "exchange"]
+# every GPU workload is timed from this step on, whatever --warmup is (the swarm needs ~250 steps for its contact
+# network to form: collide is cheaper before that); the warm-up steps are the last W steps before it
+EVOLVE_TO = 260
 
 
 # ------------------------------------------------------------------------------------------------
+class _Run:
+    """timestep / sort_interval of the cfg (stand-in for prs.RunOptions on the arm that must not load the product library)"""
+
+    def __init__(self, d):
+        self.timestep, self.sort_interval = float(np.float32(d["timestep"])), float(np.float32(d["sort_interval"]))
+
+
 def swarm_config(prs, log2n, world64=False, nx=None, ny=None, pitch=None):
-    """SimParams + hex-block geometry of the synthetic swarm with 2^log2n robots (or nx*ny)."""
-    p, o = prs.load_cfg(os.path.join(ROOT, "examples", "example.cfg"))
+    """SimParams + hex-block geometry of the synthetic swarm with 2^log2n robots (or nx*ny).
+    prs = the product package, or None: parameters from oracle/params.py (pure Python; the reference arm)."""
+    cfg = os.path.join(ROOT, "examples", "example.cfg")
+    if prs is None:
+        from oracle import params as op
+        p, run = op.load_cfg(cfg)
+        o = _Run(run)
+    else:
+        p, o = prs.load_cfg(cfg)
     pitch = PITCH if pitch is None else pitch
     if nx is None:
         nx = 1 << ((log2n + 1) // 2)
@@ -60,7 +77,10 @@ def swarm_config(prs, log2n, world64=False, nx=None, ny=None, pitch=None):
         half = float(np.ceil(max(w, h) / 2 * 1.2 / 64.0) * 64.0)
         grid = 1 << int(np.ceil(np.log2(2 * half / 0.235)))
         light = {20: (-90.0, 0.0), 26: (-700.0, 0.0)}.get(log2n, (-0.7 * half, 0.0))
-    prs.lib().prs_params_set_world(C.byref(p), grid, half)
+    if prs is None:
+        op.set_world(p, grid, half)
+    else:
+        prs.lib().prs_params_set_world(C.byref(p), grid, half)
     p.light_x, p.light_y = light
     p.max_time = 1e30
     name = {20: "S1", 26: "S2"}.get(log2n, f"S(2^{log2n})")
@@ -241,8 +261,8 @@ def hex_positions(p, geom):
 
 
 
-def timed_steps(torch, sim, dt, sort_interval, steps, warmup, flush):
-    """median ms per step of sim.update over `steps` steps (CUDA events on the current stream, L2 flushed between steps)"""
+def timed_steps(torch, sim, dt, sort_interval, steps, warmup, flush, stat="median"):
+    """ms per step of sim.update over `steps` steps (CUDA events on the current stream, L2 flushed between steps)"""
     stream = torch.cuda.current_stream()
     for _ in range(warmup):
         sim.update(dt, sort_interval)
@@ -254,7 +274,47 @@ def timed_steps(torch, sim, dt, sort_interval, steps, warmup, flush):
         sim.update(dt, sort_interval)
         b.record(stream)
     torch.cuda.synchronize()
-    return float(np.median([a.elapsed_time(b) for a, b in ev]))   # median: the reference's per-sort cudaMalloc/cudaFree makes outliers
+    t = [a.elapsed_time(b) for a, b in ev]
+    return float(np.median(t) if stat == "median" else np.mean(t))   # median: the reference's per-sort cudaMalloc/cudaFree makes outliers
+
+
+def pairs_per_robot(prs, sim, p):
+    """ordered neighbour pairs per robot that collide evaluates (5x5 stencil, wrapped), from the current hashes"""
+    n = int(p.nCells)
+    h = sim.get(prs.HASH).astype(np.int64)
+    gdim = int(p.gridSize.x)
+    cnt = np.bincount(h, minlength=gdim * gdim).reshape(gdim, gdim).astype(np.int64)
+    rows = np.flatnonzero(cnt.sum(1))
+    cols = np.flatnonzero(cnt.sum(0))
+    if rows.size and rows[0] >= 2 and rows[-1] < gdim - 2 and cols[0] >= 2 and cols[-1] < gdim - 2:
+        cnt = cnt[rows[0] - 2:rows[-1] + 3, cols[0] - 2:cols[-1] + 3]     # nothing wraps: work on the occupied box only
+    box = sum(np.roll(np.roll(cnt, dy, 0), dx, 1) for dy in range(-2, 3) for dx in range(-2, 3))
+    return int((cnt * box).sum() - n)
+
+
+def one_gpu_swarm_block(torch, prs, flush, log2n, steps, evolve_to=None, pitch=None, warmup=3):
+    """a whole synthetic swarm on THIS GPU through the fused path: evolved (untimed) to step `evolve_to`, then `steps`
+    steps timed like the primary (events per step, L2 flushed between them, mean)"""
+    evolve_to = EVOLVE_TO if evolve_to is None else evolve_to
+    p, o, geom = swarm_config(prs, log2n, pitch=pitch)
+    n = int(p.nCells)
+    sim = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
+    sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], JITTER_FRAC * p.max_radius, SEED)
+    for k in range(max(evolve_to - warmup, 0)):
+        sim.update(o.timestep, o.timestep)
+        if k == 3:
+            sim.sync()
+    ms = timed_steps(torch, sim, o.timestep, o.timestep, steps, min(warmup, evolve_to), flush, stat="mean")
+    pairs = pairs_per_robot(prs, sim, p) / n
+    finite = bool(np.isfinite(sim.get(prs.POSITION)).all())
+    sim.close()
+    _, b_alg, passes = algorithmic_bytes(p, True)
+    peak, _ = measured_peak()
+    return {"workload": workload_text(geom, n), "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "particle-steps/s",
+            "steps": steps, "timed_state_step": evolve_to, "state": f"steps {evolve_to}..{evolve_to + steps} of the swarm started from the lattice",
+            "ordered_pairs_per_robot": pairs, "state_finite": finite,
+            "roofline_step": {"alg_bytes_per_particle_step": b_alg, "achieved": b_alg * n / (ms * 1e-3) / 1e9, "peak": peak,
+                              "unit": "GB/s", "frac": b_alg * n / (ms * 1e-3) / 1e9 / peak}}
 
 
 def ref_cuda_block(torch, prs, flush, steps=30, warmup=5):
@@ -279,8 +339,8 @@ def ref_cuda_block(torch, prs, flush, steps=30, warmup=5):
 def run_reference_cpu(args):
     """--impl reference: the reference has no CPU implementation; this times the oracle port with
     every host thread on a bounded sample of the same workload (same lattice, density, physics)."""
-    import particlerobotsimulations_b200 as prs
     from oracle import binding as ob
+    prs = None      # this arm must not map the product library: parameters come from oracle/params.py
     threads = len(os.sched_getaffinity(0))
     budget_s = 120.0
     log2n = args.robots_log2 or (20 if args.gpus == 1 else 26)
@@ -328,8 +388,7 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        from particlerobotsimulations_b200 import multigpu
-        return multigpu.bench_slabs(args, rank, world, local_rank)
+        return run_slabs(args, rank, world, local_rank)
 
     torch.cuda.set_device(local_rank)
     lib = prs.lib()
@@ -346,7 +405,6 @@ def run_gpu(args):
     sort_interval = o.timestep if args.sort_interval is None else args.sort_interval
     stream = torch.cuda.current_stream()
     lib.prs_set_stream(C.c_void_p(stream.cuda_stream))
-    lib.prs_set_collide_mode(args.collide_mode)
     if args.collide_tile is not None:
         lib.prs_set_collide_tile(args.collide_tile)
     if args.pdl is not None:
@@ -374,6 +432,11 @@ def run_gpu(args):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    evolve_to = max(args.evolve_to, args.warmup)
+    for k in range(evolve_to - args.warmup):     # untimed: brings the swarm to the fixed state the timing starts from
+        step()
+        if k == 3:
+            torch.cuda.synchronize()             # the density report arrives: cell binning from here on
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -476,18 +539,16 @@ def run_gpu(args):
     # ---- the dominant kernel against the unit that actually binds it (informational, next to the HBM roofline) ----
     roofline_compute = None
     if not ref_cuda and stages and "collide" in stages:
-        h = sim.get(prs.HASH).astype(np.int64)
-        gdim = int(p.gridSize.x)
-        cnt = np.bincount(h, minlength=gdim * gdim).reshape(gdim, gdim).astype(np.int64)
-        box = sum(np.roll(np.roll(cnt, dy, 0), dx, 1) for dy in range(-2, 3) for dx in range(-2, 3))   # 5x5 stencil, wrapped
-        pairs = int((cnt * box).sum() - n)                     # ordered neighbour pairs evaluated per step
+        pairs = pairs_per_robot(prs, sim, p)                   # ordered neighbour pairs of the reference's loop per step
         sm_clock_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
         xu_peak = 148 * 16 * sm_clock_hz / 4.0                 # 16 MUFU lanes per SM and clock, 4 MUFU ops per far pair
         rate = pairs / (stages["collide"]["avg_us"] * 1e-6)
-        roofline_compute = {"kernel": "collide", "bound": "xu (MUFU) pipe", "pairs_per_step": pairs, "achieved": rate, "peak": xu_peak,
-                            "unit": "neighbour pairs/s", "frac": rate / xu_peak,
-                            "what": "4 MUFU ops (rsqrt, lg2, ex2, rcp) per far pair are what the reference's formulas need after sharing; "
-                                    "peak = 148 SMs x 16 MUFU lanes x SM clock / 4"}
+        roofline_compute = {"kernel": "collide", "bound": "xu (MUFU) pipe", "ordered_pairs_per_step": pairs,
+                            "unordered_pairs_per_step": pairs // 2, "achieved": rate / 2, "peak": xu_peak,
+                            "unit": "unordered neighbour pairs/s", "frac": rate / 2 / xu_peak, "frac_ordered_pairs": rate / xu_peak,
+                            "what": "floor = every UNORDERED pair evaluated once (F_ji = -F_ij bit for bit) at 4 MUFU ops "
+                                    "(rsqrt, lg2, ex2, rcp) per far pair; peak = 148 SMs x 16 MUFU lanes x SM clock / 4. "
+                                    "frac_ordered_pairs counts the reference's loop (each pair from both sides)"}
     sim.close()
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port, all threads, a few steps of the same swarm ----
@@ -508,6 +569,8 @@ def run_gpu(args):
         sim2.init_hex(geom["nx"], geom["ny"], geom["pitch"], JITTER_FRAC * p.max_radius, SEED)
         if args.scramble:
             sim2.set(prs.POSITION, pos0)
+        for k in range(max(evolve_to - 10, 0)):      # same timed state as the primary (the first step sorts, the rest reuse it)
+            sim2.update(o.timestep, 180.0)
         ms2 = timed_steps(torch, sim2, o.timestep, 180.0, min(args.steps, 100), 10, flush)
         secondary = {"sort_interval": 180.0, "ms_per_step": ms2, "value": n / (ms2 * 1e-3), "unit": "particle-steps/s",
                      "what": "same swarm, reference cadence: controller+integrate, gather, collide on the step-0 ordering (Q1)"}
@@ -522,6 +585,18 @@ def run_gpu(args):
     if not ref_cuda and not args.no_ref_cuda:
         ref_cuda_cmp = ref_cuda_block(torch, prs, flush)
 
+    # ---- BASELINE.md's S1 as specified (pitch 0.155 = 2*min_radius), over the steps before the reference's own kernels
+    #      blow that crystal up (profiles/workload_stability_r1.txt): steps 10..50 ----
+    spec_pitch = None
+    if not ref_cuda and not r1 and log2n == 20 and not args.no_extras:
+        spec_pitch = one_gpu_swarm_block(torch, prs, flush, 20, 40, evolve_to=10, pitch=0.155)
+        spec_pitch["what"] = ("S1 at BASELINE.md's pitch 0.155; numerically unstable under the reference's explicit-Euler DEM "
+                              "(NaN by step 300 with the reference's own kernels), hence timed over steps 10..50 only")
+    # ---- S2 (2^26 robots) on this one GPU: the same-workload baseline of the multi-GPU lines ----
+    s2_one = None
+    if not ref_cuda and not r1 and log2n == 20 and not args.no_extras and not args.no_s2:
+        s2_one = one_gpu_swarm_block(torch, prs, flush, 26, min(args.steps, 25))
+
     line = {
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -534,11 +609,159 @@ def run_gpu(args):
         "back_to_back": {"value": n * args.steps / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / args.steps, "l2": "warm"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step, "roofline_compute": roofline_compute,
         "stages": stages, "cpu_baseline": cpu, "ref_cuda": ref_cuda_cmp, "secondary": secondary, "state_finite": finite,
+        "timed_state_step": evolve_to, "secondary_spec_pitch_0155": spec_pitch, "s2_one_gpu": s2_one,
+        "scaling_note": "--gpus 1 times S1 (2^20 robots, the single-GPU roofline workload); --gpus N>1 times S2 (2^26 robots, fixed "
+                        "total: strong scaling) and carries its own same-workload 1-GPU point (one_gpu_same_workload); "
+                        "s2_one_gpu here is that point measured in this run",
     }
     if ref_cuda:
         line["impl"] = "ref-cuda"
         line["config"]["workload"] += " [reference kernels compiled verbatim; reference world +-64, grid 512^2]"
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_slabs(args, rank, world, local_rank):
+    """--gpus N (N > 1): S2 (2^26 robots, or --robots-log2) slab-decomposed over the ranks.  Before timing, the slab
+    engine is checked bit for bit against the single-GPU path on the live ranks (multigpu.selfcheck_vs_single_gpu);
+    after it, rank 0 alone runs the SAME swarm on its one GPU at the same timed state (one_gpu_same_workload)."""
+    import torch
+    import torch.distributed as dist
+    import particlerobotsimulations_b200 as prs
+    from particlerobotsimulations_b200 import multigpu
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    lib = prs.lib()
+    parity = None
+    if not args.no_parity_check:
+        parity = multigpu.selfcheck_vs_single_gpu(os.path.join(ROOT, "examples", "example.cfg"), rank, world, dev,
+                                                  exchange=args.exchange)
+        ok = torch.tensor([1 if (parity is None or parity["bit_equal"]) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"metric": "particle-steps/sec", "n_gpus": world, "error": "slab engine differs from the single-GPU path",
+                                  "parity_check": parity}))
+            dist.destroy_process_group()
+            sys.exit(3)
+    log2n = args.robots_log2 or 26
+    p, o, geom = swarm_config(prs, log2n)
+    n_total = int(p.nCells)
+    sim = multigpu.make_hex_slab(p, o, geom, multigpu.CudaBackend, rank, world, dev, SEED, JITTER_FRAC * p.max_radius,
+                                 exchange=args.exchange)
+    sort_interval = o.timestep if args.sort_interval is None else args.sort_interval
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evolve_to = max(args.evolve_to, args.warmup)
+    for _ in range(evolve_to):                 # untimed pre-evolution to the fixed timed state; its last W steps are the warm-up
+        sim.step(o.timestep, sort_interval)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler.mark()
+    lib.prs_launch_count(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(stream)
+        sim.step(o.timestep, sort_interval)
+        b.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler.mark()
+    launches = int(lib.prs_launch_count(0))
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    sim.check()
+    st = sim.stats
+    n_own = sim.n
+    own = torch.tensor([n_own, st["migrated"], st["halo"]], dtype=torch.int64, device=dev)
+    owns = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(owns, own)
+    steps_run = evolve_to + args.steps
+
+    # ---- per-stage event timing on this rank (kernels only; the neighbour transfers sit between the stages) ----
+    lib.prs_stage_timing(1)
+    for _ in range(min(args.steps, 10)):
+        flush.fill_(1)
+        sim.step(o.timestep, sort_interval)
+    ms = (C.c_float * 6)()
+    cnt = (C.c_uint * 6)()
+    lib.prs_stage_times(ms, cnt)
+    lib.prs_stage_timing(0)
+    clocks = sampler.stop()
+    per_bytes, b_alg, passes = algorithmic_bytes(p, sort_interval <= o.timestep)
+    peak, peak_src = measured_peak()
+    stages = {}
+    for i, name in enumerate(STAGES):
+        if cnt[i]:
+            per_step_us = 1e3 * ms[i] / min(args.steps, 10)
+            gbs = per_bytes[name] * n_own / (per_step_us * 1e-6) / 1e9 if per_bytes[name] else None
+            stages[name] = {"us_per_step": per_step_us, "alg_bytes_per_robot": per_bytes[name], "achieved_GBps": gbs,
+                            "frac_of_hbm_peak": (gbs / peak) if gbs else None}
+
+    # ---- e2e: every rank's pos/vel/rad come from pinned host memory and go back to it every step ----
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_s = sim.time_host_steps(o.timestep, sort_interval, e2e_steps)
+    finite = torch.tensor([int(torch.isfinite(sim.s.pos[:n_own]).all())], device=dev)
+    dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+    exchange_used = sim.exchange
+    sim.close()
+    del sim
+    torch.cuda.empty_cache()
+
+    # ---- the same swarm at the same timed state on ONE GPU (rank 0; the other ranks wait) ----
+    one = None
+    if rank == 0 and not args.no_extras:
+        lib.prs_set_stream(C.c_void_p(stream.cuda_stream))
+        one = one_gpu_swarm_block(torch, prs, flush, log2n, min(args.steps, 25), evolve_to=evolve_to)
+    dist.barrier()
+    if rank == 0:
+        value = n_total * args.steps / (total_ms_max * 1e-3)
+        per_rank = [[int(v) for v in x.tolist()] for x in owns]
+        line = {
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_text(geom, n_total), "decomposition": f"{world} slabs of grid rows",
+                       "sort_interval": "timestep (sort every step)",
+                       "l2": "flushed between timed steps (256 MiB write)", "halo_rows": multigpu.HALO_ROWS,
+                       "exchange": "peer-to-peer stores into the neighbour's mailbox (CUDA IPC over NVLink)" if exchange_used == "p2p"
+                                   else "NCCL send/recv of fixed-size buffers"},
+            "timed_state_step": evolve_to,
+            "scaling_note": "strong scaling of the fixed 2^%d-robot swarm; the driver's --gpus 1 line is S1 (2^20 robots), so the "
+                            "same-workload 1-GPU point is one_gpu_same_workload below (measured in this job on rank 0)" % log2n,
+            "one_gpu_same_workload": one,
+            "speedup_vs_one_gpu": (one["ms_per_step"] / (total_ms_max / args.steps)) if one else None,
+            "parity_check": parity,
+            "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 20 * n_total,
+                    "d2h_bytes_per_step": 20 * n_total, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "what": "per rank: pos/vel/rad of the owned robots from pinned host -> device, SlabSim.step, device -> pinned host"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": ({"bound": "hbm", "kernel": "collide (rank 0)", "achieved": stages["collide"]["achieved_GBps"], "peak": peak,
+                          "unit": "GB/s", "frac": stages["collide"]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                          "note": "collide is FP32/MUFU-issue-bound, not HBM-bound; see roofline_step"} if "collide" in stages else None),
+            "stages_rank0": stages, "cpu_baseline": None,
+            "roofline_step": {"bound": "hbm", "alg_bytes_per_particle_step": b_alg, "radix_passes": passes,
+                              "achieved": b_alg * value / 1e9, "peak": peak * world, "unit": "GB/s",
+                              "frac": b_alg * value / 1e9 / (peak * world), "peak_source": peak_src + f" x {world} GPUs"},
+            "slabs": {"robots_per_rank": [x[0] for x in per_rank],
+                      "migrated_per_step_per_rank": [x[1] / steps_run for x in per_rank],
+                      "halo_robots_per_step_per_rank": [x[2] / steps_run for x in per_rank]},
+            "state_finite": bool(finite.item()),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
 
 
 def main():
@@ -549,10 +772,13 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference", "ref-cuda"])
     ap.add_argument("--robots-log2", type=int, default=None)
     ap.add_argument("--sort-interval", type=float, default=None)
-    ap.add_argument("--collide-mode", type=int, default=0)
     ap.add_argument("--collide-tile", type=int, default=None, help="1: collide stages neighbour windows in shared memory by TMA; 0: L1/L2 (default: library default)")
     ap.add_argument("--pdl", type=int, default=None, help="1: programmatic dependent launch between the kernels of the fused step (default: library default)")
     ap.add_argument("--try-fused-gather", action="store_true", help="secondary: also time K1+gather as one kernel at this size")
+    ap.add_argument("--evolve-to", type=int, default=EVOLVE_TO, help="the timed region starts at this step of the swarm (untimed pre-evolution)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary blocks (pitch 0.155, S2 on one GPU)")
+    ap.add_argument("--no-s2", action="store_true", help="skip the 2^26-robot block of the N = 1 line")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the slab-vs-single-GPU bit-equality check before timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-kernels-on-R1 comparison block")
     ap.add_argument("--scramble", action="store_true", help="N = 1: permute the robots so that index order is unrelated to position")

@@ -21,6 +21,8 @@
 #include <stddef.h>
 #include "prs_simparams.h"
 
+/* the library is built with -fvisibility=hidden: only what this header declares is exported */
+#pragma GCC visibility push(default)
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -50,6 +52,11 @@ void unmapGLBufferObject(struct cudaGraphicsResource *res);
 void setParameters(SimParams *hostParams);            /* :111 params + 7 obstacle arrays -> constant memory */
 
 unsigned iDivUp(unsigned a, unsigned b);              /* :126 */
+#ifdef __cplusplus
+/* :132, :139 — exported by the reference's translation unit with C linkage although no header declares them */
+void computeGridSize(unsigned n, unsigned blockSize, unsigned &numBlocks, unsigned &numThreads);
+void computeGridSize2(unsigned n, unsigned blockSize, unsigned &numBlocks, unsigned &numThreads);
+#endif
 
 void integrateSystem(float *pos, float *vel, float *rad, float deltaTime, unsigned nCells,
                      float time);                     /* :145 + kernel_impl.cuh:53-103 */
@@ -86,10 +93,6 @@ void *prs_get_stream(void);
 /* wall position of integrate; the reference hard-codes 64 (kernel_impl.cuh:75-97) */
 void prs_set_world_half_extent(float half);
 float prs_get_world_half_extent(void);
-/* kept for callers of earlier builds: every mode runs the exact arithmetic (operation order of the reference,
- * IEEE div/sqrt); a reciprocal-multiply variant would break the 1e-5 @ 100 steps bar and is not built */
-void prs_set_collide_mode(int mode);
-int prs_get_collide_mode(void);
 /* collide runs one WARP per robot for swarms of up to max_robots (latency-bound sizes; default 16384,
  * 0 = always one thread per robot).  Same bits either way. */
 void prs_set_collide_warp_max(unsigned max_robots);
@@ -179,7 +182,9 @@ enum {
   PRS_SLAB_ERR_CAPACITY = 4,   /* more robots than cap */
   PRS_SLAB_ERR_TWO_SLABS = 8,  /* a robot crossed more than one slab between two sorts */
   PRS_SLAB_ERR_LEFT_WORLD = 16, /* a robot left the rows of the first / last slab (hash wrap-around) */
-  PRS_SLAB_ERR_PEER_TIMEOUT = 32 /* peer-to-peer exchange: the neighbour's data did not arrive */
+  PRS_SLAB_ERR_PEER_TIMEOUT = 32, /* peer-to-peer exchange: the neighbour's data did not arrive */
+  PRS_SLAB_ERR_DRIFT = 64      /* between two sorts an owned robot drifted so far that its 5x5 stencil leaves the rows
+                                  this rank holds (owned + halo_rows): raise halo_rows or sort more often */
 };
 typedef struct {
   /* owned robots, local slots [0, cap) */
@@ -286,4 +291,5 @@ int prs_sim_checkpoint_load(prs_sim *s, const char *path);
 #ifdef __cplusplus
 }
 #endif
+#pragma GCC visibility pop
 #endif /* PRS_CABI_H */

@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include "prs_cabi.h"
 
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 struct PrsBackend {
   void *dl_handle;
   void (*allocateArray)(void **, size_t);
@@ -134,5 +135,6 @@ class Particlebot {
   PrsRand rng_;
   unsigned configSizeX_;
 };
+#pragma GCC visibility pop
 
 #endif

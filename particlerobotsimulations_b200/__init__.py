@@ -85,7 +85,8 @@ class Slab(C.Structure):
 SC_N, SC_NLO, SC_NHI, SC_KDN, SC_KUP, SC_MIGDN, SC_MIGUP, SC_LEAVERS, SC_HOLES, SC_KEEPERS, SC_ERR, SC_STAT_MIG, SC_STAT_HALO = range(13)
 SLAB_ERRORS = {1: "more migrants than mig_cap in one step", 2: "a halo longer than halo_cap", 4: "more robots than the slab capacity",
                8: "a robot crossed more than one slab between two sorts", 16: "a robot left the grid rows of the outermost slab",
-               32: "peer-to-peer exchange timed out waiting for a neighbour"}
+               32: "peer-to-peer exchange timed out waiting for a neighbour",
+               64: "an owned robot drifted beyond the halo rows between two sorts (raise halo_rows or sort more often)"}
 SLAB_MIG_WORDS, SLAB_HALO_WORDS = 23, 7
 
 _lib = None
@@ -112,7 +113,6 @@ SIGNATURES = {
     # part 2
     "prs_version": (C.c_char_p, []), "prs_set_stream": (None, [_VP]), "prs_get_stream": (_VP, []),
     "prs_set_world_half_extent": (None, [_F]), "prs_get_world_half_extent": (_F, []),
-    "prs_set_collide_mode": (None, [_I]), "prs_get_collide_mode": (_I, []),
     "prs_set_collide_warp_max": (None, [_U]),
     "prs_set_collide_tile": (None, [_I]), "prs_get_collide_tile": (_I, []),
     "prs_set_pdl": (None, [_I]), "prs_get_pdl": (_I, []),

@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
     deps = _deps()
     if force or _newer(LIB, deps):
         cmd = [NVCC] + ARCH + COMMON + ["-Xptxas", "-v"] * bool(verbose) + [
-            "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "-o", LIB,
+            "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xlinker", "-Bsymbolic", "-o", LIB,
         ] + [os.path.join(CSRC, s) for s in LIB_SOURCES] + ["-ldl"]
         if verbose:
             print(" ".join(cmd))

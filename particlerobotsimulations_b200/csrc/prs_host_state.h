@@ -37,7 +37,6 @@ struct PrsHostState {
   PrsDevParams h_prm = {};            /* shadow of the constant block */
   bool params_set = false;
   float world_half = 64.0f;           /* reference wall (kernel_impl.cuh:75-97) */
-  int collide_mode = 0;               /* 0 exact, 1 fast */
   unsigned fuse_gather_max = 65536;   /* steps without a sort: swarms up to this size run K1 and the gather as one kernel */
   /* host-buffer step (prs_sim_update_host): second stream for the device-to-host copies that may start as soon
    * as K1 has written positions and radii, and the event K1's completion is recorded in */

@@ -660,10 +660,13 @@ static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out
   const unsigned hist_blocks = min(div_up(n, HIST_THREADS * 8), 148u * 8u);
   PRS_LAUNCH(k_histogram, hist_blocks, HIST_THREADS, 0, in_k, n, ghist, npass, n_dev);
   const uint32_t *src_k = in_k, *src_v = vals_are_iota ? nullptr : in_v;
+  /* a single pass (key_bits <= 8) would scatter into the buffer its other tiles still read when out_* aliases
+   * in_*: it then lands in scratch and is copied back */
+  const bool bounce = npass == 1 && (out_k == in_k || (in_v && out_v == in_v));
   for (int p = 0; p < npass; p++) {
     /* ping-pong through the two scratch pairs so that the LAST pass lands in out_* */
     uint32_t *dst_k, *dst_v;
-    if (p == npass - 1) { dst_k = out_k; dst_v = out_v; }
+    if (p == npass - 1 && !bounce) { dst_k = out_k; dst_v = out_v; }
     else { dst_k = w.keys[p & 1]; dst_v = w.vals[p & 1]; }
     unsigned long long *tl = g_prs.sort_timeline ? g_prs.sort_timeline + (size_t)p * tiles * 8 : nullptr;
     if (nt == 512)
@@ -674,6 +677,10 @@ static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out
                             status + (size_t)p * tiles * RADIX, counters + p, tl, n_dev);
     src_k = dst_k;
     src_v = dst_v;
+  }
+  if (bounce) {
+    PRS_CUDA(cudaMemcpyAsync(out_k, w.keys[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, g_prs.stream));
+    PRS_CUDA(cudaMemcpyAsync(out_v, w.vals[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, g_prs.stream));
   }
 }
 
@@ -757,6 +764,14 @@ void setParameters(SimParams *hp) {
 }
 
 unsigned iDivUp(unsigned a, unsigned b) { return (a % b != 0) ? (a / b + 1) : (a / b); }
+void computeGridSize(unsigned n, unsigned blockSize, unsigned &numBlocks, unsigned &numThreads) {
+  numThreads = blockSize < n ? blockSize : n;
+  numBlocks = iDivUp(n, numThreads);
+}
+void computeGridSize2(unsigned n, unsigned blockSize, unsigned &numBlocks, unsigned &numThreads) {
+  numThreads = blockSize;
+  numBlocks = iDivUp(n, numThreads);
+}
 
 void integrateSystem(float *pos, float *vel, float *rad, float deltaTime, unsigned nCells, float /*time*/) {
   if (!nCells) return;
@@ -862,8 +877,6 @@ void prs_set_world_half_extent(float half) {
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
 }
 float prs_get_world_half_extent(void) { return g_prs.world_half; }
-void prs_set_collide_mode(int mode) { g_prs.collide_mode = mode; }
-int prs_get_collide_mode(void) { return g_prs.collide_mode; }
 /* swarms of up to max_robots use the warp-per-robot collide kernel (0 = never); default 16384 */
 void prs_set_collide_warp_max(unsigned max_robots) { g_prs.collide_warp_max = max_robots; }
 void prs_set_collide_tile(int on) { g_prs.collide_tile = on ? 1 : 0; }
@@ -1145,7 +1158,11 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
                      (const float2 *)b->sortedVel, b->sortedRad, b->index, b->cellStart, b->cellEnd, n, dt, need_fa);
 }
 
+}  // extern "C"
+
 #include "prs_slab.cuh"
+
+extern "C" {
 
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n) {
   if (!n) return;

@@ -213,6 +213,10 @@ bool Particlebot::update(float deltaTime, float sort_interval) {
     if (n) be_.copyArrayToDevice(dDead, hDead, 0, n * (int)sizeof(int));
   }
 
+  /* centroid into the render trail pos[n + k] (particlebot.cpp:207-209): every centroid_int of simulated time */
+  if (n && gate(time, params.centroid_int, deltaTime))
+    be_.calcCOG(dPos, tempPos1, tempPos2, n, time, params.centroid_steps, params.centroid_int);
+
   const bool phase_step = params.control == LIGHT_WAVE && gate(time, params.phase_update_interval, deltaTime);
   /* the first update always hashes and sorts: at time 0 the gate fires anyway; after loadFromFile (time > 0)
    * the reference would build its table from never-written hash/index arrays */

@@ -1,7 +1,7 @@
 /*
  * prs_slab.cuh — slab (multi-GPU) engine: the fused step cut at the two points where ranks
  * exchange robots, with every count kept ON THE DEVICE (DESIGN.md "multi-GPU").
- * Included by prs_kernels.cu inside its extern "C" block.
+ * Included by prs_kernels.cu; the kernels are C++ (file-local), only the prs_slab_* / prs_ipc_* entry points are extern "C".
  *
  * A rank owns the grid rows [row_lo, row_hi).  Nothing in a step needs the host to know how many
  * robots it owns, how many left, or how long the halos are: kernels are launched for the slab's
@@ -159,6 +159,18 @@ k_fix_ties_by_gid(const uint32_t *__restrict__ hash, uint32_t *__restrict__ inde
     index[b] = slot;
   }
 }
+/* Between two sorts the table is frozen while robots move: collide looks up the stencil around a
+ * robot's CURRENT cell, and this rank only holds the rows [row_lo - halo_rows, row_hi + halo_rows).  An owned
+ * robot whose current row has left [row_lo - (halo_rows - 2), row_hi + (halo_rows - 2)) would silently miss
+ * neighbours the single-GPU run sees: flag it (sticky), the host hears about it through check(). */
+__device__ __forceinline__ void slab_drift_check(const prs_slab &s, float y) {
+  const uint32_t gy = c_prm.p.gridSize.y;
+  const uint32_t row = (uint32_t)((int)floorf((y - c_prm.p.worldOrigin.y) / c_prm.p.cellSize.y)) & (gy - 1u);
+  const uint32_t slack = s.halo_rows >= 2u ? s.halo_rows - 2u : 0u;
+  const bool below = s.has_dn && row + slack < s.row_lo;
+  const bool above = s.has_up && row >= s.row_hi + slack;
+  if (below || above) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_DRIFT);
+}
 /* packed sorted copy of the owned robots at [halo_cap, halo_cap + n); pr.w = local slot (the
  * scatter target of collide) */
 __global__ void __launch_bounds__(256) k_slab_gather(prs_slab s) {
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(256) k_slab_gather(prs_slab s) {
   if (k >= n) return;
   const uint32_t src = s.index_sorted[k];
   const float2 p = ((const float2 *)s.pos)[src];
+  slab_drift_check(s, p.y);
   ((float4 *)s.sortedPR)[s.halo_cap + k] = make_float4(p.x, p.y, s.rad[src], __uint_as_float(src));
   ((float2 *)s.sortedVel)[s.halo_cap + k] = ((const float2 *)s.vel)[src];
 }
@@ -263,7 +276,12 @@ __global__ void __launch_bounds__(256) k_slab_tickets(prs_slab s, uint32_t *__re
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  ticket[i] = atomicAdd(&cellCount[s.hash[i]], 1u);
+  /* a robot that could not be sent away (migration buffer full / left the world: error bits are set already)
+   * keeps a key outside the owned rows — it must not touch counters or slots that belong to nobody */
+  const uint32_t h = s.hash[i];
+  const uint32_t row = h / c_prm.p.gridSize.x;
+  if (row < s.row_lo || row >= s.row_hi) { ticket[i] = 0xffffffffu; return; }
+  ticket[i] = atomicAdd(&cellCount[h], 1u);
 }
 __global__ void __launch_bounds__(256)
 k_slab_scatter(prs_slab s, const uint32_t *__restrict__ ticket, uint32_t *__restrict__ index_by_slot) {
@@ -271,6 +289,7 @@ k_slab_scatter(prs_slab s, const uint32_t *__restrict__ ticket, uint32_t *__rest
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t h = s.hash[i];
+  if (ticket[i] == 0xffffffffu) return; /* stranded robot, see k_slab_tickets */
   const uint32_t slot = __ldg(s.cellStart + h) + ticket[i]; /* absolute slot of [halo | owned | halo] */
   s.hash_cat[slot] = h;
   index_by_slot[slot - s.halo_cap] = i;
@@ -342,6 +361,8 @@ __global__ void __launch_bounds__(256) k_slab_halo_table(prs_slab s) {
 /* -------------------------------------------------------------------------------------------- */
 /* C entry points                                                                                 */
 /* -------------------------------------------------------------------------------------------- */
+extern "C" {
+
 static uint32_t slab_log2_gx() {
   uint32_t b = 0;
   while ((1u << b) < g_prs.h_prm.p.gridSize.x) b++;
@@ -548,3 +569,5 @@ void prs_slab_wait(const prs_slab *s, const unsigned *local_flag_dn, const unsig
   StageScope t(PRS_STAGE_EXCHANGE);
   PRS_LAUNCH(k_slab_wait, 1, 32, 0, local_flag_dn, local_flag_up, seq, s->counts);
 }
+
+}  // extern "C"

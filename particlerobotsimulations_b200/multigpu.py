@@ -430,6 +430,31 @@ class SlabSim:
         be.collide(float(dt))
         self.time = np.float32(time + np.float32(dt))
 
+    # ---- steps with the state held by the HOST (what bench.py's e2e measures at N > 1) -------------------
+    def time_host_steps(self, dt, sort_interval, steps):
+        """`steps` steps in which this rank's pos / vel / rad come from pinned host memory before the step and go back
+        to it after the step; returns the wall seconds of the slowest rank (barrier on both sides)"""
+        import time as _time
+        n_own = self.n
+        h = {k: torch.empty((n_own,) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in
+             (("pos", self.s.pos), ("vel", self.s.vel), ("rad", self.s.rad))}
+        for k, v in h.items():
+            v.copy_(getattr(self.s, k)[:n_own])
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        t0 = _time.perf_counter()
+        for _ in range(steps):
+            for k, v in h.items():
+                getattr(self.s, k)[:n_own].copy_(v, non_blocking=True)
+            self.step(dt, sort_interval)
+            for k, v in h.items():
+                v.copy_(getattr(self.s, k)[:n_own], non_blocking=True)
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        t = torch.tensor([_time.perf_counter() - t0], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
     # ---- assembling global arrays (tests, observables) -------------------------------------------------
     def gather_global(self, n_total):
         """(pos, vel, rad, phase) of the whole swarm in global-id order on every rank (small swarms / tests)"""
@@ -470,134 +495,57 @@ def make_hex_slab(params, opt, geom, backend_factory, rank, world, device, seed,
 
 
 # --------------------------------------------------------------------------------------------------
-def bench_slabs(args, rank, world, local_rank):
-    """bench.py --gpus N (N > 1): 2^26 robots (or --robots-log2) slab-decomposed over the ranks."""
-    import json
-    import os
-    import sys
-    import particlerobotsimulations_b200 as prs
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import bench
+# decomposition self-check: a small swarm with migrations on the live ranks against the single-GPU path
+SELFCHECK = dict(nx=256, ny=192, pitch=0.17, steps=40, dead=150, light=(-30.0, 0.0), seed=5555)
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
-    log2n = args.robots_log2 or 26
-    p, o, geom = bench.swarm_config(prs, log2n)
+
+def selfcheck_config(cfg_path):
+    """the 49 152-robot swarm of tests/test_multigpu_gpu.py: example.cfg physics in the reference's +-64 world,
+    150 dead robots drawn on step 0, a velocity field that drives robots across the slab boundaries"""
+    p, o = prs.load_cfg(cfg_path)
+    p.nCells = SELFCHECK["nx"] * SELFCHECK["ny"]
+    p.nDead = SELFCHECK["dead"]
+    p.light_x, p.light_y = SELFCHECK["light"]
+    return p, o, dict(nx=SELFCHECK["nx"], ny=SELFCHECK["ny"], pitch=SELFCHECK["pitch"], half=64.0)
+
+
+def selfcheck_velocity(gid):
+    v = np.zeros((len(gid), 2), np.float32)
+    v[:, 1] = (1.5 * np.sin(0.37 * np.asarray(gid).astype(np.float64))).astype(np.float32)
+    return v
+
+
+def selfcheck_vs_single_gpu(cfg_path, rank, world, device, exchange="p2p", steps=None, group=None):
+    """Runs the self-check swarm on the `world` live ranks (slab engine) and on rank 0 alone (fused single-GPU path)
+    and compares positions, velocities, radii and phases bit for bit.  Rank 0 returns
+    {"bit_equal", "robots", "steps", "migrated", "halo_robots"}; the other ranks return None.  Every rank must call it."""
+    steps = steps or SELFCHECK["steps"]
+    p, o, geom = selfcheck_config(cfg_path)
     n_total = int(p.nCells)
-    sim = make_hex_slab(p, o, geom, CudaBackend, rank, world, dev, bench.SEED, bench.JITTER_FRAC * p.max_radius,
-                        exchange=args.exchange)
-    lib = prs.lib()
-    sort_interval = o.timestep if args.sort_interval is None else args.sort_interval
-    stream = torch.cuda.current_stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sampler = bench.ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(args.warmup):
-        sim.step(o.timestep, sort_interval)
-    torch.cuda.synchronize()
-    dist.barrier()
-    sampler.mark()
-    lib.prs_launch_count(1)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    for a, b in ev:
-        flush.fill_(1)
-        a.record(stream)
-        sim.step(o.timestep, sort_interval)
-        b.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    sampler.mark()
-    launches = int(lib.prs_launch_count(0))
-    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    jitter = 0.01 * p.max_radius
+    sim = make_hex_slab(p, o, geom, CudaBackend, rank, world, device, SELFCHECK["seed"], jitter, group=group, exchange=exchange)
+    n0 = sim.n
+    sim.s.vel[:n0] = torch.from_numpy(selfcheck_velocity(sim.s.gid[:n0].cpu().numpy())).to(device)
+    for _ in range(steps):
+        sim.step(o.timestep, o.timestep)
     sim.check()
-    st = sim.stats
-    n_own = sim.n
-    own = torch.tensor([n_own, st["migrated"], st["halo"]], dtype=torch.int64, device=dev)
-    owns = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(owns, own)
-
-    # ---- per-stage event timing on this rank (kernels only; the NCCL transfers sit between the stages) ----
-    lib.prs_stage_timing(1)
-    for _ in range(min(args.steps, 10)):
-        flush.fill_(1)
-        sim.step(o.timestep, sort_interval)
-    ms = (C.c_float * 6)()
-    cnt = (C.c_uint * 6)()
-    lib.prs_stage_times(ms, cnt)
-    lib.prs_stage_timing(0)
-    clocks = sampler.stop()
-    per_bytes, b_alg, passes = bench.algorithmic_bytes(p, sort_interval <= o.timestep)
-    peak, peak_src = bench.measured_peak()
-    stages = {}
-    for i, name in enumerate(bench.STAGES):
-        if cnt[i]:
-            per_step_us = 1e3 * ms[i] / min(args.steps, 10)
-            gbs = per_bytes[name] * n_own / (per_step_us * 1e-6) / 1e9 if per_bytes[name] else None
-            stages[name] = {"us_per_step": per_step_us, "alg_bytes_per_robot": per_bytes[name], "achieved_GBps": gbs,
-                            "frac_of_hbm_peak": (gbs / peak) if gbs else None}
-
-    # ---- e2e: every rank's pos/vel/rad come from pinned host memory and go back to it every step ----
-    h = {k: torch.empty((n_own,) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in
-         (("pos", sim.s.pos), ("vel", sim.s.vel), ("rad", sim.s.rad))}
-    for k, v in h.items():
-        v.copy_(getattr(sim.s, k)[:n_own])
-    e2e_steps = max(3, min(args.steps, 20))
-    torch.cuda.synchronize()
-    dist.barrier()
-    import time as _time
-    t0 = _time.perf_counter()
-    for _ in range(e2e_steps):
-        for k, v in h.items():
-            getattr(sim.s, k)[:n_own].copy_(v, non_blocking=True)
-        sim.step(o.timestep, sort_interval)
-        for k, v in h.items():
-            v.copy_(getattr(sim.s, k)[:n_own], non_blocking=True)
-        torch.cuda.synchronize()
-    dist.barrier()
-    e2e_s = torch.tensor([_time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    finite = torch.tensor([int(torch.isfinite(sim.s.pos[:n_own]).all())], device=dev)
-    dist.all_reduce(finite, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        value = n_total * args.steps / (total_ms_max * 1e-3)
-        peak, peak_src = bench.measured_peak()
-        per_bytes, b_alg, passes = bench.algorithmic_bytes(p, sort_interval <= o.timestep)
-        per_rank = [[int(v) for v in x.tolist()] for x in owns]
-        steps_run = args.steps + args.warmup
-        line = {
-            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": bench.workload_text(geom, n_total), "decomposition": f"{world} slabs of grid rows",
-                       "sort_interval": "timestep (sort every step)", "collide_mode": "exact",
-                       "l2": "flushed between timed steps (256 MiB write)", "halo_rows": HALO_ROWS,
-                       "exchange": "peer-to-peer stores into the neighbour's mailbox (CUDA IPC over NVLink)" if sim.exchange == "p2p"
-                                   else "NCCL send/recv of fixed-size buffers"},
-            "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 20 * n_total,
-                    "d2h_bytes_per_step": 20 * n_total, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "what": "per rank: pos/vel/rad of the owned robots from pinned host -> device, SlabSim.step, device -> pinned host"},
-            "gpu_launches": launches, "clocks": clocks,
-            "roofline": ({"bound": "hbm", "kernel": "collide (rank 0)", "achieved": stages["collide"]["achieved_GBps"], "peak": peak,
-                          "unit": "GB/s", "frac": stages["collide"]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
-                          "note": "collide is FP32/MUFU-issue-bound, not HBM-bound; see roofline_step"} if "collide" in stages else None),
-            "stages_rank0": stages, "cpu_baseline": None,
-            "roofline_step": {"bound": "hbm", "alg_bytes_per_particle_step": b_alg, "radix_passes": passes,
-                              "achieved": b_alg * value / 1e9, "peak": peak * world, "unit": "GB/s",
-                              "frac": b_alg * value / 1e9 / (peak * world), "peak_source": peak_src + f" x {world} GPUs"},
-            "slabs": {"robots_per_rank": [x[0] for x in per_rank],
-                      "migrated_per_step_per_rank": [x[1] / steps_run for x in per_rank],
-                      "halo_robots_per_step_per_rank": [x[2] / steps_run for x in per_rank]},
-            "state_finite": bool(finite.item()),
-        }
-        print(json.dumps(line))
+    got = sim.gather_global(n_total)
+    st = torch.tensor([sim.stats["migrated"], sim.stats["halo"]], dtype=torch.int64, device=device)
+    dist.all_reduce(st, op=dist.ReduceOp.SUM, group=group)
     sim.close()
-    dist.barrier()
-    dist.destroy_process_group()
+    out = None
+    if rank == 0:
+        one = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
+        one.srand(p.seed)                       # main.cpp:929 — the dead draw continues this stream
+        one.init_hex(geom["nx"], geom["ny"], geom["pitch"], jitter, SELFCHECK["seed"])
+        one.set(prs.VELOCITY, selfcheck_velocity(np.arange(n_total)))
+        for _ in range(steps):
+            one.update(o.timestep, o.timestep)
+        same = all(np.array_equal(got[k].view(np.uint32), one.get(w).view(np.uint32))
+                   for k, w in (("pos", prs.POSITION), ("vel", prs.VELOCITY), ("rad", prs.RADII), ("phase", prs.PHASE)))
+        one.close()
+        out = {"bit_equal": bool(same and (got["owner"] >= 0).all()), "robots": n_total, "steps": steps,
+               "migrated": int(st[0].item()), "halo_robots": int(st[1].item()), "ranks": world,
+               "what": "slab engine on the live ranks vs the fused single-GPU path on rank 0: pos, vel, rad, phase bitwise"}
+    dist.barrier(group=group)
+    return out

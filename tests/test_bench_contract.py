@@ -37,3 +37,48 @@ def test_native_arm_fails_loudly_without_a_gpu():
                         "--no-ref-cuda"], cwd=util.ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode != 0                      # no CPU fallback: the product path needs the CUDA device
     assert not [l for l in r.stdout.splitlines() if l.startswith('{"metric"')]
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """the CPU arm builds its parameters with oracle/params.py: libparticlebot_b200.so must not be loaded by it"""
+    code = ("import sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--robots-log2', '12']\n"
+            "import bench; bench.main()\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libprs_oracle' in maps\n"
+            "assert 'libparticlebot_b200' not in maps, 'product library mapped by the reference arm'\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=util.ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_oracle_params_restatement_equals_the_product_parser():
+    """oracle/params.py (pure Python, used by the reference arm) against prs_config.cpp on the shipped cfgs without
+    obstacle lists, field by field, plus the synthetic worlds of bench.swarm_config"""
+    import ctypes as C
+    import particlerobotsimulations_b200 as prs
+    from oracle import params as op
+    import bench
+    skip = {"x1obs", "x2obs", "y1obs", "y2obs", "x_cir_obs", "y_cir_obs", "r_cir_obs", "_pad0", "seed"}
+
+    def same(a, b, seed_too):
+        for name, typ in prs.SimParams._fields_:
+            if name in skip and not (name == "seed" and seed_too):
+                continue
+            va, vb = getattr(a, name), getattr(b, name)
+            if hasattr(va, "x"):
+                assert (va.x, va.y) == (vb.x, vb.y), name
+            else:
+                assert va == vb, (name, va, vb)
+
+    pa, _ = op.defaults()
+    pb, ob_ = prs.default_params()
+    same(pa, pb, False)          # the default seed is time(NULL) in the reference
+    for name in ("example", "example_dead_cells", "example_object_transport"):
+        pa, ra = op.load_cfg(os.path.join(util.EXAMPLES, name + ".cfg"))
+        pb, rb = util.cfg(name)
+        same(pa, pb, True)
+        assert abs(ra["timestep"] - rb.timestep) == 0 and ra["sort_interval"] == rb.sort_interval
+    for log2n in (14, 20, 26):
+        pa, oa, ga = bench.swarm_config(None, log2n)
+        pb, ob2, gb = bench.swarm_config(prs, log2n)
+        same(pa, pb, True)
+        assert ga == gb and oa.timestep == ob2.timestep

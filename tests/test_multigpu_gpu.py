@@ -14,21 +14,16 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 
-NX, NY, PITCH, STEPS = 256, 192, 0.17, 60
+NX, NY, PITCH, STEPS = multigpu.SELFCHECK["nx"], multigpu.SELFCHECK["ny"], multigpu.SELFCHECK["pitch"], 60
 
 
 def _config():
-    p, o = util.cfg("example")
-    p.nCells = NX * NY
-    p.nDead = 150                    # dead-cell draw on step 0 (every rank draws the same global ids)
-    p.light_x, p.light_y = -30.0, 0.0
-    return p, o, dict(nx=NX, ny=NY, pitch=PITCH, half=64.0)
+    """the self-check swarm of multigpu.selfcheck_vs_single_gpu (bench.py runs the same check on its live ranks):
+    150 dead robots drawn on step 0 (every rank draws the same global ids), velocities that make robots migrate"""
+    return multigpu.selfcheck_config(os.path.join(util.EXAMPLES, "example.cfg"))
 
 
-def _initial_velocity(gid):
-    v = np.zeros((len(gid), 2), np.float32)
-    v[:, 1] = (1.5 * np.sin(0.37 * gid.astype(np.float64))).astype(np.float32)
-    return v
+_initial_velocity = multigpu.selfcheck_velocity
 
 
 def _worker(rank, world, port, out_path, bin_mode, exchange):

@@ -106,6 +106,10 @@ def test_sort_bit_exact_and_stable(n, bits):
     L.prs_sort_pairs(d_k.ptr, d_v.ptr, o_k.ptr, o_v.ptr, n, bits)
     assert np.array_equal(o_k.get(), keys[order]) and np.array_equal(o_v.get(), vals[order])
     assert np.array_equal(d_k.get(), keys)     # out-of-place call leaves the input alone
+    # in place with the caller's key width (a single radix pass when bits <= 8 must not scatter into its own input)
+    a_k, a_v = Dev(keys), Dev(vals)
+    L.prs_sort_pairs(a_k.ptr, a_v.ptr, a_k.ptr, a_v.ptr, n, bits)
+    assert np.array_equal(a_k.get(), keys[order]) and np.array_equal(a_v.get(), vals[order])
     # in place through the reference's entry point (key width from setParameters: numCells = 2^18)
     if bits <= 18:
         p, _ = util.cfg("example")
@@ -191,8 +195,7 @@ def _collide_inputs(name, steps):
 @pytest.mark.parametrize("name,steps", [("example", 0), ("example", 150), ("example_dead_cells", 120),
                                         ("example_obstacle", 130), ("example_gap", 110),
                                         ("example_object_transport", 140)])
-@pytest.mark.parametrize("mode", [0, 1])
-def test_collide_single_call(name, steps, mode):
+def test_collide_single_call(name, steps):
     p, o, s = _collide_inputs(name, steps)
     n = p.nCells
     dt = o.timestep
@@ -225,11 +228,7 @@ def test_collide_single_call(name, steps, mode):
         return d[0].get(), d[1].get(), d[2].get()
 
     L = prs.lib()
-    L.prs_set_collide_mode(mode)
-    try:
-        v, fa, fr = run(L)
-    finally:
-        L.prs_set_collide_mode(0)
+    v, fa, fr = run(L)
     vs = max(float(np.abs(v_o).max()), 1e-3)
     assert util.rel_err(v, v_o, vs) < TOL_ORACLE
     assert util.rel_err(fr, fr_o, max(float(fr_o.max()), 1.0)) < TOL_ORACLE
@@ -239,10 +238,10 @@ def test_collide_single_call(name, steps, mode):
         assert util.rel_err(v, v_r, vs) < TOL_REF
         assert util.rel_err(fr, fr_r, max(float(fr_r.max()), 1.0)) < TOL_REF
         assert util.rel_err(fa, fa_r, max(float(fa_r.max()), 1.0)) < TOL_REF
-        if mode == 0:   # the exact variant pins the reference build's operation sequence: identical bits
-            assert np.array_equal(v.view(np.uint32), v_r.view(np.uint32))
-            assert np.array_equal(fa.view(np.uint32), fa_r.view(np.uint32))
-            assert np.array_equal(fr.view(np.uint32), fr_r.view(np.uint32))
+        # the kernel pins the reference build's operation sequence: identical bits
+        assert np.array_equal(v.view(np.uint32), v_r.view(np.uint32))
+        assert np.array_equal(fa.view(np.uint32), fa_r.view(np.uint32))
+        assert np.array_equal(fr.view(np.uint32), fr_r.view(np.uint32))
 
 
 def test_collide_wraparound_stencil_uses_cell_path():
@@ -413,9 +412,7 @@ def test_shadow_phase_modes():
 # --------------------------------------------------------------------------------------------
 # trajectories
 # --------------------------------------------------------------------------------------------
-def _run(params, opt, backend, steps, ext=None, sort_interval=None, collide_mode=0, record_every=10):
-    L = prs.lib()
-    L.prs_set_collide_mode(collide_mode)
+def _run(params, opt, backend, steps, ext=None, sort_interval=None, record_every=10):
     sim = prs.Simulation(params, 64.0, backend, ext)
     sim.srand(params.seed)
     sim.reset()
@@ -428,7 +425,6 @@ def _run(params, opt, backend, steps, ext=None, sort_interval=None, collide_mode
                               hash=sim.get(prs.HASH), index=sim.get(prs.INDEX), cs=sim.get(prs.CELLSTART),
                               ce=sim.get(prs.CELLEND), dead=sim.get(prs.DEAD), phase=sim.get(prs.PHASE)))
     sim.close()
-    L.prs_set_collide_mode(0)
     return snaps
 
 
@@ -457,8 +453,6 @@ def test_100_step_trajectory_vs_reference_kernels(name, sort_every_step):
     for bname, kind, _ in _backends():
         got = _run(p, o, kind, 100, None, si)
         _compare(got, ref, TOL_REF)
-    fast = _run(p, o, prs.BACKEND_FUSED, 100, None, si, collide_mode=1)
-    _compare(fast, ref, TOL_REF)
 
 
 @pytest.mark.parametrize("name", util.CFGS)
@@ -606,6 +600,71 @@ def test_s1_full_size_fused_equals_percall_and_invariants():
     empty[occ] = False
     assert np.all(cs[empty] == 0xFFFFFFFF)
     assert np.all(np.isfinite(a["pos"])) and float(np.abs(a["vel"]).max()) > 0
+
+
+def _headline_vs_oracle(log2n, cut=None, steps=10):
+    """bench.py's own workload (bench.swarm_config: parametric world wall, 2048^2 / 8192^2 grids) through the fused
+    path against OracleSim(p, world_half) with every host thread: hashes / index / occupied-cell tables bit-exact
+    after every compared step, floats at the bars of test_100_step_trajectory_vs_oracle's first 10 steps."""
+    import bench
+    p, o, geom = bench.swarm_config(prs, log2n)
+    if cut is not None:            # a cut of the lattice in the SAME world and grid (the oracle finishes in seconds)
+        geom["nx"], geom["ny"] = cut
+        p.nCells = cut[0] * cut[1]
+    n = int(p.nCells)
+    pos0 = bench.hex_positions(p, geom)
+    if cut is not None:            # push the block off-centre: rows far from the origin, hashes above 2^25
+        pos0 = (pos0 + np.float32([0.37 * geom["half"], -0.61 * geom["half"]])).astype(np.float32)
+    sim = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
+    sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], bench.JITTER_FRAC * p.max_radius, bench.SEED)
+    if cut is None:
+        assert np.array_equal(sim.get(prs.POSITION).view(np.uint32), pos0.view(np.uint32))   # same generator on both sides
+    else:
+        sim.set(prs.POSITION, pos0)
+    O = ob.lib()
+    O.prso_set_threads(O.prso_get_max_threads())
+    ora = ob.OracleSim(p, geom["half"])
+    ora.view("pos")[:] = pos0
+    ora.view("rad")[:] = p.min_radius
+    try:
+        for k in range(steps):
+            sim.update(o.timestep, o.timestep)
+            ora.update(o.timestep, o.timestep)
+            if k == 3:
+                sim.sync()      # the density report arrives: cell binning from here on
+            if k in (0, 4, steps - 1):
+                h, idx = sim.get(prs.HASH), sim.get(prs.INDEX)
+                assert np.array_equal(h, ora.get("hash")), k
+                assert np.array_equal(idx, ora.get("index")), k
+                occ = np.unique(h)
+                assert np.array_equal(sim.get(prs.CELLSTART)[occ], ora.get("cellStart")[occ]), k
+                assert np.array_equal(sim.get(prs.CELLEND)[occ], ora.get("cellEnd")[occ]), k
+                vs = max(float(np.abs(ora.get("vel")).max()), 1e-3)
+                assert util.rel_err(sim.get(prs.POSITION), ora.get("pos"), 1.0) < 2e-6, k
+                assert util.rel_err(sim.get(prs.VELOCITY), ora.get("vel"), vs) < 1e-3, k
+                assert util.rel_err(sim.get(prs.RADII), ora.get("rad"), 0.1) < 1e-3, k
+        assert prs.lib().prs_bin_active() == 1
+        assert float(np.abs(sim.get(prs.VELOCITY)).max()) > 0
+    finally:
+        O.prso_set_threads(1)
+        ora.close()
+        sim.close()
+    return geom
+
+
+def test_s1_headline_config_vs_oracle():
+    """BASELINE.json's S1 exactly as bench.py builds it (2^20 robots, world +-128 — the parametric wall of integrate,
+    reference kernel_impl.cuh:53-103 hard-codes 64 — and the 2048^2 grid of calcHash, :446-465), 10 steps against the
+    CPU oracle."""
+    geom = _headline_vs_oracle(20)
+    assert geom["half"] == 128.0 and geom["grid"] == 2048
+
+
+def test_s2_grid_cut_vs_oracle():
+    """S2's world (+-768) and 8192^2 grid with a 2^22-robot cut of its lattice placed off-centre, so that 26-bit cell
+    keys and the far wall geometry are compared with the oracle at a size it finishes in seconds."""
+    geom = _headline_vs_oracle(26, cut=(2048, 2048))
+    assert geom["half"] == 768.0 and geom["grid"] == 8192
 
 
 def _hex_run(mode, steps, scramble=False, crowd=0, drift=0.0):
