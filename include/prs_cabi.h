@@ -96,10 +96,16 @@ float prs_get_world_half_extent(void);
 /* collide runs one WARP per robot for swarms of up to max_robots (latency-bound sizes; default 16384,
  * 0 = always one thread per robot).  Same bits either way. */
 void prs_set_collide_warp_max(unsigned max_robots);
-/* thread-per-robot collide on the packed sorted layout: 1 = each block stages the five stencil-row windows
- * of its 256 slots in shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) and reads neighbours
- * from there; 0 = neighbours through L1/L2.  Same bits either way. */
+/* 1 = on sort steps of plain swarms (no transported object, absForce_a not wanted) collide runs as k_collide_patch
+ * (csrc/prs_collide_patch.cuh): a block owns a patch of 16 x 8 cells, stages it and its 2-cell halo in shared memory
+ * with 1-D TMA bulk copies (cp.async.bulk + mbarrier) and evaluates every pair of two patch robots ONCE, parking the
+ * force for the partner so that each robot still adds its forces in the reference's order.  Same bits either way;
+ * default 0 (measured slower than the thread-per-robot kernel, profiles/r2_collide_patch.md). */
 void prs_set_collide_tile(int on);
+/* height of a patch in cells (1..8, default 8; the width is 16): smaller for denser swarms so that a patch's robots fit one block */
+void prs_set_patch_rows(unsigned rows);
+/* tuning aid: counts {patches taken, patches handed to the per-robot slow lane, patches redone} while on; out (host, 3 words, may be NULL) */
+void prs_patch_stats(int on, unsigned *out);
 int prs_get_collide_tile(void);
 /* 1 = the kernels of prs_fused_step are launched with programmatic dependent launch (each kernel's blocks
  * become resident while the previous kernel drains; griddepcontrol.wait orders the data).  Same results. */

@@ -26,8 +26,15 @@
  * late, see prs_fused_step).
  */
 #pragma once
+#include "prs_patchlist.cuh"
 
 namespace prs_bin {
+
+/* optional work list for k_collide_patch: patches of PATCH_W x PH cells that hold robots */
+struct PatchListArgs {
+  uint32_t *epoch_of = nullptr, *list = nullptr, *count = nullptr;
+  uint32_t epoch = 0, log2_gx = 0, PH = 0;
+};
 
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
@@ -124,7 +131,8 @@ __global__ void __launch_bounds__(1024) k_cell_scan_tiles(uint32_t *scratch, uin
 template <bool SELF_PREFIX>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
-             uint32_t *scratch, uint32_t slot_offset, uint32_t *marks = nullptr, uint32_t *prev_marks = nullptr) {
+             uint32_t *scratch, uint32_t slot_offset, uint32_t *marks = nullptr, uint32_t *prev_marks = nullptr,
+             const PatchListArgs pl = PatchListArgs()) {
   prs::pdl_sync();
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,6 +176,8 @@ k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart,
   uint32_t sum = 0, mx = 0;
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; i++) { sum += cnt[i]; mx = max(mx, cnt[i]); }
+  /* my 8 cells are half a patch row: the patch holds robots if they do */
+  if (pl.list) prs::patch_mark(sum != 0u, c0, pl.log2_gx, pl.PH, pl.epoch_of, pl.list, pl.count, pl.epoch);
   /* fullest cell (guard of the in-cell ranking): one atomic per warp at most, none once the running
    * maximum is reached — same-address traffic serialises in one L2 slice */
   mx = __reduce_max_sync(0xffffffffu, mx);

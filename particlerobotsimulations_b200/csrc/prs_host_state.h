@@ -25,6 +25,17 @@ struct PrsBinState {
   unsigned report_generation = 0;
 };
 
+/* work list of k_collide_patch (prs_collide_patch.cuh): patches that hold robots, rebuilt at every sort */
+struct PrsPatchState {
+  uint32_t *epoch_of = nullptr, *list = nullptr, *count = nullptr; /* device: last epoch per patch, list, counter */
+  size_t cap_cells = 0;
+  unsigned epoch = 0;
+  unsigned rows = 8;             /* patch height PH in cells */
+  int num_sms = 0;
+  bool smem_opt_in = false;
+  uint32_t *stats = nullptr, *stats_buf = nullptr; /* tuning aid, see prs_patch_stats */
+};
+
 /* which cell table the fused step built last (steps without a sort reuse it: same keys, same table) */
 struct PrsTableState {
   const void *cellStart = nullptr, *hash = nullptr;
@@ -44,11 +55,13 @@ struct PrsHostState {
   cudaEvent_t k1_event = nullptr;
   bool k1_event_armed = false;
   int pdl = 1;                        /* 1: the fused step's kernels are launched with programmatic dependent launch */
-  int collide_tile = 0;               /* 1: thread-per-robot collide stages its neighbours in shared memory by TMA */
+  int collide_tile = 0;               /* 1: sort steps of plain large swarms use k_collide_patch (TMA-staged patches, pairs evaluated
+                                         once; bit-equal, measured slower: profiles/r2_collide_patch.md) */
   unsigned collide_warp_max = 16384;  /* swarms up to this size use the warp-per-robot collide kernel */
   prs_sort::Workspace sort_ws;
   PrsBinState bin;
   PrsTableState table;
+  PrsPatchState patch;
   bool slab_sorted_onesweep = false;
   bool slab_binned = false, slab_table_fresh = false; /* slab engine: route of the last sort / its table not consumed yet */
   int sort_threads = 0;               /* tile shape of k_onesweep: 512 / 1024 threads, 0 = by size */

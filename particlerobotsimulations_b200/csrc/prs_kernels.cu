@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
 #include <math.h>
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,6 +28,7 @@
 #include "prs_host_state.h"
 
 #include "prs_collide.cuh"
+#include "prs_collide_patch.cuh"
 
 using namespace prs;
 
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256)
 k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, float4 *__restrict__ sortedPR,
                  float2 *__restrict__ sortedVel, const uint32_t *__restrict__ hash, const uint32_t *__restrict__ index,
                  const float2 *__restrict__ pos, const float2 *__restrict__ vel, const float *__restrict__ rad,
-                 uint32_t n) {
+                 uint32_t n, const prs_bin::PatchListArgs pl = prs_bin::PatchListArgs()) {
   prs::pdl_sync();
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -158,6 +160,7 @@ k_reorder_packed(uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEn
     cellStart[h] = k;
     if (k > 0) cellEnd[hp] = k;
   }
+  if (pl.list) prs::patch_mark(k == 0 || h != hp, h, pl.log2_gx, pl.PH, pl.epoch_of, pl.list, pl.count, pl.epoch);
   if (k == n - 1) cellEnd[h] = k + 1;
   sortedPR[k] = make_float4(p.x, p.y, r, __uint_as_float(src));
   sortedVel[k] = v;
@@ -880,6 +883,22 @@ float prs_get_world_half_extent(void) { return g_prs.world_half; }
 /* swarms of up to max_robots use the warp-per-robot collide kernel (0 = never); default 16384 */
 void prs_set_collide_warp_max(unsigned max_robots) { g_prs.collide_warp_max = max_robots; }
 void prs_set_collide_tile(int on) { g_prs.collide_tile = on ? 1 : 0; }
+void prs_set_patch_rows(unsigned rows) { g_prs.patch.rows = rows < 1 ? 1 : (rows > (unsigned)prs::PATCH_HMAX ? (unsigned)prs::PATCH_HMAX : rows); }
+/* tuning aid: on != 0 starts counting {patches taken by the patch kernel, patches handed to the per-robot slow lane,
+ * patches redone because a pair left the admitted operand ranges}; returns the counts so far in out[3] and clears them */
+void prs_patch_stats(int on, unsigned *out) {
+  PrsPatchState &T = g_prs.patch;
+  if (!T.stats_buf) {
+    PRS_CUDA(cudaMalloc(&T.stats_buf, 4 * 4));
+    PRS_CUDA(cudaMemsetAsync(T.stats_buf, 0, 4 * 4, g_prs.stream));
+  }
+  if (out) {
+    PRS_CUDA(cudaMemcpyAsync(out, T.stats_buf, 3 * 4, cudaMemcpyDeviceToHost, g_prs.stream));
+    PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+  }
+  PRS_CUDA(cudaMemsetAsync(T.stats_buf, 0, 4 * 4, g_prs.stream));
+  T.stats = on ? T.stats_buf : nullptr;
+}
 void prs_set_pdl(int on) { g_prs.pdl = on ? 1 : 0; }
 
 /* ---- host-buffer step (Particlebot::updateHost): asynchronous copies around prs_fused_step ----
@@ -1012,6 +1031,72 @@ void prs_bin_invalidate(void) {
 void prs_bin_set_mode(int mode) { g_prs.bin.mode = mode; } /* 0 auto (default), 1 never (always onesweep), 2 always */
 int prs_bin_active(void) { return g_prs.bin.admitted ? 1 : 0; }
 
+/* ---- work list + launch of k_collide_patch (prs_collide_patch.cuh) ---- */
+static bool patch_eligible(uint32_t n, bool need_fa, bool fresh_table) {
+  const SimParams &p = g_prs.h_prm.p;
+  const unsigned gx = p.gridSize.x, gy = p.gridSize.y;
+  return g_prs.collide_tile && fresh_table && p.nDead != -1 && !need_fa && n > g_prs.collide_warp_max && gx >= 32 && gy >= 16 &&
+         (gx & (gx - 1)) == 0 && (gy & (gy - 1)) == 0 && gx * gy == p.numCells;
+}
+/* new epoch: the table kernels of this step append the patches that hold robots */
+static prs_bin::PatchListArgs patch_begin_step() {
+  PrsPatchState &T = g_prs.patch;
+  const SimParams &p = g_prs.h_prm.p;
+  const size_t need = (size_t)p.numCells / prs::PATCH_W; /* patches of one row at most */
+  if (T.cap_cells < need) {
+    if (T.epoch_of) { PRS_CUDA(cudaFree(T.epoch_of)); PRS_CUDA(cudaFree(T.list)); }
+    PRS_CUDA(cudaMalloc(&T.epoch_of, need * 4));
+    PRS_CUDA(cudaMalloc(&T.list, need * 4));
+    PRS_CUDA(cudaMemsetAsync(T.epoch_of, 0, need * 4, g_prs.stream));
+    T.cap_cells = need;
+  }
+  if (!T.count) {
+    PRS_CUDA(cudaMalloc(&T.count, 2 * 4));
+    PRS_CUDA(cudaMemsetAsync(T.count, 0, 2 * 4, g_prs.stream));
+  }
+  T.epoch++;
+  if (T.epoch == 0) { /* wrapped: forget every stamp */
+    PRS_CUDA(cudaMemsetAsync(T.epoch_of, 0, T.cap_cells * 4, g_prs.stream));
+    T.epoch = 1;
+  }
+  prs_bin::PatchListArgs a;
+  a.epoch_of = T.epoch_of; a.list = T.list; a.count = T.count + (T.epoch & 1u); a.epoch = T.epoch;
+  a.PH = T.rows;
+  while ((1u << a.log2_gx) < p.gridSize.x) a.log2_gx++;
+  return a;
+}
+static void launch_collide_patch(float2 *newVel, float *fr, const float4 *pr, const float2 *svel, const uint32_t *cellStart,
+                                 const uint32_t *cellEnd, float dt) {
+  PrsPatchState &T = g_prs.patch;
+  if (!T.smem_opt_in) {
+    PRS_CUDA(cudaFuncSetAttribute(prs::k_collide_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(prs::PatchSmem)));
+    PRS_CUDA(cudaFuncSetAttribute(prs::k_collide_patch, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int dev = 0;
+    PRS_CUDA(cudaGetDevice(&dev));
+    PRS_CUDA(cudaDeviceGetAttribute(&T.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    T.smem_opt_in = true;
+  }
+  const SimParams &p = g_prs.h_prm.p;
+  const unsigned long long patches = (unsigned long long)(p.gridSize.x / prs::PATCH_W) * ((p.gridSize.y + T.rows - 1) / T.rows);
+  const unsigned grid = (unsigned)std::min<unsigned long long>(patches, 2ull * (unsigned)T.num_sms);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(prs::PATCH_NT);
+  cfg.dynamicSmemBytes = sizeof(prs::PatchSmem);
+  cfg.stream = g_prs.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_prs.pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const uint32_t *count = T.count + (T.epoch & 1u);
+  uint32_t *next = T.count + ((T.epoch + 1u) & 1u);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, prs::k_collide_patch, newVel, fr, pr, svel, cellStart, cellEnd,
+                                           (const uint32_t *)T.list, count, next, (uint32_t)T.rows, dt, T.stats);
+  g_prs.launches++;
+  if (e != cudaSuccess) prs_fail("k_collide_patch", e, __FILE__, __LINE__);
+}
+
 static inline void k1_done() {
   if (g_prs.k1_event_armed) PRS_CUDA(cudaEventRecord(g_prs.k1_event, g_prs.stream));
 }
@@ -1028,6 +1113,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     const bool shape_ok = (unsigned long long)b->numCells <= 16ull * n && n < (1u << 30);
     binned = shape_ok && (B.mode == 2 || (B.mode == 0 && B.admitted));
   }
+  const bool patch = patch_eligible(n, need_fa, do_sort != 0) && b->sortedPR;
+  const prs_bin::PatchListArgs pl = patch ? patch_begin_step() : prs_bin::PatchListArgs();
   if (binned) {
     /* K1 + tickets -> scan (= cell table) -> scatter -> in-cell order + gather */
     bin_ensure(n, b->numCells);
@@ -1054,11 +1141,11 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch, (const uint32_t *)marks);
       if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u, marks, prev_marks);
+                       B.scratch, 0u, marks, prev_marks, pl);
       } else {
         PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u, marks, prev_marks);
+                       B.scratch, 0u, marks, prev_marks, pl);
       }
       PRS_LAUNCH_PDL(prs_bin::k_cell_scatter, div_up(n, 256), 256, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
     }
@@ -1073,7 +1160,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     {
       StageScope t(PRS_STAGE_COLLIDE);
       prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
-      prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+      if (patch) launch_collide_patch((float2 *)b->vel, b->absForce_r, in.pr, in.vel, b->cellStart, b->cellEnd, dt);
+      else prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
     }
     /* fullest cell of this sort -> pinned host memory (nobody touches the two words before the next step's
      * memset); issued after collide so that the kernels of the step stay adjacent in the stream */
@@ -1127,7 +1215,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
         B.marks_table = nullptr; /* the table is rebuilt from scratch here: the binned route's tile marks no longer describe it */
         PRS_CUDA(cudaMemsetAsync(b->cellStart, 0xff, (size_t)b->numCells * sizeof(unsigned), g_prs.stream));
         PRS_LAUNCH(k_reorder_packed, div_up(n, 256), 256, 0, b->cellStart, b->cellEnd, (float4 *)b->sortedPR,
-                   (float2 *)b->sortedVel, b->hash, b->index, (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n);
+                   (float2 *)b->sortedVel, b->hash, b->index, (const float2 *)b->pos, (const float2 *)b->vel, b->rad, n, pl);
         T.cellStart = b->cellStart; T.hash = b->hash; T.n = n; T.numCells = b->numCells; T.generation = B.generation;
       }
       if (do_sort && B.mode == 0 && !B.admitted && (unsigned long long)b->numCells <= 16ull * n) {
@@ -1141,7 +1229,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     {
       StageScope t(PRS_STAGE_COLLIDE);
       prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
-      prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+      if (patch) launch_collide_patch((float2 *)b->vel, b->absForce_r, in.pr, in.vel, b->cellStart, b->cellEnd, dt);
+      else prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
     }
     /* the 8-byte report goes out AFTER collide: a device-to-host copy queued before it would sit behind whatever
      * the copy engine is busy with (the host-buffer step downloads 12 MB right then) and hold collide back */
