@@ -10,6 +10,7 @@ from particlerobotsimulations_b200 import SimParams
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libprs_oracle.so")
 REFCUDA_PATH = os.path.join(_HERE, "_ref", "libprs_refcuda.so")
+REFHOST_PATH = os.path.join(_HERE, "_ref", "libprs_refhost.so")
 
 
 def build():
@@ -118,3 +119,61 @@ class OracleSim:
 
     def get(self, name):
         return self.view(name).copy()
+
+
+_refhost = None
+
+
+def refhost():
+    """oracle/_ref/libprs_refhost.so: the reference's own host class (particlebot.cpp) and kernels compiled verbatim,
+    OpenGL buffer objects replaced by device allocations (oracle/gl_stub).  Needs a GPU."""
+    global _refhost
+    if _refhost is None:
+        L = C.CDLL(REFHOST_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+        sig = {"prsref_identity": (C.c_char_p, []), "prsref_create": (_VP, [_PP, _U]), "prsref_destroy": (None, [_VP]),
+               "prsref_reset": (None, [_VP]), "prsref_update": (None, [_VP, _F, _F]), "prsref_time": (_F, [_VP]),
+               "prsref_get": (_I, [_VP, _I, _VP, C.c_size_t]), "prsref_set": (None, [_VP, _I, _VP, _I, _I])}
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _refhost = L
+    return _refhost
+
+
+class RefHostSim:
+    """`class Particlebot` of the REFERENCE (particlebot.cpp), driven like main.cpp does: srand(seed), construct, reset(),
+    update(dt, sort_interval) per step.  It uses the process-wide glibc rand(): one at a time."""
+
+    _GET = {"pos": (0, np.float32, 2), "vel": (1, np.float32, 2), "rad": (2, np.float32, 1), "phase": (3, np.float32, 1),
+            "dead": (5, np.int32, 1), "absForce_a": (100, np.float32, 1), "absForce_r": (101, np.float32, 1),
+            "hash": (102, np.uint32, 1), "index": (103, np.uint32, 1), "cellStart": (104, np.uint32, 0), "cellEnd": (105, np.uint32, 0)}
+
+    def __init__(self, params, seed):
+        self.L = refhost()
+        self.params = params
+        self.n = int(params.nCells)
+        self.h = self.L.prsref_create(C.byref(params), seed)
+
+    def close(self):
+        if self.h:
+            self.L.prsref_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        self.L.prsref_reset(self.h)
+
+    def update(self, dt, sort_interval):
+        self.L.prsref_update(self.h, dt, sort_interval)
+
+    @property
+    def time(self):
+        return float(self.L.prsref_time(self.h))
+
+    def get(self, name):
+        which, dt, w = self._GET[name]
+        shape = (int(self.params.numCells),) if w == 0 else ((self.n, 2) if w == 2 else (self.n,))
+        out = np.empty(shape, dt)
+        rc = self.L.prsref_get(self.h, which, out.ctypes.data, out.nbytes)
+        if rc != 0:
+            raise RuntimeError(f"prsref_get({name}) failed: {rc}")
+        return out

@@ -39,3 +39,16 @@ def built_libraries():
     if not os.path.exists(binding.LIB_PATH):
         binding.build()
     return True
+
+
+@pytest.fixture
+def collide_kernel_default():
+    """library defaults for the knobs other test modules vary per test"""
+    import particlerobotsimulations_b200 as prs
+    L = prs.lib()
+    L.prs_set_collide_warp_max(16384)
+    L.prs_set_collide_tile(0)
+    L.prs_set_pdl(1)
+    L.prs_set_fuse_gather_max(65536)
+    L.prs_bin_set_mode(0)
+    yield

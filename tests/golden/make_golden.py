@@ -1,7 +1,9 @@
 """Generates tests/golden/*.npz by running the REFERENCE's own kernels (oracle/_ref/libprs_refcuda.so:
 particlebot_cuda.cu + particlebot_kernel_impl.cuh compiled verbatim for sm_100a) on a B200, driven
-by this repo's headless Particlebot host logic in EXTERNAL-backend mode (the reference's own host
-class needs OpenGL and cannot run headless).
+by this repo's headless Particlebot host logic in EXTERNAL-backend mode.  Since round 2 the reference's
+OWN host class runs headless too (oracle/_ref/libprs_refhost.so: particlebot.cpp compiled verbatim over
+a buffer-object stand-in) and tests/test_refhost_gpu.py checks that it reproduces every file here bit for
+bit — the goldens are outputs of the reference, whichever of the two host classes drives the kernels.
 
 Run on the GPU box:   python tests/golden/make_golden.py gpurun_out/golden
 then copy the files into tests/golden/.  The reference ships no golden vectors of its own

@@ -21,6 +21,10 @@ def refcuda_available():
     return os.path.exists(ob.REFCUDA_PATH)
 
 
+def refhost_available():
+    return os.path.exists(ob.REFHOST_PATH)
+
+
 _ref = None
 
 
