@@ -239,6 +239,33 @@ void prs_ipc_close(void *p);
 void prs_slab_signal(unsigned *remote_flag_dn, unsigned *remote_flag_up, unsigned seq);
 void prs_slab_wait(const prs_slab *s, const unsigned *local_flag_dn, const unsigned *local_flag_up, unsigned seq);
 
+/* One whole step of a slab rank with the peer-to-peer exchange, orchestrated by the library (what Particlebot::update,
+ * particlebot.cpp:170-300, is for one GPU).  The caller sets the context up once — the slab, its own mailbox
+ * (prs_slab_mailbox_alloc(prs_slab_mailbox_words(..))) and the two neighbours' mailboxes mapped through CUDA IPC, NULL
+ * where there is no neighbour — and supplies the one collective the path has: allreduce_min(dev, user) must replace
+ * dev[0] (device memory, one float) by its minimum over all ranks, ordered on the library's stream; it is called on the
+ * steps where the phase gate fires (every phase_update_interval of simulated time).  overlap_exchange != 0: collide of
+ * the interior rows is launched before the wait for the neighbours' halos, the two edge bands after it.
+ * Returns the sticky error bits (PRS_SLAB_ERR_*) seen so far, at most one step late, without synchronising. */
+typedef struct {
+  prs_slab slab;
+  unsigned *mailbox, *peer_dn, *peer_up;   /* own mailbox; the lower / upper neighbour's, mapped (NULL: none) */
+  unsigned mw, hw;                         /* prs_slab_mig_words(mig_cap), prs_slab_halo_words(halo_cap) */
+  unsigned *scratch_mig[2], *scratch_halo[2]; /* local send buffers for the sides without a neighbour (mw / hw words) */
+  float *d_min_d;                          /* device, >= 1 float */
+  void (*allreduce_min)(float *dev, void *user);
+  void *user;
+  int overlap_exchange;
+  /* state, owned by the library after the first call */
+  float time;
+  int sorted_once;
+  unsigned seq_halo, seq_mig, split_fallbacks;
+  unsigned *h_err;
+} prs_slab_ctx;
+size_t prs_slab_mailbox_words(unsigned mig_cap, unsigned halo_cap);
+unsigned prs_slab_step(prs_slab_ctx *c, float dt, float sort_interval);
+void prs_slab_ctx_release(prs_slab_ctx *c);
+
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n);
 /* self-test: number of operand pairs for which the shared-reciprocal division used by collide
  * differs from __fdiv_rn (must be 0) */

@@ -81,6 +81,19 @@ class Slab(C.Structure):
         ("has_dn", C.c_int), ("has_up", C.c_int)]
 
 
+ALLREDUCE_MIN_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+
+class SlabCtx(C.Structure):
+    """Mirror of prs_slab_ctx (include/prs_cabi.h): a slab rank's whole-step context for prs_slab_step."""
+
+    _fields_ = [("slab", Slab), ("mailbox", C.c_void_p), ("peer_dn", C.c_void_p), ("peer_up", C.c_void_p),
+                ("mw", C.c_uint), ("hw", C.c_uint), ("scratch_mig", C.c_void_p * 2), ("scratch_halo", C.c_void_p * 2),
+                ("d_min_d", C.c_void_p), ("allreduce_min", ALLREDUCE_MIN_FN), ("user", C.c_void_p), ("overlap_exchange", C.c_int),
+                ("time", C.c_float), ("sorted_once", C.c_int), ("seq_halo", C.c_uint), ("seq_mig", C.c_uint),
+                ("split_fallbacks", C.c_uint), ("h_err", C.c_void_p)]
+
+
 # words of Slab.counts (PRS_SC_*) and error bits (PRS_SLAB_ERR_*)
 SC_N, SC_NLO, SC_NHI, SC_KDN, SC_KUP, SC_MIGDN, SC_MIGUP, SC_LEAVERS, SC_HOLES, SC_KEEPERS, SC_ERR, SC_STAT_MIG, SC_STAT_HALO = range(13)
 SLAB_ERRORS = {1: "more migrants than mig_cap in one step", 2: "a halo longer than halo_cap", 4: "more robots than the slab capacity",
@@ -135,6 +148,7 @@ SIGNATURES = {
     "prs_ipc_handle_size": (C.c_size_t, []), "prs_slab_mailbox_alloc": (_VP, [C.c_size_t]), "prs_slab_mailbox_free": (None, [_VP]),
     "prs_ipc_export": (None, [_VP, _VP]), "prs_ipc_open": (_VP, [_VP]), "prs_ipc_close": (None, [_VP]),
     "prs_slab_signal": (None, [_VP, _VP, _U]), "prs_slab_wait": (None, [_VP, _VP, _VP, _U]),
+    "prs_slab_mailbox_words": (C.c_size_t, [_U, _U]), "prs_slab_step": (_U, [_VP, _F, _F]), "prs_slab_ctx_release": (None, [_VP]),
     "prs_unpack_sorted": (None, [_VP, _VP, _VP, _U]), "prs_selftest_div": (C.c_ulonglong, [_VP, _VP, _U]),
     "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
     "prs_bin_invalidate": (None, []), "prs_bin_set_mode": (None, [_I]), "prs_bin_active": (_I, []),

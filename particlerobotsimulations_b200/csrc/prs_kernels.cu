@@ -297,7 +297,8 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
                          const float *__restrict__ phase, const float *__restrict__ fa, const float *__restrict__ fr,
                          const int *__restrict__ dead, uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
                          float time, float dt, int run_controller, uint32_t n, const uint32_t *__restrict__ n_dev,
-                         uint32_t *__restrict__ cellCount = nullptr, uint32_t *__restrict__ tileMark = nullptr) {
+                         uint32_t *__restrict__ cellCount = nullptr, uint32_t *__restrict__ tileMark = nullptr,
+                         uint32_t row_lo = 0u, uint32_t row_hi = 0xffffffffu, uint32_t log2_gx = 0u) {
   prs::pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
@@ -326,7 +327,13 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
     const int2 g = cell_of(p.x, p.y);
     const uint32_t h = cell_hash(g.x, g.y);
     hash[i] = h;
-    index[i] = COUNT ? atomicAdd(&cellCount[h], 1u) : i;
+    if (COUNT) {
+      /* slab ranks: a robot whose new row left [row_lo, row_hi) migrates and takes its ticket where it arrives */
+      const uint32_t row = h >> log2_gx;
+      index[i] = (row >= row_lo && row < row_hi) ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu;
+    } else {
+      index[i] = i;
+    }
     if (COUNT && tileMark) {
       /* the scan skips tiles nobody marked: the first lane of a run of equal tiles stores, into the way of its block */
       const uint32_t tile = h / prs_bin::SCAN_TILE;
@@ -1133,7 +1140,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
       PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                      b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
-                     (const uint32_t *)nullptr, B.cellCount, marks);
+                     (const uint32_t *)nullptr, B.cellCount, marks, 0u, 0xffffffffu, 0u);
       k1_done();
     }
     {
@@ -1198,7 +1205,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     StageScope t(PRS_STAGE_K1);
     PRS_LAUNCH_PDL((k_control_integrate_hash<false, false>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                    b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n,
-                   (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr);
+                   (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
     k1_done();
   }
   if (b->sortedPR) {

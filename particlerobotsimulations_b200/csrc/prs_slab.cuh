@@ -67,6 +67,7 @@ __device__ __forceinline__ void slab_move_record(const prs_slab &s, uint32_t dst
 
 /* resets the per-step counters (everything except n and the statistics) */
 __global__ void k_slab_begin_step(uint32_t *counts) {
+  prs::pdl_sync();
   const int i = threadIdx.x;
   if (i >= PRS_SC_NLO && i <= PRS_SC_KEEPERS) counts[i] = 0;
 }
@@ -75,6 +76,7 @@ __global__ void k_slab_begin_step(uint32_t *counts) {
  * and listed; `scratch[i]` = 1 marks a leaver */
 __global__ void __launch_bounds__(256) k_slab_select(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up,
                                                      uint32_t log2_gx) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(256) k_slab_select(prs_slab s, uint32_t *__res
 /* M2: with L leavers the survivors must end up in [0, n-L).  Holes = leavers below n-L, movers =
  * survivors at or above it; both lists have the same length. */
 __global__ void __launch_bounds__(256) k_slab_list_holes(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N], L = s.counts[PRS_SC_LEAVERS];
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q == 0) { /* the count words of the outgoing buffers */
@@ -106,14 +109,18 @@ __global__ void __launch_bounds__(256) k_slab_list_holes(prs_slab s, uint32_t *_
   if (!s.scratch[j]) movers[atomicAdd(&s.counts[PRS_SC_KEEPERS], 1u)] = j;
 }
 /* M3: movers fill the holes; then the arrivals are appended and n is updated */
-__global__ void __launch_bounds__(256) k_slab_fill_holes(prs_slab s) {
+__global__ void __launch_bounds__(256) k_slab_fill_holes(prs_slab s, uint32_t *__restrict__ ticket) {
+  prs::pdl_sync();
   const uint32_t H = s.counts[PRS_SC_HOLES];
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= H) return;
-  slab_move_record(s, s.lists[2 * s.mig_cap + q], s.lists[4 * s.mig_cap + q]);
+  const uint32_t dst = s.lists[2 * s.mig_cap + q], src = s.lists[4 * s.mig_cap + q];
+  slab_move_record(s, dst, src);
+  if (ticket) ticket[dst] = ticket[src]; /* the cell ticket K1 took travels with the robot */
 }
 __global__ void __launch_bounds__(256) k_slab_append(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up,
-                                                     uint32_t log2_gx) {
+                                                     uint32_t log2_gx, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ ticket) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N], L = s.counts[PRS_SC_LEAVERS];
   const uint32_t c_dn = s.has_dn ? min(recv_dn[0], s.mig_cap) : 0u, c_up = s.has_up ? min(recv_up[0], s.mig_cap) : 0u;
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,10 +129,14 @@ __global__ void __launch_bounds__(256) k_slab_append(prs_slab s, const uint32_t 
   if (dst >= s.cap) { atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_CAPACITY); return; }
   if (q < c_dn) slab_load_record(recv_dn, s.mig_cap, q, s, dst);
   else slab_load_record(recv_up, s.mig_cap, q - c_dn, s, dst);
-  const uint32_t row = s.hash[dst] >> log2_gx; /* a robot may cross one slab per sort at most */
-  if (row < s.row_lo || row >= s.row_hi) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_TWO_SLABS);
+  const uint32_t h = s.hash[dst];
+  const uint32_t row = h >> log2_gx; /* a robot may cross one slab per sort at most */
+  const bool mine = row >= s.row_lo && row < s.row_hi;
+  if (!mine) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_TWO_SLABS);
+  if (ticket) ticket[dst] = mine ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu; /* binned sort: the arrival's cell ticket */
 }
 __global__ void k_slab_commit_count(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up) {
+  prs::pdl_sync();
   const uint32_t c_dn = s.has_dn ? min(recv_dn[0], s.mig_cap) : 0u, c_up = s.has_up ? min(recv_up[0], s.mig_cap) : 0u;
   const uint32_t L = s.counts[PRS_SC_LEAVERS];
   uint32_t n = s.counts[PRS_SC_N] - L + c_dn + c_up;
@@ -144,6 +155,7 @@ __global__ void k_slab_commit_count(prs_slab s, const uint32_t *__restrict__ rec
 __global__ void __launch_bounds__(256)
 k_fix_ties_by_gid(const uint32_t *__restrict__ hash, uint32_t *__restrict__ index, const uint32_t *__restrict__ gid,
                   const uint32_t *__restrict__ n_dev) {
+  prs::pdl_sync();
   const uint32_t n = *n_dev;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -174,6 +186,7 @@ __device__ __forceinline__ void slab_drift_check(const prs_slab &s, float y) {
 /* packed sorted copy of the owned robots at [halo_cap, halo_cap + n); pr.w = local slot (the
  * scatter target of collide) */
 __global__ void __launch_bounds__(256) k_slab_gather(prs_slab s) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -196,6 +209,7 @@ __device__ __forceinline__ uint32_t slab_lower_bound(const uint32_t *hash, uint3
  * finds them, then the block copies them into the outgoing buffers (count word first). */
 __global__ void __launch_bounds__(256) k_slab_halo_pack(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up,
                                                         uint32_t gx) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t *hs = s.hash_cat + s.halo_cap; /* owned keys, sorted */
   __shared__ uint32_t sh[2];
@@ -230,6 +244,7 @@ __global__ void __launch_bounds__(256) k_slab_halo_pack(prs_slab s, uint32_t *__
 /* arrivals go to the flanks: the lower neighbour's rows end at halo_cap, the upper neighbour's
  * start at halo_cap + n */
 __global__ void __launch_bounds__(256) k_slab_halo_unpack(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t n_lo = s.has_dn ? min(recv_dn[0], s.halo_cap) : 0u, n_hi = s.has_up ? min(recv_up[0], s.halo_cap) : 0u;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -251,6 +266,7 @@ __global__ void __launch_bounds__(256) k_slab_halo_unpack(prs_slab s, const uint
 }
 /* cellStart/cellEnd (reference format) over the keys of [lower halo | owned | upper halo] */
 __global__ void __launch_bounds__(256) k_slab_cell_table(prs_slab s) {
+  prs::pdl_sync();
   const uint32_t n_lo = s.counts[PRS_SC_NLO], n_tot = n_lo + s.counts[PRS_SC_N] + s.counts[PRS_SC_NHI];
   const uint32_t slot0 = s.halo_cap - n_lo;
   const uint32_t *hash = s.hash_cat + slot0;
@@ -267,12 +283,14 @@ __global__ void __launch_bounds__(256) k_slab_cell_table(prs_slab s) {
 /* XORWOW states for robots that carry GLOBAL ids: subsequence = global id, so every robot's noise
  * stream is the one the single-GPU run (and the reference) gives it */
 __global__ void __launch_bounds__(256) k_curand_setup_ids(curandState *__restrict__ st, const uint32_t *__restrict__ gid, uint32_t n) {
+  prs::pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) curand_init(c_prm.p.seed, gid[i], 0, &st[i]);
 }
 
 /* ---- binned route of the slab sort (prs_cellbin.cuh): tickets, scatter, in-cell order by GLOBAL id ---- */
 __global__ void __launch_bounds__(256) k_slab_tickets(prs_slab s, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ ticket) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -285,6 +303,7 @@ __global__ void __launch_bounds__(256) k_slab_tickets(prs_slab s, uint32_t *__re
 }
 __global__ void __launch_bounds__(256)
 k_slab_scatter(prs_slab s, const uint32_t *__restrict__ ticket, uint32_t *__restrict__ index_by_slot) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -297,6 +316,7 @@ k_slab_scatter(prs_slab s, const uint32_t *__restrict__ ticket, uint32_t *__rest
 /* the robots of one cell in ascending GLOBAL id (= the single-GPU stable order) + packed sorted copy */
 __global__ void __launch_bounds__(256)
 k_slab_gather_binned(prs_slab s, const uint32_t *__restrict__ index_by_slot, uint32_t *scratch) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -321,6 +341,7 @@ k_slab_gather_binned(prs_slab s, const uint32_t *__restrict__ index_by_slot, uin
 }
 /* fullest owned cell (guard of the binned route) from the sorted owned keys and the finished table */
 __global__ void __launch_bounds__(256) k_slab_max_population(prs_slab s, uint32_t *__restrict__ out_max) {
+  prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t *hash = s.hash_cat + s.halo_cap;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,6 +362,7 @@ __global__ void __launch_bounds__(256) k_slab_max_population(prs_slab s, uint32_
 }
 /* cell table entries of the two halo flanks only (the owned rows' entries come from the scan) */
 __global__ void __launch_bounds__(256) k_slab_halo_table(prs_slab s) {
+  prs::pdl_sync();
   const uint32_t n_lo = s.counts[PRS_SC_NLO], n = s.counts[PRS_SC_N], n_hi = s.counts[PRS_SC_NHI];
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_lo + n_hi) return;
@@ -383,80 +405,106 @@ void prs_slab_rng_setup(const prs_slab *s, unsigned n) {
   if (!n) return;
   PRS_LAUNCH(k_curand_setup_ids, div_up(n, 256), 256, 0, (curandState *)s->rng, s->gid, n);
 }
+/* K1.  On sort steps the route of the sort is decided HERE (binned while the swarm is known to be sparse, the
+ * same asynchronous guard as the single-GPU step) because the binned route takes the cell tickets inside K1:
+ * one pass over the robots less than ticketing after the migration.  Robots that leave keep no ticket, arrivals
+ * take theirs when they are appended. */
 void prs_slab_k1(const prs_slab *s, float time, float dt, int do_hash) {
   slab_check(s);
   const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
   StageScope t(PRS_STAGE_K1);
-  PRS_LAUNCH(k_slab_begin_step, 1, 32, 0, s->counts);
-  if (do_hash)
-    PRS_LAUNCH(k_control_integrate_hash<true>, div_up(s->cap, 256), 256, 0, (float2 *)s->pos, (float2 *)s->vel, s->rad, s->phase,
-               s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap, s->counts + PRS_SC_N);
-  else
-    PRS_LAUNCH(k_control_integrate_hash<false>, div_up(s->cap, 256), 256, 0, (float2 *)s->pos, (float2 *)s->vel, s->rad, s->phase,
-               s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap, s->counts + PRS_SC_N);
+  PRS_LAUNCH_PDL(k_slab_begin_step, 1, 32, s->counts);
+  g_prs.slab_tickets = false;
+  if (do_hash) {
+    PrsBinState &B = g_prs.bin;
+    bin_poll_report();
+    const unsigned gx = g_prs.h_prm.p.gridSize.x;
+    const unsigned cells = (s->row_hi - s->row_lo) * gx; /* cells of the owned rows */
+    g_prs.slab_binned = (B.mode == 2 || (B.mode == 0 && B.admitted)) && (unsigned long long)cells <= 16ull * s->cap;
+    if (g_prs.slab_binned) {
+      bin_ensure(s->cap, g_prs.h_prm.p.numCells);
+      PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
+      PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
+                     s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, g_prs.sort_ws.vals[0], time, dt, run_controller, s->cap,
+                     (const uint32_t *)(s->counts + PRS_SC_N), B.cellCount, (uint32_t *)nullptr, s->row_lo, s->row_hi, slab_log2_gx());
+      g_prs.slab_tickets = true;
+    } else {
+      PRS_LAUNCH_PDL((k_control_integrate_hash<true, false>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
+                     s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap,
+                     (const uint32_t *)(s->counts + PRS_SC_N), (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
+    }
+  } else {
+    PRS_LAUNCH_PDL((k_control_integrate_hash<false, false>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
+                   s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap,
+                   (const uint32_t *)(s->counts + PRS_SC_N), (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
+  }
 }
 void prs_slab_migrate_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up) {
   StageScope t(PRS_STAGE_EXCHANGE);
-  PRS_LAUNCH(k_slab_select, div_up(s->cap, 256), 256, 0, *s, send_dn, send_up, slab_log2_gx());
-  PRS_LAUNCH(k_slab_list_holes, div_up(2 * s->mig_cap, 256), 256, 0, *s, send_dn, send_up);
+  PRS_LAUNCH_PDL(k_slab_select, div_up(s->cap, 256), 256, *s, send_dn, send_up, slab_log2_gx());
+  PRS_LAUNCH_PDL(k_slab_list_holes, div_up(2 * s->mig_cap, 256), 256, *s, send_dn, send_up);
 }
 void prs_slab_migrate_unpack(const prs_slab *s, const unsigned *recv_dn, const unsigned *recv_up) {
   StageScope t(PRS_STAGE_EXCHANGE);
-  PRS_LAUNCH(k_slab_fill_holes, div_up(2 * s->mig_cap, 256), 256, 0, *s);
-  PRS_LAUNCH(k_slab_append, div_up(2 * s->mig_cap, 256), 256, 0, *s, recv_dn, recv_up, slab_log2_gx());
-  PRS_LAUNCH(k_slab_commit_count, 1, 1, 0, *s, recv_dn, recv_up);
+  uint32_t *ticket = g_prs.slab_tickets ? g_prs.sort_ws.vals[0] : nullptr;
+  PRS_LAUNCH_PDL(k_slab_fill_holes, div_up(2 * s->mig_cap, 256), 256, *s, ticket);
+  PRS_LAUNCH_PDL(k_slab_append, div_up(2 * s->mig_cap, 256), 256, *s, recv_dn, recv_up, slab_log2_gx(),
+                 g_prs.slab_tickets ? g_prs.bin.cellCount : (uint32_t *)nullptr, ticket);
+  PRS_LAUNCH_PDL(k_slab_commit_count, 1, 1, *s, recv_dn, recv_up);
 }
 /* (hash, local slot) of the owned robots sorted by hash into hash_cat[halo_cap ..] / index_sorted,
  * robots of one cell in ascending global id */
 void prs_slab_sort(const prs_slab *s) {
   PrsBinState &B = g_prs.bin;
-  bin_poll_report();
   const unsigned gx = g_prs.h_prm.p.gridSize.x;
   const unsigned cells = (s->row_hi - s->row_lo) * gx; /* cells of the owned rows */
-  g_prs.slab_binned = (B.mode == 2 || (B.mode == 0 && B.admitted)) && (unsigned long long)cells <= 16ull * s->cap;
   StageScope t(PRS_STAGE_SORT);
   if (g_prs.slab_binned) {
-    /* tickets -> scan of the owned rows' cells (= their cell table, slots offset by the lower halo)
-     * -> scatter; the in-cell order by global id is part of the gather */
-    bin_ensure(s->cap, g_prs.h_prm.p.numCells);
+    /* tickets (taken by K1 and by the arrivals) -> scan of the owned rows' cells (= their cell table, slots
+     * offset by the lower halo) -> scatter; the in-cell order by global id is part of the gather */
     prs_sort::Workspace &w = g_prs.sort_ws;
     const size_t c_lo = (size_t)s->row_lo * gx;
     const unsigned tiles = div_up(cells, prs_bin::SCAN_TILE);
-    PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
-    PRS_LAUNCH(k_slab_tickets, div_up(s->cap, 256), 256, 0, *s, B.cellCount, w.vals[0]);
-    PRS_LAUNCH(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, cells, B.scratch);
-    if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
-      PRS_LAUNCH(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                 cells, B.scratch, s->halo_cap);
-    } else {
-      PRS_LAUNCH(prs_bin::k_cell_scan_tiles, 1, 1024, 0, B.scratch, tiles);
-      PRS_LAUNCH(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, 0, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                 cells, B.scratch, s->halo_cap);
+    if (!g_prs.slab_tickets) { /* K1 ran without the route being known (callers of earlier builds) */
+      bin_ensure(s->cap, g_prs.h_prm.p.numCells);
+      PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
+      PRS_LAUNCH_PDL(k_slab_tickets, div_up(s->cap, 256), 256, *s, B.cellCount, w.vals[0]);
     }
-    PRS_LAUNCH(k_slab_scatter, div_up(s->cap, 256), 256, 0, *s, w.vals[0], w.vals[1]);
+    PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, (const uint32_t *)(B.cellCount + c_lo), cells, B.scratch,
+                   (const uint32_t *)nullptr);
+    if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
+      PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs());
+    } else {
+      PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
+      PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs());
+    }
+    PRS_LAUNCH_PDL(k_slab_scatter, div_up(s->cap, 256), 256, *s, (const uint32_t *)w.vals[0], w.vals[1]);
     g_prs.slab_table_fresh = true; /* consumed by this step's gather and cell_table */
     return;
   }
   g_prs.slab_sorted_onesweep = true;
   sort_pairs(s->hash, nullptr, s->hash_cat + s->halo_cap, s->index_sorted, s->cap, key_bits_of_grid(), true, s->counts + PRS_SC_N);
-  PRS_LAUNCH(k_fix_ties_by_gid, div_up(s->cap, 256), 256, 0, s->hash_cat + s->halo_cap, s->index_sorted, s->gid, s->counts + PRS_SC_N);
+  PRS_LAUNCH_PDL(k_fix_ties_by_gid, div_up(s->cap, 256), 256, (const uint32_t *)(s->hash_cat + s->halo_cap), s->index_sorted,
+                 (const uint32_t *)s->gid, (const uint32_t *)(s->counts + PRS_SC_N));
 }
 void prs_slab_gather(const prs_slab *s) {
   StageScope t(PRS_STAGE_REORDER);
   if (g_prs.slab_binned && g_prs.slab_table_fresh) {
-    PRS_LAUNCH(k_slab_gather_binned, div_up(s->cap, 256), 256, 0, *s, g_prs.sort_ws.vals[1], g_prs.bin.scratch);
+    PRS_LAUNCH_PDL(k_slab_gather_binned, div_up(s->cap, 256), 256, *s, (const uint32_t *)g_prs.sort_ws.vals[1], g_prs.bin.scratch);
     bin_send_report(g_prs.bin.scratch + 1);
     return;
   }
-  PRS_LAUNCH(k_slab_gather, div_up(s->cap, 256), 256, 0, *s);
+  PRS_LAUNCH_PDL(k_slab_gather, div_up(s->cap, 256), 256, *s);
 }
 void prs_slab_halo_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up) {
   StageScope t(PRS_STAGE_EXCHANGE);
-  PRS_LAUNCH(k_slab_halo_pack, min(div_up(2 * s->halo_cap, 256), 592u), 256, 0, *s, send_dn, send_up, g_prs.h_prm.p.gridSize.x);
+  PRS_LAUNCH_PDL(k_slab_halo_pack, min(div_up(2 * s->halo_cap, 256), 592u), 256, *s, send_dn, send_up, g_prs.h_prm.p.gridSize.x);
 }
 void prs_slab_halo_unpack(const prs_slab *s, const unsigned *recv_dn, const unsigned *recv_up) {
   StageScope t(PRS_STAGE_EXCHANGE);
-  PRS_LAUNCH(k_slab_halo_unpack, min(div_up(2 * s->halo_cap, 256), 592u), 256, 0, *s, recv_dn, recv_up);
+  PRS_LAUNCH_PDL(k_slab_halo_unpack, min(div_up(2 * s->halo_cap, 256), 592u), 256, *s, recv_dn, recv_up);
 }
 /* cell table over [halo | owned | halo].  After a binned sort the owned rows' entries already exist
  * (the scan wrote them): only the halo rows are cleared and filled.  Otherwise (onesweep route, or
@@ -469,29 +517,35 @@ void prs_slab_cell_table(const prs_slab *s) {
   if (g_prs.slab_binned && g_prs.slab_table_fresh) {
     if (s->row_lo > r0) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(s->row_lo - r0) * gx * sizeof(unsigned), g_prs.stream));
     if (r1 > s->row_hi) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)s->row_hi * gx, 0xff, (size_t)(r1 - s->row_hi) * gx * sizeof(unsigned), g_prs.stream));
-    PRS_LAUNCH(k_slab_halo_table, div_up(2 * s->halo_cap, 256), 256, 0, *s);
+    PRS_LAUNCH_PDL(k_slab_halo_table, div_up(2 * s->halo_cap, 256), 256, *s);
     g_prs.slab_table_fresh = false;
     return;
   }
   PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(r1 - r0) * gx * sizeof(unsigned), g_prs.stream));
-  PRS_LAUNCH(k_slab_cell_table, div_up(s->cap + 2 * s->halo_cap, 256), 256, 0, *s);
+  PRS_LAUNCH_PDL(k_slab_cell_table, div_up(s->cap + 2 * s->halo_cap, 256), 256, *s);
   if (g_prs.slab_sorted_onesweep && g_prs.bin.mode == 0 && !g_prs.bin.admitted) {
     /* report the fullest cell so that the binned route can be admitted */
     bin_ensure(s->cap, g_prs.h_prm.p.numCells);
     PRS_CUDA(cudaMemsetAsync(g_prs.bin.scratch, 0, 16, g_prs.stream));
-    PRS_LAUNCH(k_slab_max_population, div_up(s->cap, 256), 256, 0, *s, g_prs.bin.scratch + 1);
+    PRS_LAUNCH_PDL(k_slab_max_population, div_up(s->cap, 256), 256, *s, g_prs.bin.scratch + 1);
     bin_send_report(g_prs.bin.scratch + 1);
   }
   g_prs.slab_sorted_onesweep = false;
 }
-/* collide for the owned sorted slots [halo_cap, halo_cap + n); results go to the local slots */
+/* collide for the owned sorted slots [halo_cap, halo_cap + n); results go to the local slots.
+ * band 0: all of them; 1: the interior rows only (their stencils stay inside the owned rows: needs no halo);
+ * 2 / 3: the first / last halo_rows rows (after the halo has been unpacked and tabled) */
+static void slab_collide_band(const prs_slab *s, float dt, int band) {
+  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
+  prs::PackedLayout in{(const float4 *)s->sortedPR, (const float2 *)s->sortedVel};
+  const unsigned span = (band >= 2) ? min(s->halo_cap, s->cap) : s->cap; /* an edge band is what goes out as a halo: <= halo_cap slots */
+  prs_launch_collide_t((float2 *)s->vel, s->absForce_a, s->absForce_r, in, s->cellStart, s->cellEnd, s->halo_cap + span, dt,
+                       need_fa, s->halo_cap, s->counts + PRS_SC_N, band);
+}
 void prs_slab_collide(const prs_slab *s, float dt) {
   slab_check(s);
   StageScope t(PRS_STAGE_COLLIDE);
-  const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
-  prs::PackedLayout in{(const float4 *)s->sortedPR, (const float2 *)s->sortedVel};
-  prs_launch_collide_t((float2 *)s->vel, s->absForce_a, s->absForce_r, in, s->cellStart, s->cellEnd, s->halo_cap + s->cap, dt,
-                       need_fa, s->halo_cap, s->counts + PRS_SC_N);
+  slab_collide_band(s, dt, 0);
 }
 void prs_slab_min_light_distance(const prs_slab *s, float *d_min_d) {
   PRS_CUDA(cudaMemsetAsync(d_min_d, 0x7f, sizeof(float), g_prs.stream));
@@ -515,6 +569,7 @@ void prs_slab_add_noise(const prs_slab *s, float std) {
 /* on), so the buffer of exchange t+2 is free when t+2 is written.                                */
 /* -------------------------------------------------------------------------------------------- */
 __global__ void k_slab_signal(unsigned *remote_dn, unsigned *remote_up, unsigned seq) {
+  prs::pdl_sync();
   /* the pack kernel that ran before this one in the stream has completed: order its peer writes
    * before the flag at system scope */
   __threadfence_system();
@@ -522,13 +577,23 @@ __global__ void k_slab_signal(unsigned *remote_dn, unsigned *remote_up, unsigned
   if (remote_up) *reinterpret_cast<volatile unsigned *>(remote_up) = seq;
   __threadfence_system();
 }
-__global__ void k_slab_wait(const unsigned *local_dn, const unsigned *local_up, unsigned seq, unsigned *counts) {
+/* recv_dn / recv_up (optional): the local buffers the neighbours fill.  A neighbour that does not show up within
+ * ~15 s sets the sticky PEER_TIMEOUT bit AND empties that buffer (count word 0), so that the unpack kernels do not
+ * consume whatever an earlier exchange left there; the host hears about the bit one step later at most. */
+__global__ void k_slab_wait(const unsigned *local_dn, const unsigned *local_up, unsigned seq, unsigned *counts,
+                            unsigned *recv_dn, unsigned *recv_up) {
+  prs::pdl_sync();
   const volatile unsigned *f = threadIdx.x == 0 ? local_dn : local_up;
   if (threadIdx.x < 2 && f) {
     unsigned long long spins = 0;
     while ((int)(*f - seq) < 0) {
       __nanosleep(64);
-      if (++spins > (1ull << 24)) { atomicOr(&counts[PRS_SC_ERR], PRS_SLAB_ERR_PEER_TIMEOUT); break; } /* ~15 s: never hang the GPU */
+      if (++spins > (1ull << 24)) { /* never hang the GPU */
+        atomicOr(&counts[PRS_SC_ERR], PRS_SLAB_ERR_PEER_TIMEOUT);
+        unsigned *r = threadIdx.x == 0 ? recv_dn : recv_up;
+        if (r) *r = 0u;
+        break;
+      }
     }
   }
   __threadfence_system();
@@ -563,11 +628,119 @@ void *prs_ipc_open(const void *handle) {
 void prs_ipc_close(void *p) { if (p) PRS_CUDA(cudaIpcCloseMemHandle(p)); }
 void prs_slab_signal(unsigned *remote_flag_dn, unsigned *remote_flag_up, unsigned seq) {
   StageScope t(PRS_STAGE_EXCHANGE);
-  PRS_LAUNCH(k_slab_signal, 1, 1, 0, remote_flag_dn, remote_flag_up, seq);
+  PRS_LAUNCH_PDL(k_slab_signal, 1, 1, remote_flag_dn, remote_flag_up, seq);
 }
 void prs_slab_wait(const prs_slab *s, const unsigned *local_flag_dn, const unsigned *local_flag_up, unsigned seq) {
   StageScope t(PRS_STAGE_EXCHANGE);
-  PRS_LAUNCH(k_slab_wait, 1, 32, 0, local_flag_dn, local_flag_up, seq, s->counts);
+  PRS_LAUNCH_PDL(k_slab_wait, 1, 32, local_flag_dn, local_flag_up, seq, s->counts, (unsigned *)nullptr, (unsigned *)nullptr);
+}
+static void slab_wait_drop(const prs_slab *s, const unsigned *flag_dn, const unsigned *flag_up, unsigned seq, unsigned *recv_dn,
+                           unsigned *recv_up) {
+  StageScope t(PRS_STAGE_EXCHANGE);
+  PRS_LAUNCH_PDL(k_slab_wait, 1, 32, flag_dn, flag_up, seq, s->counts, flag_dn ? recv_dn : (unsigned *)nullptr,
+                 flag_up ? recv_up : (unsigned *)nullptr);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One whole step of a slab rank, orchestrated here (Particlebot::update, particlebot.cpp:170-300, cut at the two
+ * exchanges) — the caller only provides what needs the process group: the mapped mailboxes of the two neighbours
+ * (set up once) and, every phase_update_interval, the MIN over all ranks of one float.
+ *
+ *   [phase gate] local min light distance -> allreduce_min callback -> phase offsets (+ noise)
+ *   K1 (controller, integrate, hash + cell tickets on sort steps)
+ *   [sort steps] leavers packed straight into the neighbours' mailboxes -> signal -> wait -> arrivals appended -> sort
+ *   gather -> first / last halo_rows rows packed into the neighbours' mailboxes -> signal
+ *   collide of the INTERIOR rows (their stencils need no halo): the neighbours' halos arrive underneath it
+ *   wait -> halo unpack -> halo rows of the cell table -> collide of the two edge bands
+ *
+ * Mailbox layout (uint32 words), identical on every rank: for source s in {0: from the lower neighbour, 1: from the upper}
+ * halo[2 parities][hw] then mig[2 parities][mw]; after both regions the flag words halo_seq[2], mig_seq[2].
+ * Returns the sticky error bits seen so far (counts[PRS_SC_ERR], copied to pinned memory asynchronously: at most one
+ * step late and never a synchronisation); a peer time-out makes the receiving side drop that exchange (count 0).
+ * --------------------------------------------------------------------------------------------------------------- */
+static inline unsigned *mb_buf(unsigned *base, const prs_slab_ctx *c, int src, int halo, unsigned parity) {
+  const size_t region = 2 * (size_t)c->hw + 2 * (size_t)c->mw;
+  return base + src * region + (halo ? parity * (size_t)c->hw : 2 * (size_t)c->hw + parity * (size_t)c->mw);
+}
+static inline unsigned *mb_flag(unsigned *base, const prs_slab_ctx *c, int src, int halo) {
+  const size_t region = 2 * (size_t)c->hw + 2 * (size_t)c->mw;
+  return base + 2 * region + (halo ? 0 : 2) + src;
+}
+static inline bool slab_gate(float time, float interval, float dt) { return time - interval * floorf(time / interval) < dt; }
+
+size_t prs_slab_mailbox_words(unsigned mig_cap, unsigned halo_cap) {
+  return 2 * (2 * prs_slab_halo_words(halo_cap) + 2 * prs_slab_mig_words(mig_cap)) + 16;
+}
+
+unsigned prs_slab_step(prs_slab_ctx *c, float dt, float sort_interval) {
+  const prs_slab *s = &c->slab;
+  const SimParams &P = g_prs.h_prm.p;
+  const float time = c->time;
+  const bool phase_step = P.control == LIGHT_WAVE && slab_gate(time, P.phase_update_interval, dt);
+  const bool sort_step = slab_gate(time, sort_interval, dt) || !c->sorted_once;
+  if (phase_step) {
+    StageScope t(PRS_STAGE_PHASE);
+    prs_slab_min_light_distance(s, c->d_min_d);
+    if (c->allreduce_min) c->allreduce_min(c->d_min_d, c->user);
+    prs_slab_update_phase(s, 2.0f * P.min_radius, c->d_min_d);
+    if (P.phase_std) prs_slab_add_noise(s, P.phase_std);
+  }
+  prs_slab_k1(s, time, dt, sort_step ? 1 : 0);
+  if (sort_step) {
+    const unsigned q = ++c->seq_mig, par = q & 1u;
+    unsigned *dn = c->peer_dn ? mb_buf(c->peer_dn, c, 1, 0, par) : c->scratch_mig[0]; /* I am the lower rank's UPPER neighbour */
+    unsigned *up = c->peer_up ? mb_buf(c->peer_up, c, 0, 0, par) : c->scratch_mig[1];
+    prs_slab_migrate_pack(s, dn, up);
+    prs_slab_signal(c->peer_dn ? mb_flag(c->peer_dn, c, 1, 0) : nullptr, c->peer_up ? mb_flag(c->peer_up, c, 0, 0) : nullptr, q);
+    slab_wait_drop(s, c->peer_dn ? mb_flag(c->mailbox, c, 0, 0) : nullptr, c->peer_up ? mb_flag(c->mailbox, c, 1, 0) : nullptr, q,
+                   mb_buf(c->mailbox, c, 0, 0, par), mb_buf(c->mailbox, c, 1, 0, par));
+    prs_slab_migrate_unpack(s, mb_buf(c->mailbox, c, 0, 0, par), mb_buf(c->mailbox, c, 1, 0, par));
+    prs_slab_sort(s);
+    c->sorted_once = 1;
+  }
+  k1_done(); /* owned state final in its slots: host-buffer steps may start copying positions / radii back */
+  prs_slab_gather(s);
+  {
+    const unsigned q = ++c->seq_halo, par = q & 1u;
+    unsigned *dn = c->peer_dn ? mb_buf(c->peer_dn, c, 1, 1, par) : c->scratch_halo[0];
+    unsigned *up = c->peer_up ? mb_buf(c->peer_up, c, 0, 1, par) : c->scratch_halo[1];
+    prs_slab_halo_pack(s, dn, up);
+    prs_slab_signal(c->peer_dn ? mb_flag(c->peer_dn, c, 1, 1) : nullptr, c->peer_up ? mb_flag(c->peer_up, c, 0, 1) : nullptr, q);
+    const bool split = c->overlap_exchange && (c->peer_dn || c->peer_up);
+    if (split) {
+      /* interior first: after a binned sort the owned rows' table entries exist already; otherwise (onesweep route,
+       * steps without a sort) the table is built by cell_table below, which needs the halo — no overlap then */
+      if (g_prs.slab_binned && g_prs.slab_table_fresh) {
+        StageScope t(PRS_STAGE_COLLIDE);
+        slab_collide_band(s, dt, 1);
+      } else {
+        c->split_fallbacks++;
+      }
+    }
+    const bool interior_done = split && g_prs.slab_binned && g_prs.slab_table_fresh;
+    slab_wait_drop(s, c->peer_dn ? mb_flag(c->mailbox, c, 0, 1) : nullptr, c->peer_up ? mb_flag(c->mailbox, c, 1, 1) : nullptr, q,
+                   mb_buf(c->mailbox, c, 0, 1, par), mb_buf(c->mailbox, c, 1, 1, par));
+    prs_slab_halo_unpack(s, mb_buf(c->mailbox, c, 0, 1, par), mb_buf(c->mailbox, c, 1, 1, par));
+    prs_slab_cell_table(s);
+    StageScope t(PRS_STAGE_COLLIDE);
+    if (interior_done) {
+      slab_collide_band(s, dt, 2);
+      slab_collide_band(s, dt, 3);
+    } else {
+      slab_collide_band(s, dt, 0);
+    }
+  }
+  c->time = time + dt;
+  /* sticky error bits -> pinned host word, asynchronously */
+  if (!c->h_err) {
+    PRS_CUDA(cudaMallocHost((void **)&c->h_err, sizeof(unsigned)));
+    *c->h_err = 0u;
+  }
+  PRS_CUDA(cudaMemcpyAsync(c->h_err, s->counts + PRS_SC_ERR, sizeof(unsigned), cudaMemcpyDeviceToHost, g_prs.stream));
+  return *c->h_err;
+}
+void prs_slab_ctx_release(prs_slab_ctx *c) {
+  if (c->h_err) { PRS_CUDA(cudaStreamSynchronize(g_prs.stream)); PRS_CUDA(cudaFreeHost(c->h_err)); c->h_err = nullptr; }
 }
 
 }  // extern "C"

@@ -206,7 +206,7 @@ class SlabSim:
     stand-in); `group` is the torch.distributed process group (None = default)."""
 
     def __init__(self, params, opt, backend, rank, world, device, pos, gid, rows, capacity=None, halo_cap=None,
-                 mig_cap=None, group=None, exchange="nccl"):
+                 mig_cap=None, group=None, exchange="nccl", native_step=True, overlap_exchange=True):
         self.p, self.opt, self.be = params, opt, backend
         self.rank, self.world, self.dev, self.group = rank, world, device, group
         self.R_lo, self.R_hi = rows[rank], rows[rank + 1]
@@ -245,10 +245,34 @@ class SlabSim:
         self.be.rng_setup(n)
         self.exchange = exchange
         self.seq = {"halo": 0, "mig": 0}
+        self.ctx = None
         if exchange == "p2p":
             self._setup_p2p(mw, hw)
         elif exchange != "nccl":
             raise ValueError(exchange)
+        if self.exchange == "p2p" and native_step and isinstance(backend, CudaBackend):
+            self._setup_native_step(mw, hw, overlap_exchange)
+
+    # ---- the whole step in the library (prs_slab_step): this class only keeps the process-group plumbing ------------
+    def _setup_native_step(self, mw, hw, overlap_exchange):
+        c = prs.SlabCtx()
+        c.slab = self.be.slab
+        c.mailbox, c.peer_dn, c.peer_up = self.mailbox, self.peer[0], self.peer[1]
+        c.mw, c.hw = mw, hw
+        for i in range(2):
+            c.scratch_mig[i] = self.mig_send[i].data_ptr()
+            c.scratch_halo[i] = self.halo_send[i].data_ptr()
+        c.d_min_d = self.min_d.data_ptr()
+
+        def allreduce_min(dev_ptr, user):
+            # the one collective of the path: MIN of a float over the ranks, every phase_update_interval
+            dist.all_reduce(self.min_d[:1], op=dist.ReduceOp.MIN, group=self.group)
+
+        self._allreduce_cb = prs.ALLREDUCE_MIN_FN(allreduce_min)     # keep the callback object alive
+        c.allreduce_min = self._allreduce_cb
+        c.overlap_exchange = 1 if overlap_exchange else 0
+        c.time, c.sorted_once = 0.0, 0
+        self.ctx = c
 
     # ---- peer-to-peer mailboxes (exchange="p2p") ---------------------------------------------------
     def _setup_p2p(self, mw, hw):
@@ -311,6 +335,9 @@ class SlabSim:
                 self._mb_flag(self.mailbox, 1, kind) if self.peer[1] else None, q)
 
     def close(self):
+        if self.ctx is not None:
+            self.be.lib.prs_slab_ctx_release(C.byref(self.ctx))
+            self.ctx = None
         if self.exchange == "p2p" and getattr(self, "mailbox", None):
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
@@ -394,6 +421,14 @@ class SlabSim:
         time = self.time
         if np.float32(time) >= np.float32(p.time_to_dead) and np.float32(time) < np.float32(p.time_to_dead) + np.float32(dt):
             self._dead_draw()
+        if self.ctx is not None:
+            # the step itself is the library's: K1, migration, sort, gather, halo exchange under the interior collide, edge bands
+            err = self.be.lib.prs_slab_step(C.byref(self.ctx), float(dt), float(sort_interval))
+            self.time = np.float32(self.ctx.time)
+            self.sorted_once = bool(self.ctx.sorted_once)
+            if err:
+                raise RuntimeError(f"rank {self.rank}: " + "; ".join(msg for bit, msg in prs.SLAB_ERRORS.items() if err & bit))
+            return
         phase_step = self._gate(time, p.phase_update_interval, dt)
         sort_step = self._gate(time, sort_interval, dt) or not self.sorted_once
         if phase_step:
@@ -442,14 +477,30 @@ class SlabSim:
             v.copy_(getattr(self.s, k)[:n_own])
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
+        lib = getattr(self.be, "lib", None)
+        overlap = self.ctx is not None and lib is not None
         t0 = _time.perf_counter()
         for _ in range(steps):
-            for k, v in h.items():
-                getattr(self.s, k)[:n_own].copy_(v, non_blocking=True)
-            self.step(dt, sort_interval)
-            for k, v in h.items():
-                v.copy_(getattr(self.s, k)[:n_own], non_blocking=True)
-            torch.cuda.synchronize()
+            if overlap:
+                # asynchronous uploads on the launching stream; positions and radii travel back on a second stream as soon
+                # as they are final in their slots (after K1 / the migration), under sort, gather and collide; velocities
+                # after collide.  Slots [0, n_own) are round-tripped: the device stays the truth across migrations.
+                for k, v in h.items():
+                    lib.prs_h2d_async(C.c_void_p(getattr(self.s, k).data_ptr()), C.c_void_p(v.data_ptr()), v.numel() * 4)
+                lib.prs_arm_k1_event(1)
+                self.step(dt, sort_interval)
+                lib.prs_arm_k1_event(0)
+                lib.prs_d2h_async(C.c_void_p(h["pos"].data_ptr()), C.c_void_p(self.s.pos.data_ptr()), h["pos"].numel() * 4, 1)
+                lib.prs_d2h_async(C.c_void_p(h["rad"].data_ptr()), C.c_void_p(self.s.rad.data_ptr()), h["rad"].numel() * 4, 1)
+                lib.prs_d2h_async(C.c_void_p(h["vel"].data_ptr()), C.c_void_p(self.s.vel.data_ptr()), h["vel"].numel() * 4, 0)
+                lib.prs_host_step_sync()
+            else:
+                for k, v in h.items():
+                    getattr(self.s, k)[:n_own].copy_(v, non_blocking=True)
+                self.step(dt, sort_interval)
+                for k, v in h.items():
+                    v.copy_(getattr(self.s, k)[:n_own], non_blocking=True)
+                torch.cuda.synchronize()
         dist.barrier(group=self.group)
         t = torch.tensor([_time.perf_counter() - t0], dtype=torch.float64, device=self.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)

@@ -183,7 +183,7 @@ def test_cabi_exports_every_declared_symbol():
     hdr = open(os.path.join(util.ROOT, "include", "prs_cabi.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", hdr))
-    names -= {"defined"}
+    names -= {"defined", "void"}     # "void (*callback)(...)" members are not functions of the library
     assert {"collide", "calcHash", "sortParticlebots", "reorderDataAndFindCellStart", "integrateSystem",
             "prs_fused_step", "prs_sim_update"} <= names
     out = subprocess.check_output(["nm", "-D", "--defined-only", prs.LIB_PATH], text=True)
