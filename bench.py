@@ -621,6 +621,86 @@ def run_gpu(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_sort_only(args):
+    """--sort-only: the hand-written onesweep sort (prs_sort_pairs) beside cub::DeviceRadixSort::SortPairs (cross-check
+    build, oracle/_build/libprs_cubsort.so — what the reference reaches through thrust::sort_by_key,
+    particlebot_cuda.cu:377-382) on the cell keys of the S1 / S2 lattices at 2^20, 2^23 and 2^26 pairs: identical
+    output, median of `--steps` runs each (CUDA events, L2 flushed between runs), algorithmic bytes 4 + 16 P per pair."""
+    import torch
+    import particlerobotsimulations_b200 as prs
+    from oracle import binding as ob
+    torch.cuda.set_device(0)
+    lib = prs.lib()
+    stream = torch.cuda.current_stream()
+    lib.prs_set_stream(C.c_void_p(stream.cuda_stream))
+    cub_path = os.path.join(os.path.dirname(ob.LIB_PATH), "libprs_cubsort.so")
+    cub = C.CDLL(cub_path) if os.path.exists(cub_path) else None
+    if cub:
+        cub.prs_cub_sort_temp_bytes.restype = C.c_size_t
+        cub.prs_cub_sort_temp_bytes.argtypes = [C.c_uint, C.c_int, C.c_int]
+        cub.prs_cub_sort_pairs.restype = C.c_int
+        cub.prs_cub_sort_pairs.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4 + [C.c_uint, C.c_int, C.c_int, C.c_void_p]
+    peak, peak_src = measured_peak()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    reps = max(5, min(args.steps, 30))
+    rows = []
+    for log2n in (20, 23, 26):
+        p, o, geom = swarm_config(prs, log2n)
+        n = int(p.nCells)
+        pos = torch.from_numpy(hex_positions(p, geom)).cuda()
+        # cell keys of the lattice (calcHash through the C-ABI), robots in index order: the distribution the step sorts
+        keys = torch.empty(n, dtype=torch.int32, device="cuda")
+        vals = torch.empty(n, dtype=torch.int32, device="cuda")
+        lib.setParameters(C.byref(p))
+        lib.calcHash(keys.data_ptr(), vals.data_ptr(), pos.data_ptr(), n)
+        bits = int(np.ceil(np.log2(p.numCells)))
+        passes = (bits + 7) // 8
+        ok, ov = torch.empty_like(keys), torch.empty_like(vals)
+        ck, cv = torch.empty_like(keys), torch.empty_like(vals)
+
+        def timed(fn):
+            ts = []
+            for _ in range(reps):
+                flush.fill_(1)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                fn()
+                b_.record(stream)
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b_))
+            return float(np.median(ts))
+
+        own = lambda: lib.prs_sort_pairs(keys.data_ptr(), vals.data_ptr(), ok.data_ptr(), ov.data_ptr(), n, bits)
+        own()
+        t_own = timed(own)
+        row = {"pairs": n, "workload": workload_text(geom, n), "key_bits": bits, "radix_passes": passes,
+               "alg_bytes_per_pair": 4 + 16 * passes,
+               "onesweep": {"ms": t_own, "GBps": (4 + 16 * passes) * n / (t_own * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": (4 + 16 * passes) * n / (t_own * 1e-3) / 1e9 / peak}}
+        if cub:
+            for name, end_bit in (("cub_key_bits", bits), ("cub_32_bits", 32)):
+                tb = cub.prs_cub_sort_temp_bytes(n, 0, end_bit)
+                temp = torch.empty(max(tb, 16), dtype=torch.uint8, device="cuda")
+                f = lambda: cub.prs_cub_sort_pairs(temp.data_ptr(), tb, keys.data_ptr(), ck.data_ptr(), vals.data_ptr(), cv.data_ptr(),
+                                                   n, 0, end_bit, C.c_void_p(stream.cuda_stream))
+                assert f() == 0
+                t = timed(f)
+                pp = (end_bit + 7) // 8
+                row[name] = {"ms": t, "end_bit": end_bit, "GBps": (4 + 16 * pp) * n / (t * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": (4 + 16 * pp) * n / (t * 1e-3) / 1e9 / peak}
+            torch.cuda.synchronize()
+            row["identical_output"] = bool(torch.equal(ok, ck) and torch.equal(ov, cv))
+            row["onesweep_vs_cub_key_bits"] = row["cub_key_bits"]["ms"] / t_own
+            row["onesweep_vs_cub_32_bits"] = row["cub_32_bits"]["ms"] / t_own
+        rows.append(row)
+        del pos, keys, vals, ok, ov, ck, cv
+    print(json.dumps({"metric": "sort: pairs/s (informational, --sort-only)", "impl": "sort-only", "peak_GBps": peak, "peak_source": peak_src,
+                      "what": "prs_sort_pairs (hand-written onesweep, csrc/prs_onesweep.cuh) vs cub::DeviceRadixSort::SortPairs on the "
+                              "cell keys of the synthetic lattices; cub_32_bits is what thrust::sort_by_key runs (full key width), "
+                              "cub_key_bits is CUB told the real key width", "rows": rows}))
+
+
+# ------------------------------------------------------------------------------------------------
 def run_slabs(args, rank, world, local_rank):
     """--gpus N (N > 1): S2 (2^26 robots, or --robots-log2) slab-decomposed over the ranks.  Before timing, the slab
     engine is checked bit for bit against the single-GPU path on the live ranks (multigpu.selfcheck_vs_single_gpu);
@@ -779,6 +859,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary blocks (pitch 0.155, S2 on one GPU)")
     ap.add_argument("--no-s2", action="store_true", help="skip the 2^26-robot block of the N = 1 line")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the slab-vs-single-GPU bit-equality check before timing")
+    ap.add_argument("--sort-only", action="store_true", help="time prs_sort_pairs against cub::DeviceRadixSort on the lattices' cell keys")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-kernels-on-R1 comparison block")
     ap.add_argument("--scramble", action="store_true", help="N = 1: permute the robots so that index order is unrelated to position")
@@ -792,6 +873,8 @@ def main():
         if int(os.environ.get("RANK", "0")) == 0:
             run_reference_cpu(args)
         return
+    if args.sort_only:
+        return run_sort_only(args)
     run_gpu(args)
 
 

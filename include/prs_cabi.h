@@ -266,6 +266,10 @@ size_t prs_slab_mailbox_words(unsigned mig_cap, unsigned halo_cap);
 unsigned prs_slab_step(prs_slab_ctx *c, float dt, float sort_interval);
 void prs_slab_ctx_release(prs_slab_ctx *c);
 
+/* synthetic hex block placed by a kernel (the same bits as Particlebot::initHexBlock's host loop): n = nx * ny robots on a hex
+ * lattice centred on the origin, jitter from a counter hash of (seed, robot), velocity 0, radius min_radius, phase 0, alive */
+void prs_init_hex_block(float *pos, float *vel, float *rad, float *phase, int *dead, unsigned n, unsigned nx, unsigned ny,
+                        float pitch, float jitter, unsigned seed, float min_radius);
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n);
 /* self-test: number of operand pairs for which the shared-reciprocal division used by collide
  * differs from __fdiv_rn (must be 0) */
@@ -280,6 +284,15 @@ typedef struct {
   float camera_x, camera_y, light_radius;
   int display_interval, video_interval;
   char csv_filename[300], video_filename[300];
+  /* extension keys of this repository's parser (the reference skips unknown names together with their value line, so a
+   * cfg that uses them still loads there): init_config = random | grid | hex | line | hexblock; hexblock_nx, hexblock_ny,
+   * hexblock_pitch, hexblock_jitter (fraction of max_radius), hexblock_seed; world_half (wall of integrate, reference: 64),
+   * grid_dim (cells per axis, power of two, reference: 512) */
+  int init_hexblock;             /* 1: place the swarm with initHexBlock instead of reset() */
+  unsigned hexblock_nx, hexblock_ny, hexblock_seed;
+  float hexblock_pitch, hexblock_jitter;
+  float world_half;              /* 0 = the reference's 64 */
+  unsigned grid_dim;             /* 0 = the reference's 512 */
 } prs_run_options;
 void prs_params_defaults(SimParams *p, prs_run_options *opt);
 /* parses a .cfg file with the reference's grammar and quirks (main.cpp:594-816, 913-928) on top

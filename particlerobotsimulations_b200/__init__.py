@@ -62,6 +62,8 @@ class RunOptions(C.Structure):
         ("camera_x", C.c_float), ("camera_y", C.c_float), ("light_radius", C.c_float),
         ("display_interval", C.c_int), ("video_interval", C.c_int),
         ("csv_filename", C.c_char * 300), ("video_filename", C.c_char * 300),
+        ("init_hexblock", C.c_int), ("hexblock_nx", C.c_uint), ("hexblock_ny", C.c_uint), ("hexblock_seed", C.c_uint),
+        ("hexblock_pitch", C.c_float), ("hexblock_jitter", C.c_float), ("world_half", C.c_float), ("grid_dim", C.c_uint),
     ]
 
 
@@ -149,6 +151,7 @@ SIGNATURES = {
     "prs_ipc_export": (None, [_VP, _VP]), "prs_ipc_open": (_VP, [_VP]), "prs_ipc_close": (None, [_VP]),
     "prs_slab_signal": (None, [_VP, _VP, _U]), "prs_slab_wait": (None, [_VP, _VP, _VP, _U]),
     "prs_slab_mailbox_words": (C.c_size_t, [_U, _U]), "prs_slab_step": (_U, [_VP, _F, _F]), "prs_slab_ctx_release": (None, [_VP]),
+    "prs_init_hex_block": (None, [_VP, _VP, _VP, _VP, _VP, _U, _U, _U, _F, _F, _U, _F]),
     "prs_unpack_sorted": (None, [_VP, _VP, _VP, _U]), "prs_selftest_div": (C.c_ulonglong, [_VP, _VP, _U]),
     "prs_fused_step": (None, [C.POINTER(StepBuffers), _F, _F, _I]),
     "prs_bin_invalidate": (None, []), "prs_bin_set_mode": (None, [_I]), "prs_bin_active": (_I, []),

@@ -18,6 +18,11 @@
  *   - `config` compares the NAME against CONFIG_* and therefore never changes anything;
  *   - unknown names still consume their value line;
  *   - phase_std's default 0.3*rise_period is fixed before the file is read.
+ *
+ * Extension keys (not in the reference, which skips an unknown name together with its value line — a cfg that uses them
+ * still loads there and runs its default CONFIG_RANDOM placement): init_config, hexblock_nx / _ny / _pitch / _jitter /
+ * _seed, world_half, grid_dim.  They make the placement selector and the synthetic worlds of SURVEY.md §8d reachable
+ * from a cfg file (the reference's own `config` key can never change anything, see above).
  */
 #include <math.h>
 #include <stdio.h>
@@ -105,6 +110,7 @@ extern "C" void prs_params_defaults(SimParams *p, prs_run_options *o) {
     o->video_interval = 1;
     snprintf(o->csv_filename, sizeof(o->csv_filename), "particle_bot_output_data.csv");
     snprintf(o->video_filename, sizeof(o->video_filename), "particle_bot_output_video.avi");
+    o->hexblock_jitter = 0.01f;
   }
   prs_params_derive_grid(p);
 }
@@ -180,6 +186,23 @@ static void set_param(const std::string &name, const std::string &value, SimPara
   else if (starts(name, "phase_update_interval", 21)) p->phase_update_interval = L();
   else if (starts(name, "Nx", 2)) p->Nx = (int)L(); /* unreachable: 2-character names are filtered out */
   else if (starts(name, "config", 6)) { /* no-op in the reference: it tests the name against CONFIG_* */ }
+  /* ---- extension keys ---- */
+  else if (starts(name, "init_config", 11)) {
+    o->init_hexblock = 0;
+    if (starts(value, "random", 6)) p->config = CONFIG_RANDOM;
+    else if (starts(value, "grid", 4)) p->config = CONFIG_GRID;
+    else if (starts(value, "hexblock", 8)) o->init_hexblock = 1;
+    else if (starts(value, "hex", 3)) p->config = CONFIG_HEX;
+    else if (starts(value, "line", 4)) p->config = CONFIG_LINE;
+    else { fprintf(stderr, "cfg: unknown init_config '%s' (random, grid, hex, line, hexblock)\n", v); exit(EXIT_FAILURE); }
+  }
+  else if (starts(name, "hexblock_nx", 11)) o->hexblock_nx = (unsigned)L();
+  else if (starts(name, "hexblock_ny", 11)) o->hexblock_ny = (unsigned)L();
+  else if (starts(name, "hexblock_pitch", 14)) o->hexblock_pitch = F();
+  else if (starts(name, "hexblock_jitter", 15)) o->hexblock_jitter = F();
+  else if (starts(name, "hexblock_seed", 13)) o->hexblock_seed = (unsigned)L();
+  else if (starts(name, "world_half", 10)) o->world_half = F();
+  else if (starts(name, "grid_dim", 8)) o->grid_dim = (unsigned)L();
   else if (starts(name, "DISPLAY_INTERVAL", 16)) o->display_interval = (int)L();
   else if (starts(name, "VIDEO_INTERVAL", 14)) o->video_interval = (int)L();
 }
@@ -195,5 +218,17 @@ extern "C" int prs_params_load_cfg(const char *path, SimParams *p, prs_run_optio
       if (std::getline(f, value)) set_param(name, value, p, o);
   }
   prs_params_derive_grid(p);
+  /* extension: synthetic world and hex block */
+  if (o->grid_dim || o->world_half > 0.0f) {
+    const unsigned g = o->grid_dim ? o->grid_dim : 512u;
+    if (g & (g - 1)) { fprintf(stderr, "cfg: grid_dim must be a power of two\n"); exit(EXIT_FAILURE); }
+    prs_params_set_world(p, g, o->world_half > 0.0f ? o->world_half : 64.0f);
+  }
+  if (o->init_hexblock) {
+    if (!o->hexblock_nx || !o->hexblock_ny) { fprintf(stderr, "cfg: init_config hexblock needs hexblock_nx and hexblock_ny\n"); exit(EXIT_FAILURE); }
+    p->nCells = o->hexblock_nx * o->hexblock_ny;
+    if (!(o->hexblock_pitch > 0.0f)) o->hexblock_pitch = 2.0f * p->min_radius;
+    if (!o->hexblock_seed) o->hexblock_seed = p->seed;
+  }
   return opened ? 0 : -1;
 }

@@ -555,6 +555,32 @@ __global__ void k_centroid_final(const double2 *__restrict__ part, int nb, uint3
   out[1] = (float)(ay / (double)n);
 }
 
+/* Synthetic hex block ON THE DEVICE: robot i of an nx-wide hex lattice, every coordinate
+ * jittered by a counter hash of (seed, i) — the arithmetic of Particlebot::initHexBlock's host loop operation for operation
+ * (plain IEEE mul / add, no contraction: identical bits), plus the state reset() gives a fresh swarm (zero velocity, minimum
+ * radius, zero phase, alive).  A 2^26-robot swarm is placed in a millisecond instead of a host loop and 1.3 GB of uploads. */
+__global__ void __launch_bounds__(256)
+k_init_hex_block(float2 *__restrict__ pos, float2 *__restrict__ vel, float *__restrict__ rad, float *__restrict__ phase,
+                 int *__restrict__ dead, unsigned long long n, uint32_t nx, float pitch, float row, float x0, float y0, float jitter,
+                 uint32_t seed, float min_radius) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t iy = (uint32_t)(i / nx), ix = (uint32_t)(i % nx);
+  unsigned long long z = ((unsigned long long)seed << 32) ^ i;
+  z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; z = z ^ (z >> 31);
+  const float jx = __fmul_rn(__fsub_rn(__fdiv_rn((float)(uint32_t)(z & 0xffffffull), 8388608.0f), 1.0f), jitter);
+  const float jy = __fmul_rn(__fsub_rn(__fdiv_rn((float)(uint32_t)((z >> 24) & 0xffffffull), 8388608.0f), 1.0f), jitter);
+  const float odd = (iy & 1u) ? __fmul_rn(0.5f, pitch) : 0.0f;
+  const float x = __fadd_rn(__fadd_rn(__fadd_rn(x0, __fmul_rn((float)ix, pitch)), odd), jx);
+  const float y = __fadd_rn(__fadd_rn(y0, __fmul_rn((float)iy, row)), jy);
+  pos[i] = make_float2(x, y);
+  vel[i] = make_float2(0.0f, 0.0f);
+  rad[i] = min_radius;
+  phase[i] = 0.0f;
+  dead[i] = 0;
+}
+
 /* radius -> colour for the optional renderer (result of updateCol_k, :401-443; the shadow
  * darkening halves the HSL lightness) */
 __device__ float hue_channel(float p, float q, float t) {
@@ -1259,6 +1285,17 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
 #include "prs_slab.cuh"
 
 extern "C" {
+
+void prs_init_hex_block(float *pos, float *vel, float *rad, float *phase, int *dead, unsigned n, unsigned nx, unsigned ny, float pitch,
+                        float jitter, unsigned seed, float min_radius) {
+  if (!n) return;
+  (void)ny;
+  const float row = pitch * 0.8660254037844386f; /* the host generator's constants, same expressions */
+  const float x0 = -0.5f * ((float)(nx - 1) * pitch + 0.5f * pitch), y0 = -0.5f * (float)(ny - 1) * row;
+  prs_bin_invalidate(); /* positions are rewritten behind the fused step's back */
+  PRS_LAUNCH(k_init_hex_block, div_up(n, 256), 256, 0, (float2 *)pos, (float2 *)vel, rad, phase, dead, (unsigned long long)n, nx, pitch, row,
+             x0, y0, jitter, seed, min_radius);
+}
 
 void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad, unsigned n) {
   if (!n) return;

@@ -47,9 +47,12 @@ int main(int argc, char **argv) {
   if (!fp) { perror(opt.csv_filename); return 1; }
   if (quiet) { if (!freopen("/dev/null", "w", stdout)) return 1; }
 
-  Particlebot bot(params, 64.0f, backend, ext);
+  Particlebot bot(params, opt.world_half > 0.0f ? opt.world_half : 64.0f, backend, ext);
   bot.srand(params.seed); /* main.cpp:929 */
-  bot.reset();
+  if (opt.init_hexblock) /* extension key init_config = hexblock: the synthetic swarms of SURVEY.md §8d, placed on the device */
+    bot.initHexBlock(opt.hexblock_nx, opt.hexblock_ny, opt.hexblock_pitch, opt.hexblock_jitter * params.max_radius, opt.hexblock_seed);
+  else
+    bot.reset();
   if (ck_in) {
     FILE *ck = fopen(ck_in, "rb");
     if (!ck || bot.loadCheckpoint(ck) != 0) { fprintf(stderr, "cannot restore %s\n", ck_in); return 1; }

@@ -439,6 +439,27 @@ void Particlebot::initHexBlock(unsigned nx, unsigned ny, float pitch, float jitt
    * a counter hash of (seed, robot id) so that any subset can be generated independently. */
   time = 0;
   const size_t n = params.nCells;
+  if (backend_kind_ != PRS_BACKEND_EXTERNAL) {
+    /* own library: the lattice is generated by a kernel (same bits as the loop below, which stays for other libraries and
+     * as the cross-check of the tests); only the render trail and the frequency array come from the host */
+    const size_t trail = (size_t)params.centroid_steps + 1;
+    for (int i = 0; i < params.centroid_steps; i++) { hRad[n + i] = params.centroid_radius; hPos[(n + i) * 2] = -5000.0f; hPos[(n + i) * 2 + 1] = 0.0f; }
+    hRad[n + params.centroid_steps] = 0.0f;
+    hPos[(n + params.centroid_steps) * 2] = hPos[(n + params.centroid_steps) * 2 + 1] = 0.0f;
+    memset(hDead, 0, n * sizeof(int));
+    prs_init_hex_block(dPos, dVel, dRad, dphase, dDead, (unsigned)n, nx, ny, pitch, jitter, seed, params.min_radius);
+    be_.copyArrayToDevice(dPos, hPos + 2 * n, (int)(n * 2 * sizeof(float)), (int)(trail * 2 * sizeof(float)));
+    be_.copyArrayToDevice(dRad, hRad + n, (int)(n * sizeof(float)), (int)(trail * sizeof(float)));
+    if (n) setArray(FREQUENCY, hfreq, 0, (int)n);
+    if (params.nDead == -1 && n) { /* the last robot is the transported object (reset(), particlebot.cpp:784-791) */
+      const float r_obj = params.min_radius * params.radFactor;
+      const int one = 1;
+      hDead[n - 1] = 1;
+      be_.copyArrayToDevice(dRad, &r_obj, (int)((n - 1) * sizeof(float)), (int)sizeof(float));
+      be_.copyArrayToDevice(dDead, &one, (int)((n - 1) * sizeof(int)), (int)sizeof(int));
+    }
+    return;
+  }
   const float row = pitch * 0.8660254037844386f;
   const float x0 = -0.5f * ((float)(nx - 1) * pitch + 0.5f * pitch), y0 = -0.5f * (float)(ny - 1) * row;
   auto mix = [](uint64_t z) {

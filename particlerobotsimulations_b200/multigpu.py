@@ -485,8 +485,10 @@ class SlabSim:
                 # asynchronous uploads on the launching stream; positions and radii travel back on a second stream as soon
                 # as they are final in their slots (after K1 / the migration), under sort, gather and collide; velocities
                 # after collide.  Slots [0, n_own) are round-tripped: the device stays the truth across migrations.
+                # (the uploads bring back exactly what the last step sent out, so the library's "swarm is sparse" knowledge
+                # stays valid: plain stream copies, not prs_h2d_async, which would withdraw the binned sort's admission)
                 for k, v in h.items():
-                    lib.prs_h2d_async(C.c_void_p(getattr(self.s, k).data_ptr()), C.c_void_p(v.data_ptr()), v.numel() * 4)
+                    getattr(self.s, k)[:n_own].copy_(v, non_blocking=True)
                 lib.prs_arm_k1_event(1)
                 self.step(dt, sort_interval)
                 lib.prs_arm_k1_event(0)

@@ -77,6 +77,30 @@ def test_cfg_parser_quirks(tmp_path):
     assert p.time_to_dead == 5.0           # exact-match key (:749); time_to_dead_x is not it
 
 
+def test_cfg_extension_keys(tmp_path):
+    """init_config / hexblock_* / world_half / grid_dim: the placement selector and the synthetic worlds reachable from a cfg
+    (the reference's own `config` key never changes anything); shipped example: examples/synthetic_s1.cfg == bench.py's S1"""
+    import bench
+    p, o = util.cfg("synthetic_s1")
+    q, _, geom = bench.swarm_config(prs, 20)
+    assert o.init_hexblock == 1 and (o.hexblock_nx, o.hexblock_ny) == (geom["nx"], geom["ny"]) == (1024, 1024)
+    assert abs(o.hexblock_pitch - geom["pitch"]) < 1e-7 and abs(o.hexblock_jitter - bench.JITTER_FRAC) < 1e-9 and o.hexblock_seed == bench.SEED
+    assert p.nCells == q.nCells == 1 << 20 and o.world_half == geom["half"] == 128.0
+    for f in ("numCells", "light_x", "light_y", "min_radius", "max_radius", "spring", "damping", "shear", "attraction", "gravity",
+              "friction", "phase_std", "phase_update_interval", "rise_period", "nDead", "seed"):
+        assert getattr(p, f) == getattr(q, f), f
+    assert (p.gridSize.x, p.gridSize.y, p.worldOrigin.x, p.cellSize.x) == (q.gridSize.x, q.gridSize.y, q.worldOrigin.x, q.cellSize.x)
+    assert abs(o.sort_interval - o.timestep) < 1e-9
+    f = tmp_path / "grid.cfg"
+    f.write_text("init_config\ngrid\nnCells\n64\n")
+    p, o = prs.load_cfg(str(f))
+    assert p.config == 1 and o.init_hexblock == 0 and p.gridSize.x == 512     # CONFIG_GRID, the reference's world
+    f.write_text("init_config\nhex\n")
+    assert prs.load_cfg(str(f))[0].config == 4                                   # CONFIG_HEX
+    f.write_text("config\nhex\n")
+    assert prs.load_cfg(str(f))[0].config == 0                                   # the reference's key stays a no-op
+
+
 def _np_hash(p, pos):
     ox, oy = np.float32(p.worldOrigin.x), np.float32(p.worldOrigin.y)
     cx, cy = np.float32(p.cellSize.x), np.float32(p.cellSize.y)

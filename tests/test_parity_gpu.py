@@ -681,6 +681,26 @@ def _headline_vs_oracle(log2n, cut=None, steps=10):
     return geom
 
 
+def test_device_hex_block_equals_host_generator():
+    """init_hex of this library places the lattice with a kernel (prs_init_hex_block); driving ANOTHER library (EXTERNAL
+    backend) keeps the host loop of Particlebot::initHexBlock: same bits, also for a swarm with a transported object."""
+    if not util.refcuda_available():
+        pytest.skip("oracle/_ref/libprs_refcuda.so not built")
+    for cfg_name, nx, ny in (("example", 300, 211), ("example_object_transport", 64, 33)):
+        p, o = util.cfg(cfg_name)
+        p.nCells = nx * ny
+        out = []
+        for backend, ext in ((prs.BACKEND_FUSED, None), (prs.BACKEND_EXTERNAL, ob.REFCUDA_PATH)):
+            sim = prs.Simulation(p, 64.0, backend, ext)
+            sim.init_hex(nx, ny, 0.17, 0.01 * p.max_radius, 4242)
+            out.append({k: sim.get(w) for k, w in (("pos", prs.POSITION), ("vel", prs.VELOCITY), ("rad", prs.RADII), ("phase", prs.PHASE),
+                                                   ("dead", prs.DEAD))})
+            sim.close()
+        for k in out[0]:
+            assert np.array_equal(out[0][k].view(np.uint32), out[1][k].view(np.uint32)), (cfg_name, k)
+        assert float(np.abs(out[0]["pos"]).max()) > 10.0
+
+
 def test_s1_headline_config_vs_oracle():
     """BASELINE.json's S1 exactly as bench.py builds it (2^20 robots, world +-128 — the parametric wall of integrate,
     reference kernel_impl.cuh:53-103 hard-codes 64 — and the 2048^2 grid of calcHash, :446-465), 10 steps against the
