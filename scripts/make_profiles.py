@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""Builds profiles/r1_ncu_summary.md, profiles/r1_launches_s1.csv and profiles/traffic.json from the ncu
-reports and launch list that scripts/gpu_job_profiles.sh left in gpurun_out/ (run here, no GPU needed)."""
+"""Builds profiles/<tag>_ncu_summary.md, profiles/<tag>_launches_s1.csv and profiles/traffic.json from the ncu
+reports and launch list that scripts/gpu_job_profiles.sh left in gpurun_out/ (run here, no GPU needed).
+The round tag comes from the environment (ROUND, default r2)."""
 import collections, csv, io, json, os, shutil, subprocess
+TAG = os.environ.get("ROUND", "r2")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
-shutil.copy(os.path.join(G, "launches_r1_s1.csv"), os.path.join(P, "r1_launches_s1.csv"))
-shutil.copy(os.path.join(G, "sort_timeline_r1.txt"), os.path.join(P, "r1_sort_timeline.txt"))
+shutil.copy(os.path.join(G, f"launches_{TAG}_s1.csv"), os.path.join(P, f"{TAG}_launches_s1.csv"))
+if os.path.exists(os.path.join(G, f"sort_timeline_{TAG}.txt")):
+    shutil.copy(os.path.join(G, f"sort_timeline_{TAG}.txt"), os.path.join(P, f"{TAG}_sort_timeline.txt"))
 
-rows = list(csv.reader(open(os.path.join(G, "launches_r1_s1.csv"))))
+rows = list(csv.reader(open(os.path.join(G, f"launches_{TAG}_s1.csv"))))
 hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 h = rows[hdr]; kn, mn, mv = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value")
 agg = collections.OrderedDict()
@@ -70,20 +73,36 @@ try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     PEAK = 6650.0
-out = ["# Round 1 — ncu evidence (B200, S1 = 2^20 robots, sort every step)", "",
+STAGE_NOTE = ""
+bj = os.path.join(G, f"bench_{TAG}.json")
+if os.path.exists(bj):
+    try:
+        d = json.loads(open(bj).read().strip().splitlines()[-1])
+        st = d["stages"]
+        STAGE_NOTE = (f"bench.py stage times of the same build (CUDA events, L2 flushed, timed from step {d.get('timed_state_step')}): "
+                      + ", ".join(f"{k} {v['avg_us']:.1f} µs" for k, v in st.items())
+                      + f"; whole step with programmatic dependent launch {1e3 * d['ms_per_step']:.1f} µs (under ncu the small kernels pay "
+                        "relatively more for cold caches and serialisation).")
+    except Exception:
+        pass
+out = [f"# Round {TAG[1:]} — ncu evidence (B200, S1 = 2^20 robots, sort every step)", "",
        "Generated by `scripts/make_profiles.py` from `scripts/gpu_job_profiles.sh` (reports under `gpurun_out/`).", "",
-       "## Launch list of `python bench.py --steps 6 --warmup 4` (`ncu --metrics gpu__time_duration.sum,dram__bytes_* --clock-control none`)", "",
-       "Cold-cache, serialised launches: compare SHARES with the CUDA-event stage times of `bench.py`, not absolutes. Raw list: `r1_launches_s1.csv`.", ""]
+       "## Launch list of `python bench.py --steps 6 --warmup 4` at the timed state (launches of the first 260 untimed steps skipped; "
+       "`ncu --metrics gpu__time_duration.sum,dram__bytes_* --clock-control none`)", "",
+       f"Cold-cache, serialised launches: compare SHARES with the CUDA-event stage times of `bench.py`, not absolutes. Raw list: `{TAG}_launches_s1.csv`.", ""]
 for title, names, passes in (("binned route (the route of every timed step once the swarm is known to be sparse)", binned, 1),
                              ("onesweep route (first sort steps, crowded swarms, C-ABI sortParticlebots)", onesweep, 3)):
     t, tot = table(names, passes)
+    if not t or not any(n.startswith(("k_cell", "k_onesweep", "k_histogram")) for n, *_ in t):
+        continue      # this route does not occur in the captured launches
     out += [f"### {title}", "", "| kernel | launches | avg µs | per step µs | share | dram rd MB | dram wr MB |", "|---|---|---|---|---|---|---|"]
     out += [f"| {n} | {c} | {a:.1f} | {s:.1f} | {100 * s / tot:.1f} % | {rd:.1f} | {wr:.1f} |" for n, c, a, s, rd, wr in t]
     out += [f"| **sum** | | | **{tot:.1f}** | | | |", ""]
-out += ["bench.py stage times of the same build (CUDA events, L2 flushed, evolved state after 250 steps): K1 22.8 µs, cell sort 21.5 µs, "
-        "reorder 13.8 µs, collide 154.0 µs; whole step with programmatic dependent launch 194.8 µs (collide 79 %; under ncu the small "
-        "kernels pay relatively more for cold caches and serialisation, and the launch list is taken at step ~10, before most contacts have formed).", ""]
-for title, rep in (("`ncu --set full` of the step's kernels (prof_r1_step)", "prof_r1_step.ncu-rep"), ("`ncu --set full` of the onesweep route's kernels (prof_r1_onesweep)", "prof_r1_onesweep.ncu-rep")):
+out += [STAGE_NOTE, ""]
+for title, rep in ((f"`ncu --set full` of the step's kernels (prof_{TAG}_step)", f"prof_{TAG}_step.ncu-rep"),
+                   (f"`ncu --set full` of the onesweep route's kernels (prof_{TAG}_onesweep)", f"prof_{TAG}_onesweep.ncu-rep")):
+    if not os.path.exists(os.path.join(G, rep)):
+        continue
     lines, hd, units, rr = full_table(rep)
     out += [f"## {title}", "", "| kernel | " + " | ".join(n for _, n in M) + " | DRAM GB/s | % of measured HBM peak |", "|---|" + "---|" * (len(M) + 2)]
     out += [f"| {n} | " + " | ".join(v) + " |" for n, v in lines]
@@ -96,13 +115,13 @@ for title, rep in (("`ncu --set full` of the step's kernels (prof_r1_step)", "pr
                 rd = float(r[hd.index("dram__bytes_read.sum")].replace(",", "")) * UNIT.get(units[hd.index("dram__bytes_read.sum")], 1.0)
                 wr = float(r[hd.index("dram__bytes_write.sum")].replace(",", "")) * UNIT.get(units[hd.index("dram__bytes_write.sum")], 1.0)
                 traffic = {"collide": rd + wr, "_what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) of k_collide_exact at S1, "
-                                                        "ncu --set full (profiles/r1_ncu_summary.md)", "_read": rd, "_write": wr}
+                                                        f"ncu --set full (profiles/{TAG}_ncu_summary.md)", "_read": rd, "_write": wr}
                 break
         json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 out += ["dram bytes are per launch; at 2^20 robots the whole state (~100 MB) nearly fits the 126 MB L2, so under ncu's serialised replay DRAM traffic "
         "under-reads the algorithmic bytes (collide: 43 B x 2^20 = 45 MB algorithmic vs 33 MB read; its scattered 16 MB of results stay in L2).",
         "collide: XU (MUFU) and FMA pipes ~45-50 % busy each, issue slots ~70 % — a balanced FP32/MUFU bound, DRAM at 2 %.",
-        "`r1_collide_evolved.md`: the same kernel captured at step 260 of the S1 run (the state the bench times), with the per-region instruction and stall-sample shares.", "",
-        "## onesweep phase timeline (`scripts/sort_timeline.py`, %globaltimer stamps per tile): `r1_sort_timeline.txt`", ""]
-open(os.path.join(P, "r1_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+        "`r1_collide_evolved.md`: the round-1 capture of the same kernel at step 260 with the per-region instruction and stall-sample shares; "
+        "`r2_collide_patch.md`: the pair-sharing patch kernel against it.", ""]
+open(os.path.join(P, f"{TAG}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[:60]))
