@@ -183,8 +183,8 @@ __device__ __forceinline__ void slab_drift_check(const prs_slab &s, float y) {
   const bool above = s.has_up && row >= s.row_hi + slack;
   if (below || above) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_DRIFT);
 }
-/* packed sorted copy of the owned robots at [halo_cap, halo_cap + n); pr.w = local slot (the
- * scatter target of collide) */
+/* packed sorted copy of the owned robots at [halo_cap, halo_cap + n); pr.w = GLOBAL id (the robot's identity: the
+ * transported object is robot nCells - 1 wherever it lives); collide scatters its results through index_sorted */
 __global__ void __launch_bounds__(256) k_slab_gather(prs_slab s) {
   prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) k_slab_gather(prs_slab s) {
   const uint32_t src = s.index_sorted[k];
   const float2 p = ((const float2 *)s.pos)[src];
   slab_drift_check(s, p.y);
-  ((float4 *)s.sortedPR)[s.halo_cap + k] = make_float4(p.x, p.y, s.rad[src], __uint_as_float(src));
+  ((float4 *)s.sortedPR)[s.halo_cap + k] = make_float4(p.x, p.y, s.rad[src], __uint_as_float(s.gid[src]));
   ((float2 *)s.sortedVel)[s.halo_cap + k] = ((const float2 *)s.vel)[src];
 }
 /* first owned sorted slot whose key is >= bound (binary search over the device-side count) */
@@ -336,7 +336,7 @@ k_slab_gather_binned(prs_slab s, const uint32_t *__restrict__ index_by_slot, uin
   }
   const uint32_t dst = c0 + below;
   s.index_sorted[dst - s.halo_cap] = a;
-  ((float4 *)s.sortedPR)[dst] = make_float4(p.x, p.y, r, __uint_as_float(a));
+  ((float4 *)s.sortedPR)[dst] = make_float4(p.x, p.y, r, __uint_as_float(g));
   ((float2 *)s.sortedVel)[dst] = v;
 }
 /* fullest owned cell (guard of the binned route) from the sorted owned keys and the finished table */
@@ -391,10 +391,6 @@ static uint32_t slab_log2_gx() {
   return b;
 }
 static void slab_check(const prs_slab *s) {
-  if (g_prs.h_prm.p.nDead == -1) {
-    fprintf(stderr, "prs_slab: object-transport mode (nDead == -1) is single-GPU only\n");
-    exit(EXIT_FAILURE);
-  }
   if (!s->cap || !s->halo_cap || !s->mig_cap) { fprintf(stderr, "prs_slab: zero capacity\n"); exit(EXIT_FAILURE); }
 }
 
@@ -540,7 +536,7 @@ static void slab_collide_band(const prs_slab *s, float dt, int band) {
   prs::PackedLayout in{(const float4 *)s->sortedPR, (const float2 *)s->sortedVel};
   const unsigned span = (band >= 2) ? min(s->halo_cap, s->cap) : s->cap; /* an edge band is what goes out as a halo: <= halo_cap slots */
   prs_launch_collide_t((float2 *)s->vel, s->absForce_a, s->absForce_r, in, s->cellStart, s->cellEnd, s->halo_cap + span, dt,
-                       need_fa, s->halo_cap, s->counts + PRS_SC_N, band);
+                       need_fa, s->halo_cap, s->counts + PRS_SC_N, band, s->index_sorted - s->halo_cap);
 }
 void prs_slab_collide(const prs_slab *s, float dt) {
   slab_check(s);

@@ -29,8 +29,9 @@ copy anywhere in it (overflow and "crossed two slabs" conditions set sticky erro
 few MB (latency-bound on NVLink) and one 4-byte all_reduce per phase update.  Ownership changes
 only on sort steps (the table is frozen between sorts); HALO_ROWS = 3 = the 2-row
 stencil + 1 guard row for drift between sorts.  Limits of this version: the hash wrap-around (Q9)
-is not exchanged — the world must fit the grid — a robot may cross at most one slab per sort,
-object transport (nDead == -1) is single-GPU only.  Robots of one cell are ordered by GLOBAL id
+is not exchanged — the world must fit the grid — and a robot may cross at most one slab per sort.
+Object transport (nDead == -1) works across slabs: sorted and halo records carry the robot's GLOBAL
+id as identity, so every rank recognises the object (robot nCells - 1) wherever it lives.  Robots of one cell are ordered by GLOBAL id
 after the local sort, which is the order the reference's stable sort gives them, so the forces are
 summed in the single-GPU order and the results are bit-equal for any number of slabs.
 
@@ -225,6 +226,12 @@ class SlabSim:
         s.pos[:n] = torch.from_numpy(np.ascontiguousarray(pos)).to(device)
         s.gid[:n] = torch.from_numpy(np.ascontiguousarray(gid).astype(np.int32)).to(device)
         s.rad[:n] = float(np.float32(params.min_radius))
+        if int(params.nDead) == -1:
+            # object transport: the last robot (global id nCells - 1) is the transported object — larger, never
+            # oscillating (reset(), particlebot.cpp:784-791); whichever rank holds it marks it
+            obj = s.gid[:n] == int(params.nCells) - 1
+            s.rad[:n][obj] = float(np.float32(params.min_radius) * np.float32(params.radFactor))
+            s.dead[:n][obj] = 1
         ncat = cap + 2 * self.halo_cap
         self.pr, self.svel, self.hash_cat = z((ncat, 4), f32), z((ncat, 2), f32), z(ncat, i32)
         self.index_sorted = z(cap, i32)

@@ -17,26 +17,53 @@ pytestmark = pytest.mark.gpu
 NX, NY, PITCH, STEPS = multigpu.SELFCHECK["nx"], multigpu.SELFCHECK["ny"], multigpu.SELFCHECK["pitch"], 60
 
 
-def _config():
+def _config(scenario="plain"):
     """the self-check swarm of multigpu.selfcheck_vs_single_gpu (bench.py runs the same check on its live ranks):
-    150 dead robots drawn on step 0 (every rank draws the same global ids), velocities that make robots migrate"""
+    150 dead robots drawn on step 0 (every rank draws the same global ids), velocities that make robots migrate.
+    scenario "object": example_object_transport.cfg physics (nDead = -1: the last robot is the transported object,
+    twice the radius, its own mass / friction / attraction factors) on the same lattice"""
+    if scenario == "object":
+        p, o, geom = multigpu.selfcheck_config(os.path.join(util.EXAMPLES, "example_object_transport.cfg"))
+        p.nDead = -1
+        return p, o, geom
     return multigpu.selfcheck_config(os.path.join(util.EXAMPLES, "example.cfg"))
+
+
+def _object_start(n_total):
+    """the object (robot n_total - 1) is dropped into the middle of the block, just below the cut between the two middle
+    slabs, moving up: it ploughs through the lattice and changes owner"""
+    return np.float32([0.031, -0.3]), np.float32([0.0, 3.0])
 
 
 _initial_velocity = multigpu.selfcheck_velocity
 
 
-def _worker(rank, world, port, out_path, bin_mode, exchange):
+def _worker(rank, world, port, out_path, bin_mode, exchange, scenario="plain"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    p, o, geom = _config()
+    p, o, geom = _config(scenario)
     prs.lib().prs_bin_set_mode(bin_mode)      # 0 auto, 1 onesweep + in-cell insertion sort, 2 cell binning
-    sim = multigpu.make_hex_slab(p, o, geom, multigpu.CudaBackend, rank, world, dev, 5555, 0.01 * p.max_radius, exchange=exchange)
+    if scenario == "object":
+        # the object starts near the middle cut: the rank that owns that row must hold it from the start
+        obj_pos, obj_vel = _object_start(NX * NY)
+        rows = multigpu.slab_rows(p, NY, PITCH, world)
+        ids = np.arange(NX * NY, dtype=np.int64)
+        pos = multigpu.hex_block_positions(ids, NX, NY, PITCH, 0.01 * p.max_radius, 5555)
+        pos[-1] = obj_pos
+        r = multigpu.grid_row_of(pos[:, 1], p)
+        keep = (r >= rows[rank]) & (r < rows[rank + 1])
+        sim = multigpu.SlabSim(p, o, multigpu.CudaBackend(p, geom["half"]), rank, world, dev, pos[keep], ids[keep], rows,
+                               capacity=int(NX * NY / world * 1.5) + 4096, halo_cap=16384, mig_cap=4096, exchange=exchange)
+    else:
+        sim = multigpu.make_hex_slab(p, o, geom, multigpu.CudaBackend, rank, world, dev, 5555, 0.01 * p.max_radius, exchange=exchange)
     n0 = sim.n
-    sim.s.vel[:n0] = torch.from_numpy(_initial_velocity(sim.s.gid[:n0].cpu().numpy())).to(dev)
+    vel0 = _initial_velocity(sim.s.gid[:n0].cpu().numpy())
+    if scenario == "object":
+        vel0[sim.s.gid[:n0].cpu().numpy() == NX * NY - 1] = _object_start(NX * NY)[1]
+    sim.s.vel[:n0] = torch.from_numpy(vel0).to(dev)
     snaps = {}
     for k in range(1, STEPS + 1):
         sim.step(o.timestep, o.timestep)
@@ -58,23 +85,31 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,bin_mode,exchange", [(2, 0, "p2p"), (2, 1, "nccl"), (2, 2, "p2p"), (2, 2, "nccl"), (4, 0, "p2p"),
-                                                     (8, 0, "p2p"), (8, 2, "nccl")])
-def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, tmp_path):
+@pytest.mark.parametrize("world,bin_mode,exchange,scenario", [
+    (2, 0, "p2p", "plain"), (2, 1, "nccl", "plain"), (2, 2, "p2p", "plain"), (2, 2, "nccl", "plain"), (2, 0, "p2p", "object"),
+    (2, 1, "nccl", "object"), (4, 0, "p2p", "plain"), (4, 0, "p2p", "object"), (8, 0, "p2p", "plain"), (8, 2, "nccl", "plain")])
+def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     out = str(tmp_path / "slabs.npz")
-    mp.spawn(_worker, args=(world, _free_port(), out, bin_mode, exchange), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, bin_mode, exchange, scenario), nprocs=world, join=True)
     got = np.load(out)
-    p, o, geom = _config()
+    p, o, geom = _config(scenario)
     torch.cuda.set_device(0)
     lib = prs.lib()
     lib.prs_set_stream(None)
     sim = prs.Simulation(p, 64.0, prs.BACKEND_FUSED)
     sim.srand(p.seed)                # main.cpp:929 — the dead draw continues this stream
     sim.init_hex(NX, NY, PITCH, 0.01 * p.max_radius, 5555)
-    sim.set(prs.VELOCITY, _initial_velocity(np.arange(NX * NY)))
+    vel0 = _initial_velocity(np.arange(NX * NY))
+    if scenario == "object":
+        obj_pos, obj_vel = _object_start(NX * NY)
+        pos0 = sim.get(prs.POSITION)
+        pos0[-1] = obj_pos
+        sim.set(prs.POSITION, pos0)
+        vel0[-1] = obj_vel
+    sim.set(prs.VELOCITY, vel0)
     stats = got["stats"]
     assert stats[:, 0].sum() == NX * NY and stats[:, 1].sum() > 0 and stats[:, 2].sum() > 0
     for k in range(1, STEPS + 1):
@@ -84,4 +119,10 @@ def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, tmp_path):
             assert np.array_equal(got[f"vel_{k}"], sim.get(prs.VELOCITY)), k
             assert np.array_equal(got[f"rad_{k}"], sim.get(prs.RADII)), k
             assert np.array_equal(got[f"phase_{k}"], sim.get(prs.PHASE)), k
+            if scenario == "object":       # the object really is the heavy, never-oscillating robot on both sides
+                assert got[f"rad_{k}"][-1] == np.float32(p.min_radius) * np.float32(p.radFactor)
+    if scenario == "object":
+        owners = [int(got[f"owner_{k}"][-1]) for k in (1, STEPS)]
+        if world == 2:
+            assert owners[0] != owners[1], owners    # it changed hands across the cut
     sim.close()
