@@ -32,7 +32,7 @@ def _config(scenario="plain"):
 def _object_start(n_total):
     """the object (robot n_total - 1) is dropped into the middle of the block, just below the cut between the two middle
     slabs, moving up: it ploughs through the lattice and changes owner"""
-    return np.float32([0.031, -0.3]), np.float32([0.0, 3.0])
+    return np.float32([0.031, -0.085]), np.float32([0.0, 3.0])
 
 
 _initial_velocity = multigpu.selfcheck_velocity
@@ -121,8 +121,9 @@ def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_
             assert np.array_equal(got[f"phase_{k}"], sim.get(prs.PHASE)), k
             if scenario == "object":       # the object really is the heavy, never-oscillating robot on both sides
                 assert got[f"rad_{k}"][-1] == np.float32(p.min_radius) * np.float32(p.radFactor)
-    if scenario == "object":
-        owners = [int(got[f"owner_{k}"][-1]) for k in (1, STEPS)]
-        if world == 2:
-            assert owners[0] != owners[1], owners    # it changed hands across the cut
+    if scenario == "object" and world == 2:
+        rows = multigpu.slab_rows(p, NY, PITCH, world)
+        first_owner = int(np.searchsorted(np.array(rows[1:]), multigpu.grid_row_of(_object_start(NX * NY)[0][1:2], p)[0], "right"))
+        owners = [int(got[f"owner_{k}"][-1]) for k in (1, 10, STEPS)]
+        assert any(w != first_owner for w in owners), (first_owner, owners)    # the object changed hands across the cut
     sim.close()
