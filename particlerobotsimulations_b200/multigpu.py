@@ -472,6 +472,47 @@ class SlabSim:
         be.collide(float(dt))
         self.time = np.float32(time + np.float32(dt))
 
+    # ---- re-balancing (slab boundaries by equal robot count) ---------------------------------
+    _REC = (("pos", 2), ("vel", 2), ("rad", 1), ("phase", 1), ("fa", 1), ("fr", 1), ("dead", 1), ("gid", 1), ("hash", 1), ("rng", 12))
+
+    def rebalance(self):
+        """Moves the slab boundaries so that every rank owns about the same number of robots again, and the robots to
+        their new owners with their whole state (the migration record: positions, velocities, radius, phase, force sums,
+        dead flag, global id, generator state).  A COLLECTIVE control-plane operation between two steps — every rank
+        calls it, typically every few thousand steps of a drifting swarm; the data path of a step is unchanged.  The
+        histogram of robots per grid row is summed over the ranks, the cuts are placed on its cumulative count
+        (`balanced_rows`), robots whose row now belongs to another rank are exchanged, and the next step hashes and sorts
+        (ownership is defined by the sorted order).  Results do not depend on the decomposition, so a re-balanced run
+        stays bit-equal to the single-GPU run."""
+        s, n = self.s, self.n
+        y = s.pos[:n, 1].cpu().numpy()
+        rows = balanced_rows(self.p, y, self.world, self.group)
+        row = np.clip(grid_row_of(y, self.p), 0, self.GY - 1)
+        owner = np.searchsorted(np.array(rows[1:-1]), row, "right") if self.world > 1 else np.zeros(n, np.int64)
+        rec = torch.cat([getattr(s, name)[:n].reshape(n, w).view(torch.int32) for name, w in self._REC], 1).cpu().numpy()
+        parts = {int(d): rec[owner == d] for d in np.unique(owner) if int(d) != self.rank}
+        inbox = [None] * self.world
+        dist.all_gather_object(inbox, parts, group=self.group)
+        arrivals = [p_[self.rank] for r_, p_ in enumerate(inbox) if r_ != self.rank and self.rank in p_]
+        new = np.concatenate([rec[owner == self.rank]] + arrivals, 0) if arrivals else rec[owner == self.rank]
+        n_new = int(new.shape[0])
+        if n_new > self.cap:
+            raise RuntimeError(f"rank {self.rank}: {n_new} robots after re-balancing exceed the slab capacity {self.cap}")
+        t = torch.from_numpy(np.ascontiguousarray(new)).to(self.dev)
+        col = 0
+        for name, w in self._REC:
+            dst = getattr(s, name)
+            dst[:n_new] = t[:, col:col + w].contiguous().view(dst.dtype).reshape((n_new,) + tuple(dst.shape[1:]))
+            col += w
+        self.counts[prs.SC_N] = n_new
+        self.R_lo, self.R_hi = rows[self.rank], rows[self.rank + 1]
+        self.be.bind(self)
+        self.sorted_once = False                      # the next step hashes, migrates nothing and sorts
+        if self.ctx is not None:
+            self.ctx.slab = self.be.slab
+            self.ctx.sorted_once = 0
+        return dict(rows=rows, moved_out=int((owner != self.rank).sum()), n=n_new)
+
     # ---- steps with the state held by the HOST (what bench.py's e2e measures at N > 1) -------------------
     def time_host_steps(self, dt, sort_interval, steps):
         """`steps` steps in which this rank's pos / vel / rad come from pinned host memory before the step and go back

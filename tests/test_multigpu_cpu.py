@@ -219,16 +219,31 @@ def _initial_velocity(gid):
     return v
 
 
-def _worker(rank, world, port, out_path, sort_every):
+def _worker(rank, world, port, out_path, sort_every, rebalance_at=()):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     p, o, geom = _config()
-    sim = multigpu.make_hex_slab(p, o, geom, OracleBackend, rank, world, torch.device("cpu"), 5555, 0.01 * p.max_radius)
+    if rebalance_at:
+        # a deliberately lopsided start: the cuts sit far from the equal-count positions, rebalance() has to move them
+        ids = np.arange(NX * NY, dtype=np.int64)
+        pos = multigpu.hex_block_positions(ids, NX, NY, PITCH, 0.01 * p.max_radius, 5555)
+        r = multigpu.grid_row_of(pos[:, 1], p)
+        lo, hi = int(r.min()), int(r.max()) + 1
+        rows = [0] + [lo + max(1, ((hi - lo) * (b + 1)) // (4 * world)) * 1 + b for b in range(world - 1)] + [int(p.gridSize.y)]
+        keep = (r >= rows[rank]) & (r < rows[rank + 1])
+        sim = multigpu.SlabSim(p, o, OracleBackend(p, geom["half"]), rank, world, torch.device("cpu"), pos[keep], ids[keep], rows,
+                               capacity=NX * NY + 64, halo_cap=NX * NY, mig_cap=NX * NY)
+    else:
+        sim = multigpu.make_hex_slab(p, o, geom, OracleBackend, rank, world, torch.device("cpu"), 5555, 0.01 * p.max_radius)
     n0 = sim.n
     sim.s.vel[:n0] = torch.from_numpy(_initial_velocity(sim.s.gid[:n0].numpy()))   # makes robots cross slabs
     snaps = {}
+    moved = 0
     for k in range(1, STEPS + 1):
+        if k in rebalance_at:
+            info = sim.rebalance()
+            moved += info["moved_out"]
         sim.step(o.timestep, sort_every * o.timestep)
         if k in (1, 5, STEPS):
             snaps[k] = sim.gather_global(NX * NY)
@@ -244,7 +259,7 @@ def _worker(rank, world, port, out_path, sort_every):
         np.savez(out_path, centroid=cen, dead=dead, migrated=sim.stats["migrated"], halo=sim.stats["halo"],
                  **{f"{key}_{k}": v for k, g in snaps.items() for key, v in g.items()})
     stats = [None] * world
-    dist.all_gather_object(stats, (sim.n, sim.stats["migrated"], sim.stats["halo"]))
+    dist.all_gather_object(stats, (sim.n, sim.stats["migrated"] + moved, sim.stats["halo"]))
     if rank == 0:
         np.save(out_path + ".stats.npy", np.array(stats))
     dist.barrier()
@@ -273,6 +288,26 @@ def _single_process_reference(sort_every=1):
             snaps[k] = dict(pos=s.get("pos"), vel=s.get("vel"), rad=s.get("rad"), phase=s.get("phase"))
     snaps["dead"] = s.get("dead")
     return snaps, p
+
+
+def test_rebalanced_slabs_match_single_process(tmp_path):
+    """SURVEY.md §8e, slabs by equal robot count: three ranks start from lopsided cuts, rebalance() moves the cuts and the
+    robots (with their whole state) twice during the run — still bit-equal to the single-process run, and balanced."""
+    world = 3
+    out = str(tmp_path / "slabs.npz")
+    mp.spawn(_worker, args=(world, _free_port(), out, 1, (3, 21)), nprocs=world, join=True)
+    got = np.load(out)
+    stats = np.load(out + ".stats.npy")
+    ref, p = _single_process_reference(1)
+    assert stats[:, 0].sum() == NX * NY and stats[:, 1].sum() > NX * NY // 4       # a large part of the swarm changed rank
+    assert stats[:, 0].max() < 1.25 * NX * NY / world, stats[:, 0]                  # and the ranks ended up balanced
+    for k in (1, 5, STEPS):
+        assert np.all(got[f"owner_{k}"] >= 0)
+        assert np.array_equal(got[f"phase_{k}"], ref[k]["phase"])
+        assert np.array_equal(got[f"pos_{k}"], ref[k]["pos"]), k
+        assert np.array_equal(got[f"vel_{k}"], ref[k]["vel"]), k
+        assert np.array_equal(got[f"rad_{k}"], ref[k]["rad"]), k
+    assert np.array_equal(got["dead"], ref["dead"])
 
 
 @pytest.mark.parametrize("world,sort_every", [(2, 1), (3, 1), (2, 4)])

@@ -57,6 +57,16 @@ def _worker(rank, world, port, out_path, bin_mode, exchange, scenario="plain"):
         keep = (r >= rows[rank]) & (r < rows[rank + 1])
         sim = multigpu.SlabSim(p, o, multigpu.CudaBackend(p, geom["half"]), rank, world, dev, pos[keep], ids[keep], rows,
                                capacity=int(NX * NY / world * 1.5) + 4096, halo_cap=16384, mig_cap=4096, exchange=exchange)
+    elif scenario == "rebalance":
+        # lopsided cuts to start with: rebalance() (called twice below) has to move the boundaries and a large part of the swarm
+        ids = np.arange(NX * NY, dtype=np.int64)
+        pos = multigpu.hex_block_positions(ids, NX, NY, PITCH, 0.01 * p.max_radius, 5555)
+        r = multigpu.grid_row_of(pos[:, 1], p)
+        lo, hi = int(r.min()), int(r.max()) + 1
+        rows = [0] + [lo + max(1, ((hi - lo) * (b + 1)) // (4 * world)) + b for b in range(world - 1)] + [int(p.gridSize.y)]
+        keep = (r >= rows[rank]) & (r < rows[rank + 1])
+        sim = multigpu.SlabSim(p, o, multigpu.CudaBackend(p, geom["half"]), rank, world, dev, pos[keep], ids[keep], rows,
+                               capacity=NX * NY + 4096, halo_cap=32768, mig_cap=8192, exchange=exchange)
     else:
         sim = multigpu.make_hex_slab(p, o, geom, multigpu.CudaBackend, rank, world, dev, 5555, 0.01 * p.max_radius, exchange=exchange)
     n0 = sim.n
@@ -65,13 +75,16 @@ def _worker(rank, world, port, out_path, bin_mode, exchange, scenario="plain"):
         vel0[sim.s.gid[:n0].cpu().numpy() == NX * NY - 1] = _object_start(NX * NY)[1]
     sim.s.vel[:n0] = torch.from_numpy(vel0).to(dev)
     snaps = {}
+    moved = 0
     for k in range(1, STEPS + 1):
+        if scenario == "rebalance" and k in (12, 40):
+            moved += sim.rebalance()["moved_out"]
         sim.step(o.timestep, o.timestep)
         if k in (1, 10, STEPS):
             snaps[k] = sim.gather_global(NX * NY)
     sim.check()      # capacity / "crossed two slabs" flags raised on the device
     stats = [None] * world
-    dist.all_gather_object(stats, (sim.n, sim.stats["migrated"], sim.stats["halo"]))
+    dist.all_gather_object(stats, (sim.n, sim.stats["migrated"] + moved, sim.stats["halo"]))
     if rank == 0:
         np.savez(out_path, stats=np.array(stats), **{f"{key}_{k}": v for k, g in snaps.items() for key, v in g.items()})
     sim.close()
@@ -87,7 +100,7 @@ def _free_port():
 
 @pytest.mark.parametrize("world,bin_mode,exchange,scenario", [
     (2, 0, "p2p", "plain"), (2, 1, "nccl", "plain"), (2, 2, "p2p", "plain"), (2, 2, "nccl", "plain"), (2, 0, "p2p", "object"),
-    (2, 1, "nccl", "object"), (4, 0, "p2p", "plain"), (4, 0, "p2p", "object"), (8, 0, "p2p", "plain"), (8, 2, "nccl", "plain")])
+    (2, 1, "nccl", "object"), (2, 0, "p2p", "rebalance"), (4, 0, "p2p", "rebalance"), (4, 0, "p2p", "plain"), (4, 0, "p2p", "object"), (8, 0, "p2p", "plain"), (8, 2, "nccl", "plain")])
 def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -121,6 +134,8 @@ def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_
             assert np.array_equal(got[f"phase_{k}"], sim.get(prs.PHASE)), k
             if scenario == "object":       # the object really is the heavy, never-oscillating robot on both sides
                 assert got[f"rad_{k}"][-1] == np.float32(p.min_radius) * np.float32(p.radFactor)
+    if scenario == "rebalance":
+        assert stats[:, 1].sum() > NX * NY // 8 and stats[:, 0].max() < 1.25 * NX * NY / world, stats     # moved a lot, ended balanced
     if scenario == "object" and world == 2:
         rows = multigpu.slab_rows(p, NY, PITCH, world)
         first_owner = int(np.searchsorted(np.array(rows[1:]), multigpu.grid_row_of(_object_start(NX * NY)[0][1:2], p)[0], "right"))
