@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libprs_oracle.so")
 REFCUDA_PATH = os.path.join(_HERE, "_ref", "libprs_refcuda.so")
 REFHOST_PATH = os.path.join(_HERE, "_ref", "libprs_refhost.so")
+DROPIN_PATH = os.path.join(_HERE, "_ref", "libprs_dropin.so")   # the reference's host class over the PRODUCT library
 
 
 def build():
@@ -121,23 +122,24 @@ class OracleSim:
         return self.view(name).copy()
 
 
-_refhost = None
+_refhost = {}
 
 
-def refhost():
+def refhost(path=None):
     """oracle/_ref/libprs_refhost.so: the reference's own host class (particlebot.cpp) and kernels compiled verbatim,
-    OpenGL buffer objects replaced by device allocations (oracle/gl_stub).  Needs a GPU."""
-    global _refhost
-    if _refhost is None:
-        L = C.CDLL(REFHOST_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    OpenGL buffer objects replaced by device allocations (oracle/gl_stub).  path = DROPIN_PATH: the same class linked
+    against libparticlebot_b200.so instead of the reference's kernels.  Needs a GPU."""
+    path = path or REFHOST_PATH
+    if path not in _refhost:
+        L = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
         sig = {"prsref_identity": (C.c_char_p, []), "prsref_create": (_VP, [_PP, _U]), "prsref_destroy": (None, [_VP]),
                "prsref_reset": (None, [_VP]), "prsref_update": (None, [_VP, _F, _F]), "prsref_time": (_F, [_VP]),
                "prsref_get": (_I, [_VP, _I, _VP, C.c_size_t]), "prsref_set": (None, [_VP, _I, _VP, _I, _I])}
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        _refhost = L
-    return _refhost
+        _refhost[path] = L
+    return _refhost[path]
 
 
 class RefHostSim:
@@ -148,8 +150,8 @@ class RefHostSim:
             "dead": (5, np.int32, 1), "absForce_a": (100, np.float32, 1), "absForce_r": (101, np.float32, 1),
             "hash": (102, np.uint32, 1), "index": (103, np.uint32, 1), "cellStart": (104, np.uint32, 0), "cellEnd": (105, np.uint32, 0)}
 
-    def __init__(self, params, seed):
-        self.L = refhost()
+    def __init__(self, params, seed, library=None):
+        self.L = refhost(library)
         self.params = params
         self.n = int(params.nCells)
         self.h = self.L.prsref_create(C.byref(params), seed)

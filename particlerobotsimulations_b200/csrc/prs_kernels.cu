@@ -748,7 +748,13 @@ void cudaInit(int argc, char **argv) {
 }
 void cudaGLInit(int argc, char **argv) { cudaInit(argc, argv); }
 
-void allocateArray(void **devPtr, size_t size) { PRS_CUDA(cudaMalloc(devPtr, size)); }
+void allocateArray(void **devPtr, size_t size) {
+  /* zero-filled: the reference's host class reads absForce_a / absForce_r (first controller step, `0 * absForce_r[i]` in
+   * the first collide) and its grid arrays before anything wrote them and relies on a fresh process handing out zeroed
+   * device memory; a long-lived process does not, so the assumption is made true here */
+  PRS_CUDA(cudaMalloc(devPtr, size));
+  if (size) PRS_CUDA(cudaMemsetAsync(*devPtr, 0, size, g_prs.stream));
+}
 void freeArray(void *devPtr) {
   g_prs.table.cellStart = nullptr; /* a recycled address must not look like the cached table */
   g_prs.bin.marks_table = nullptr;

@@ -25,9 +25,9 @@ def _need_refhost():
         pytest.skip("oracle/_ref/libprs_refhost.so not built (needs /root/reference at build time)")
 
 
-def _reference_run(name, sort_every_step):
+def _reference_run(name, sort_every_step, library=None):
     p, o = util.cfg(name)
-    ref = ob.RefHostSim(p, p.seed)
+    ref = ob.RefHostSim(p, p.seed, library)
     ref.reset()
     snaps = {0: {k: ref.get(k) for k in ("pos", "rad", "dead", "phase")}}
     si = o.timestep if sort_every_step else o.sort_interval
@@ -119,3 +119,28 @@ def test_committed_goldens_equal_the_reference_class(name, tag, collide_kernel_d
         occ = g[f"occ_{k}"]
         assert np.array_equal(np.nonzero(ref[k]["cellStart"] != 0xFFFFFFFF)[0].astype(np.uint32), occ), k
         assert np.array_equal(ref[k]["cellStart"][occ], g[f"cs_occ_{k}"]) and np.array_equal(ref[k]["cellEnd"][occ], g[f"ce_occ_{k}"]), k
+
+
+@pytest.mark.parametrize("name", util.CFGS)
+@pytest.mark.parametrize("sort_every_step", [False, True])
+def test_reference_class_linked_against_this_library(name, sort_every_step, collide_kernel_default):
+    """THE DROP-IN, EXECUTED: oracle/_ref/libprs_dropin.so is the reference's own
+    particlebot.cpp, verbatim, linked against libparticlebot_b200.so instead of the reference's particlebot_cuda.o — every
+    allocateArray / setParameters / curand_setup / updatePhase / updateRad_light_wave / integrateSystem / calcHash /
+    sortParticlebots / reorderDataAndFindCellStart / collide / calcCOG / updateCol call of the class lands in this library.
+    Same placement, same 100 steps, bit for bit, as the class over its own kernels."""
+    _need_refhost()
+    if not os.path.exists(ob.DROPIN_PATH):
+        pytest.skip("oracle/_ref/libprs_dropin.so not built (needs /root/reference at build time)")
+    prs.lib().prs_set_stream(None)
+    prs.lib().prs_set_world_half_extent(64.0)
+    p, o, ref = _reference_run(name, sort_every_step)
+    _, _, own = _reference_run(name, sort_every_step, ob.DROPIN_PATH)
+    for key in ("pos", "rad", "dead", "phase"):
+        assert np.array_equal(_bits(own[0][key]), _bits(ref[0][key])), ("after reset()", key)
+    for k in STEPS:
+        occ = np.nonzero(ref[k]["cellStart"] != 0xFFFFFFFF)[0]
+        assert np.array_equal(np.nonzero(own[k]["cellStart"] != 0xFFFFFFFF)[0], occ), k
+        assert np.array_equal(own[k]["cellStart"][occ], ref[k]["cellStart"][occ]) and np.array_equal(own[k]["cellEnd"][occ], ref[k]["cellEnd"][occ]), k
+        for key in ("dead", "hash", "index", "pos", "vel", "rad", "phase", "absForce_r", "absForce_a"):
+            assert np.array_equal(_bits(own[k][key]), _bits(ref[k][key])), (k, key)
