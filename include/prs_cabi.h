@@ -110,6 +110,12 @@ int prs_get_collide_tile(void);
 /* 1 = the kernels of prs_fused_step are launched with programmatic dependent launch (each kernel's blocks
  * become resident while the previous kernel drains; griddepcontrol.wait orders the data).  Same results. */
 void prs_set_pdl(int on);
+/* 1 (default) = K1 of the fused binned step handles two robots per thread with 128-bit position / velocity and 64-bit
+ * scalar accesses (swarms of >= 65536 robots with 16-byte aligned arrays); 0 = one robot per thread.  Same results. */
+void prs_set_k1_x2(int on);
+/* 1 (default) = on binned sort steps of plain swarms collide takes the slot range of a stencil row from the dense start table
+ * the scan writes next to cellStart / cellEnd (two words per row instead of six); 0 = always from cellStart / cellEnd.  Same results. */
+void prs_set_collide_dense(int on);
 /* steps without a sort: swarms of up to max_robots run controller+integrate and the gather into the sorted
  * copy as ONE kernel (one launch less per step; default 65536, 0 = never).  Same bits. */
 void prs_set_fuse_gather_max(unsigned max_robots);

@@ -131,7 +131,7 @@ SIGNATURES = {
     "prs_set_collide_warp_max": (None, [_U]),
     "prs_set_collide_tile": (None, [_I]), "prs_get_collide_tile": (_I, []),
     "prs_set_patch_rows": (None, [_U]), "prs_patch_stats": (None, [_I, _VP]),
-    "prs_set_pdl": (None, [_I]), "prs_get_pdl": (_I, []),
+    "prs_set_pdl": (None, [_I]), "prs_get_pdl": (_I, []), "prs_set_k1_x2": (None, [_I]), "prs_set_collide_dense": (None, [_I]),
     "prs_set_fuse_gather_max": (None, [_U]),
     "prs_launch_count": (C.c_ulonglong, [_I]),
     "prs_stage_timing": (None, [_I]), "prs_stage_times": (None, [_VP, _VP]),

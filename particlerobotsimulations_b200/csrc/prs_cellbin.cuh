@@ -30,6 +30,16 @@
 
 namespace prs_bin {
 
+/* optional DENSE start table for collide's fresh-table steps: dense[c] = number of robots with a key below c for EVERY cell
+ * (the reference's cellStart says 0xffffffff for an empty cell, so a stencil row's slot range needs the first and the last
+ * non-empty of its five cells: 25 + 5 table words per robot; with the dense table it is dense[first cell], dense[last cell + 1]:
+ * 10 words, one round trip).  `live` = per scan tile "a robot hashed into this tile or into one within `dil` tiles of it":
+ * the tiles collide can look into this step; the others keep stale dense entries that nobody reads. */
+struct DenseArgs {
+  uint32_t *dense = nullptr, *live = nullptr;
+  uint32_t dil = 0;
+};
+
 /* optional work list for k_collide_patch: patches of PATCH_W x PH cells that hold robots */
 struct PatchListArgs {
   uint32_t *epoch_of = nullptr, *list = nullptr, *count = nullptr;
@@ -70,11 +80,31 @@ __device__ __forceinline__ void load_counts(const uint32_t *cellCount, uint32_t 
 /* sums of the tiles of 4096 cells (no atomics: thousands of same-address atomics — a "last block
  * done" counter, per-robot tile sums from K1, a running maximum — each cost 10-100 us in L2) */
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch, const uint32_t *marks = nullptr) {
+k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch, const uint32_t *marks = nullptr,
+                 const DenseArgs dn = DenseArgs()) {
   prs::pdl_sync();
   __shared__ uint32_t s_sum[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (marks && !tile_marked(marks, blockIdx.x)) { /* no robot hashed into this tile in this step: nothing to read */
+  bool own = true;
+  if (marks && dn.live) {
+    /* liveness for the dense table: this tile or one within dil tiles (cyclically: the hash wraps) was hashed into.  All mark
+     * words are requested at once (one round trip), the first warp decides */
+    uint32_t mine = marks[blockIdx.x * MARK_WAYS + lane], around = 0u;
+    if (warp == 0) {
+      for (uint32_t d = 1; d <= dn.dil; d++) {
+        const uint32_t up = (blockIdx.x + d) % gridDim.x, down = (blockIdx.x + gridDim.x - d % gridDim.x) % gridDim.x;
+        around |= marks[up * MARK_WAYS + lane] | marks[down * MARK_WAYS + lane];
+      }
+    }
+    own = __any_sync(0xffffffffu, mine != 0u);
+    if (warp == 0) {
+      const bool alive = __any_sync(0xffffffffu, (mine | around) != 0u);
+      if (lane == 0) dn.live[blockIdx.x] = alive ? 1u : 0u;
+    }
+  } else if (marks) {
+    own = tile_marked(marks, blockIdx.x);
+  }
+  if (!own) { /* no robot hashed into this tile in this step: nothing to read */
     if (tid == 0) scratch[4 + blockIdx.x] = 0u;
     return;
   }
@@ -132,7 +162,7 @@ template <bool SELF_PREFIX>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
              uint32_t *scratch, uint32_t slot_offset, uint32_t *marks = nullptr, uint32_t *prev_marks = nullptr,
-             const PatchListArgs pl = PatchListArgs()) {
+             const PatchListArgs pl = PatchListArgs(), const DenseArgs dn = DenseArgs()) {
   prs::pdl_sync();
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,7 +172,8 @@ k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart,
      * tile was also empty in the previous step its cellStart words are 0xffffffff already and nothing is
      * touched; if it held robots then, only the empty markers are written.  (A world much larger than the
      * swarm — S1: 4 M cells, a third of the tiles occupied — otherwise pays for the whole table.) */
-    const bool now = tile_marked(marks, blockIdx.x);
+    /* with a dense table the tiles AROUND the hashed ones are processed too (their dense entries are read by collide) */
+    const bool now = dn.live ? dn.live[blockIdx.x] != 0u : tile_marked(marks, blockIdx.x);
     const uint32_t before_ = prev_marks[blockIdx.x];
     __syncthreads(); /* every thread has read the words before they are rewritten */
     if (tid < MARK_WAYS) marks[blockIdx.x * MARK_WAYS + tid] = 0u;
@@ -194,12 +225,24 @@ k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart,
 #pragma unroll
   for (int w = 0; w < SCAN_THREADS / 32; w++) before += (w < (int)warp) ? s_warp[w] : 0u;
   uint32_t run = tile_offset + before + (inc - sum);
-  uint32_t st[SCAN_ITEMS];
+  uint32_t st[SCAN_ITEMS], ds[SCAN_ITEMS];
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; i++) {
     st[i] = cnt[i] ? run : 0xffffffffu;
+    ds[i] = run;
     if (cnt[i] && c0 + i < C) cellEnd[c0 + i] = run + cnt[i]; /* empty cells keep their stale cellEnd (reference) */
     run += cnt[i];
+  }
+  if (dn.dense) {
+    if (c0 + SCAN_ITEMS <= C) {
+      *reinterpret_cast<uint4 *>(dn.dense + c0) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+      *reinterpret_cast<uint4 *>(dn.dense + c0 + 4) = make_uint4(ds[4], ds[5], ds[6], ds[7]);
+      if (c0 + SCAN_ITEMS == C) dn.dense[C] = run; /* one past the last cell: the robot count */
+    } else {
+#pragma unroll
+      for (int i = 0; i < SCAN_ITEMS; i++)
+        if (c0 + i <= C) dn.dense[c0 + i] = ds[i];
+    }
   }
   if (c0 + SCAN_ITEMS <= C) {
     *reinterpret_cast<uint4 *>(cellStart + c0) = make_uint4(st[0], st[1], st[2], st[3]);

@@ -12,6 +12,7 @@
 /* guard state of the binned (counting-sort) route of the fused step, see prs_fused_step */
 struct PrsBinState {
   uint32_t *cellCount = nullptr, *scratch = nullptr;
+  uint32_t *dense = nullptr, *live = nullptr; /* dense start table (numCells + 1 words) and per-tile liveness, see prs_cellbin.cuh */
   uint32_t *marks = nullptr;     /* per scan tile: a robot hashed into it this step / the previous step (prs_cellbin.cuh) */
   const void *marks_table = nullptr; /* the cellStart array the previous-step marks describe */
   unsigned marks_cells = 0, marks_generation = 0;
@@ -54,6 +55,8 @@ struct PrsHostState {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t k1_event = nullptr;
   bool k1_event_armed = false;
+  int collide_dense = 1;              /* binned sort steps of plain swarms: collide reads the dense start table of the scan */
+  int k1_x2 = 1;                      /* K1 of the fused binned step: two robots per thread, vector accesses */
   int pdl = 1;                        /* 1: the fused step's kernels are launched with programmatic dependent launch */
   int collide_tile = 0;               /* 1: sort steps of plain large swarms use k_collide_patch (TMA-staged patches, pairs evaluated
                                          once; bit-equal, measured slower: profiles/r2_collide_patch.md) */

@@ -344,6 +344,72 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
   }
 }
 
+/* K1 of the fused binned step with TWO robots per thread and vector accesses (north_star (1): 128-bit coalesced loads and
+ * stores of positions and velocities, 64-bit ones of radius / phase / |force| / dead flag / key / ticket): the kernel is a
+ * chain of memory round trips at 2^20 robots, and a thread that keeps two robots' loads in flight walks that chain half as
+ * often.  Per-robot arithmetic is controller_one / integrate_one / cell_of as above — same bits.  Needs 16-byte aligned
+ * pos / vel and 8-byte aligned scalar arrays (the launcher checks); an odd last robot is handled by the scalar tail. */
+__global__ void __launch_bounds__(256)
+k_control_integrate_hash_x2(float4 *__restrict__ pos, float4 *__restrict__ vel, float2 *__restrict__ rad,
+                            const float2 *__restrict__ phase, const float2 *__restrict__ fa, const float2 *__restrict__ fr,
+                            const int2 *__restrict__ dead, uint2 *__restrict__ hash, uint2 *__restrict__ ticket, float time, float dt,
+                            int run_controller, uint32_t n, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ tileMark) {
+  prs::pdl_sync();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i0 = 2u * t;
+  if (i0 >= n) return;
+  const bool cc = c_prm.p.constrained_contraction != 0;
+  if (i0 + 1u >= n) { /* odd tail: one robot, scalar accesses */
+    float2 p = reinterpret_cast<float2 *>(pos)[i0], v = reinterpret_cast<float2 *>(vel)[i0];
+    float r = reinterpret_cast<float *>(rad)[i0];
+    if (run_controller && !reinterpret_cast<const int *>(dead)[i0]) {
+      const float ph = reinterpret_cast<const float *>(phase)[i0], f_r = reinterpret_cast<const float *>(fr)[i0];
+      const float rn = cc ? controller_one<true>(r, ph, f_r, reinterpret_cast<const float *>(fa)[i0], time, dt)
+                          : controller_one<false>(r, ph, f_r, 0.0f, time, dt);
+      if (rn != r) { reinterpret_cast<float *>(rad)[i0] = rn; r = rn; }
+    }
+    const float2 v0 = v;
+    integrate_one(p, v, r, dt);
+    reinterpret_cast<float2 *>(pos)[i0] = p;
+    if (v.x != v0.x || v.y != v0.y) reinterpret_cast<float2 *>(vel)[i0] = v;
+    const int2 g = cell_of(p.x, p.y);
+    const uint32_t h = cell_hash(g.x, g.y);
+    reinterpret_cast<uint32_t *>(hash)[i0] = h;
+    reinterpret_cast<uint32_t *>(ticket)[i0] = atomicAdd(&cellCount[h], 1u);
+    if (tileMark) tileMark[(h / prs_bin::SCAN_TILE) * prs_bin::MARK_WAYS + (blockIdx.x % prs_bin::MARK_WAYS)] = 1u;
+    return;
+  }
+  const float4 P = pos[t], V = vel[t];
+  float2 R = rad[t];
+  float2 p0 = make_float2(P.x, P.y), p1 = make_float2(P.z, P.w), v0 = make_float2(V.x, V.y), v1 = make_float2(V.z, V.w);
+  if (run_controller) {
+    const int2 D = dead[t];
+    const float2 PH = phase[t], FR = fr[t];
+    const float2 FA = cc ? fa[t] : make_float2(0.0f, 0.0f);
+    const float2 R_in = R;
+    if (!D.x) R.x = cc ? controller_one<true>(R.x, PH.x, FR.x, FA.x, time, dt) : controller_one<false>(R.x, PH.x, FR.x, 0.0f, time, dt);
+    if (!D.y) R.y = cc ? controller_one<true>(R.y, PH.y, FR.y, FA.y, time, dt) : controller_one<false>(R.y, PH.y, FR.y, 0.0f, time, dt);
+    if (R.x != R_in.x || R.y != R_in.y) rad[t] = R;
+  }
+  integrate_one(p0, v0, R.x, dt);
+  integrate_one(p1, v1, R.y, dt);
+  pos[t] = make_float4(p0.x, p0.y, p1.x, p1.y);
+  if (v0.x != V.x || v0.y != V.y || v1.x != V.z || v1.y != V.w) vel[t] = make_float4(v0.x, v0.y, v1.x, v1.y);
+  const int2 g0 = cell_of(p0.x, p0.y), g1 = cell_of(p1.x, p1.y);
+  const uint32_t h0 = cell_hash(g0.x, g0.y), h1 = cell_hash(g1.x, g1.y);
+  hash[t] = make_uint2(h0, h1);
+  const uint32_t k0 = atomicAdd(&cellCount[h0], 1u), k1 = atomicAdd(&cellCount[h1], 1u);
+  ticket[t] = make_uint2(k0, k1);
+  if (tileMark) {
+    const uint32_t tile0 = h0 / prs_bin::SCAN_TILE, tile1 = h1 / prs_bin::SCAN_TILE;
+    const unsigned act = __activemask();
+    const uint32_t left = __shfl_up_sync(act, tile1, 1);
+    const uint32_t way = blockIdx.x % prs_bin::MARK_WAYS;
+    if ((threadIdx.x & 31u) == 0 || left != tile0) tileMark[tile0 * prs_bin::MARK_WAYS + way] = 1u;
+    if (tile1 != tile0) tileMark[tile1 * prs_bin::MARK_WAYS + way] = 1u;
+  }
+}
+
 /* Steps WITHOUT a sort, small swarms: K1 and the gather in ONE launch.  Thread k owns sorted slot k, runs
  * controller + integrate for the robot in that slot (every robot sits in exactly one slot; same arithmetic
  * as k_control_integrate_hash) and writes both its state and its packed sorted record.  One launch less per
@@ -939,6 +1005,11 @@ void prs_patch_stats(int on, unsigned *out) {
   T.stats = on ? T.stats_buf : nullptr;
 }
 void prs_set_pdl(int on) { g_prs.pdl = on ? 1 : 0; }
+/* 1 (default): K1 of the fused binned step handles two robots per thread with 128 / 64-bit accesses; 0: one robot per thread */
+void prs_set_k1_x2(int on) { g_prs.k1_x2 = on ? 1 : 0; }
+/* 1 (default): on binned sort steps of plain swarms collide finds its stencil rows in the dense start table the scan writes (10 table
+ * words per robot instead of 30); 0: always through cellStart / cellEnd */
+void prs_set_collide_dense(int on) { g_prs.collide_dense = on ? 1 : 0; }
 
 /* ---- host-buffer step (Particlebot::updateHost): asynchronous copies around prs_fused_step ----
  * prs_h2d_async: pinned host -> device on the launching stream (counts as an upload: the binned route re-earns
@@ -1058,6 +1129,12 @@ static void bin_ensure(uint32_t n, uint32_t C) {
     PRS_CUDA(cudaMalloc(&B.marks, (tiles * prs_bin::MARK_WAYS + tiles) * 4));
     PRS_CUDA(cudaMemsetAsync(B.marks, 0, (tiles * prs_bin::MARK_WAYS + tiles) * 4, g_prs.stream));
     B.marks_table = nullptr;
+    /* dense start table (collide's fresh-table steps) + per-tile liveness */
+    if (B.dense) { PRS_CUDA(cudaFree(B.dense)); PRS_CUDA(cudaFree(B.live)); }
+    PRS_CUDA(cudaMalloc(&B.dense, ((size_t)C + 4) * 4));
+    PRS_CUDA(cudaMalloc(&B.live, tiles * 4));
+    PRS_CUDA(cudaMemsetAsync(B.dense, 0, ((size_t)C + 4) * 4, g_prs.stream));
+    PRS_CUDA(cudaMemsetAsync(B.live, 0, tiles * 4, g_prs.stream));
     B.cap_cells = C;
   }
   ensure_sort_workspace(n, 1, 4096);
@@ -1170,21 +1247,36 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     {
       StageScope t(PRS_STAGE_K1);
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
-      PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
-                     b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
-                     (const uint32_t *)nullptr, B.cellCount, marks, 0u, 0xffffffffu, 0u);
+      const uintptr_t al = (uintptr_t)b->pos | (uintptr_t)b->vel | (((uintptr_t)b->rad | (uintptr_t)b->phase | (uintptr_t)b->absForce_a |
+                            (uintptr_t)b->absForce_r | (uintptr_t)b->dead | (uintptr_t)b->hash | (uintptr_t)ticket) << 1);
+      if (g_prs.k1_x2 && (al & 15u) == 0 && n >= 65536u) {
+        PRS_LAUNCH_PDL(k_control_integrate_hash_x2, div_up(div_up(n, 2), 256), 256, (float4 *)b->pos, (float4 *)b->vel, (float2 *)b->rad,
+                       (const float2 *)b->phase, (const float2 *)b->absForce_a, (const float2 *)b->absForce_r, (const int2 *)b->dead,
+                       (uint2 *)b->hash, (uint2 *)ticket, time, dt, run_controller, n, B.cellCount, marks);
+      } else {
+        PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
+                       b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
+                       (const uint32_t *)nullptr, B.cellCount, marks, 0u, 0xffffffffu, 0u);
+      }
       k1_done();
+    }
+    /* dense start table for collide (plain swarms, thread-per-robot kernel): the scan writes it for the tiles collide can reach */
+    const bool use_dense = g_prs.collide_dense && !patch && !need_fa && g_prs.h_prm.p.nDead != -1 && n > g_prs.collide_warp_max;
+    prs_bin::DenseArgs dn;
+    if (use_dense) {
+      dn.dense = B.dense; dn.live = B.live;
+      dn.dil = (2u * g_prs.h_prm.p.gridSize.x + 3u + prs_bin::SCAN_TILE - 1u) / prs_bin::SCAN_TILE;
     }
     {
       StageScope t(PRS_STAGE_SORT);
-      PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch, (const uint32_t *)marks);
+      PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch, (const uint32_t *)marks, dn);
       if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u, marks, prev_marks, pl);
+                       B.scratch, 0u, marks, prev_marks, pl, dn);
       } else {
         PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u, marks, prev_marks, pl);
+                       B.scratch, 0u, marks, prev_marks, pl, dn);
       }
       PRS_LAUNCH_PDL(prs_bin::k_cell_scatter, div_up(n, 256), 256, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
     }
@@ -1200,7 +1292,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       StageScope t(PRS_STAGE_COLLIDE);
       prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
       if (patch) launch_collide_patch((float2 *)b->vel, b->absForce_r, in.pr, in.vel, b->cellStart, b->cellEnd, dt);
-      else prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa);
+      else prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa, 0u,
+                                (const uint32_t *)nullptr, 0, (const uint32_t *)nullptr, use_dense ? (const uint32_t *)B.dense : nullptr);
     }
     /* fullest cell of this sort -> pinned host memory (nobody touches the two words before the next step's
      * memset); issued after collide so that the kernels of the step stay adjacent in the stream */

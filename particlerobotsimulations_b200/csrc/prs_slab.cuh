@@ -467,14 +467,14 @@ void prs_slab_sort(const prs_slab *s) {
       PRS_LAUNCH_PDL(k_slab_tickets, div_up(s->cap, 256), 256, *s, B.cellCount, w.vals[0]);
     }
     PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, (const uint32_t *)(B.cellCount + c_lo), cells, B.scratch,
-                   (const uint32_t *)nullptr);
+                   (const uint32_t *)nullptr, prs_bin::DenseArgs());
     if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
       PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs());
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), prs_bin::DenseArgs());
     } else {
       PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
       PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs());
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), prs_bin::DenseArgs());
     }
     PRS_LAUNCH_PDL(k_slab_scatter, div_up(s->cap, 256), 256, *s, (const uint32_t *)w.vals[0], w.vals[1]);
     g_prs.slab_table_fresh = true; /* consumed by this step's gather and cell_table */

@@ -15,6 +15,8 @@ ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--evolve", type=int, default=260)
 ap.add_argument("--pitch", type=float, default=None)
 ap.add_argument("--only", type=int, default=None, help="only tile = this value")
+ap.add_argument("--k1x2", type=int, default=1, help="K1 with two robots per thread (1) or one (0)")
+ap.add_argument("--dense", type=int, default=1, help="collide reads the dense start table (1) or cellStart / cellEnd (0)")
 a = ap.parse_args()
 lib = prs.lib()
 torch.cuda.set_device(0)
@@ -25,6 +27,8 @@ out = {}
 for tile in ([a.only] if a.only is not None else [0, 1]):
     lib.prs_set_collide_tile(tile)
     lib.prs_set_patch_rows(a.rows)
+    lib.prs_set_k1_x2(a.k1x2)
+    lib.prs_set_collide_dense(a.dense)
     p, o, geom = bench.swarm_config(prs, a.log2, pitch=a.pitch)
     sim = prs.Simulation(p, geom["half"], prs.BACKEND_FUSED)
     sim.init_hex(geom["nx"], geom["ny"], geom["pitch"], bench.JITTER_FRAC * p.max_radius, bench.SEED)

@@ -49,6 +49,8 @@ def collide_kernel_default():
     L.prs_set_collide_warp_max(16384)
     L.prs_set_collide_tile(0)
     L.prs_set_pdl(1)
+    L.prs_set_k1_x2(1)
+    L.prs_set_collide_dense(1)
     L.prs_set_fuse_gather_max(65536)
     L.prs_bin_set_mode(0)
     yield

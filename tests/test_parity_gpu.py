@@ -44,7 +44,12 @@ def collide_kernel(request):
     L.prs_set_pdl(0 if request.param == "thread-per-robot-nopdl" else 1)   # programmatic dependent launch: on by default
     # steps without a sort: K1 + gather as one kernel (default) / as two kernels in the second variant
     L.prs_set_fuse_gather_max(0 if request.param == "thread-per-robot-nopdl" else 65536)
+    # K1 of the fused binned step: two robots per thread with vector accesses (default) / one robot per thread in the second variant
+    L.prs_set_k1_x2(0 if request.param == "thread-per-robot-nopdl" else 1)
+    L.prs_set_collide_dense(0 if request.param == "thread-per-robot-nopdl" else 1)     # dense start table of the binned scan (default on)
     yield request.param
+    L.prs_set_k1_x2(1)
+    L.prs_set_collide_dense(1)
     L.prs_set_fuse_gather_max(65536)
     L.prs_set_collide_warp_max(16384)
     L.prs_set_collide_tile(TILE_DEFAULT)
