@@ -466,15 +466,18 @@ void prs_slab_sort(const prs_slab *s) {
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
       PRS_LAUNCH_PDL(k_slab_tickets, div_up(s->cap, 256), 256, *s, B.cellCount, w.vals[0]);
     }
+    /* dense start table over the owned rows' cells (same slot offset as the table): read by the collide of the interior rows */
+    prs_bin::DenseArgs dn;
+    if (g_prs.collide_dense) dn.dense = B.dense + c_lo;
     PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, (const uint32_t *)(B.cellCount + c_lo), cells, B.scratch,
                    (const uint32_t *)nullptr, prs_bin::DenseArgs());
     if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
       PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), prs_bin::DenseArgs());
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), dn);
     } else {
       PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
       PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), prs_bin::DenseArgs());
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), dn);
     }
     PRS_LAUNCH_PDL(k_slab_scatter, div_up(s->cap, 256), 256, *s, (const uint32_t *)w.vals[0], w.vals[1]);
     g_prs.slab_table_fresh = true; /* consumed by this step's gather and cell_table */
@@ -535,8 +538,10 @@ static void slab_collide_band(const prs_slab *s, float dt, int band) {
   const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
   prs::PackedLayout in{(const float4 *)s->sortedPR, (const float2 *)s->sortedVel};
   const unsigned span = (band >= 2) ? min(s->halo_cap, s->cap) : s->cap; /* an edge band is what goes out as a halo: <= halo_cap slots */
+  /* interior rows right after a binned sort: their stencils stay inside the owned rows, whose dense start table the scan has written */
+  const uint32_t *dense = (band == 1 && g_prs.collide_dense && g_prs.slab_binned && g_prs.slab_table_fresh) ? g_prs.bin.dense : nullptr;
   prs_launch_collide_t((float2 *)s->vel, s->absForce_a, s->absForce_r, in, s->cellStart, s->cellEnd, s->halo_cap + span, dt,
-                       need_fa, s->halo_cap, s->counts + PRS_SC_N, band, s->index_sorted - s->halo_cap);
+                       need_fa, s->halo_cap, s->counts + PRS_SC_N, band, s->index_sorted - s->halo_cap, dense);
 }
 void prs_slab_collide(const prs_slab *s, float dt) {
   slab_check(s);
