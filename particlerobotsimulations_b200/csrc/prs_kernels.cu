@@ -353,11 +353,15 @@ __global__ void __launch_bounds__(256)
 k_control_integrate_hash_x2(float4 *__restrict__ pos, float4 *__restrict__ vel, float2 *__restrict__ rad,
                             const float2 *__restrict__ phase, const float2 *__restrict__ fa, const float2 *__restrict__ fr,
                             const int2 *__restrict__ dead, uint2 *__restrict__ hash, uint2 *__restrict__ ticket, float time, float dt,
-                            int run_controller, uint32_t n, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ tileMark) {
+                            int run_controller, uint32_t n, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ tileMark,
+                            const uint32_t *__restrict__ n_dev, uint32_t row_lo, uint32_t row_hi, uint32_t log2_gx) {
   prs::pdl_sync();
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i0 = 2u * t;
+  if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
   if (i0 >= n) return;
+  /* slab ranks: a robot whose new row left [row_lo, row_hi) migrates and takes its ticket where it arrives */
+  auto take = [&](uint32_t h) { const uint32_t row = h >> log2_gx; return (row >= row_lo && row < row_hi) ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu; };
   const bool cc = c_prm.p.constrained_contraction != 0;
   if (i0 + 1u >= n) { /* odd tail: one robot, scalar accesses */
     float2 p = reinterpret_cast<float2 *>(pos)[i0], v = reinterpret_cast<float2 *>(vel)[i0];
@@ -375,7 +379,7 @@ k_control_integrate_hash_x2(float4 *__restrict__ pos, float4 *__restrict__ vel, 
     const int2 g = cell_of(p.x, p.y);
     const uint32_t h = cell_hash(g.x, g.y);
     reinterpret_cast<uint32_t *>(hash)[i0] = h;
-    reinterpret_cast<uint32_t *>(ticket)[i0] = atomicAdd(&cellCount[h], 1u);
+    reinterpret_cast<uint32_t *>(ticket)[i0] = take(h);
     if (tileMark) tileMark[(h / prs_bin::SCAN_TILE) * prs_bin::MARK_WAYS + (blockIdx.x % prs_bin::MARK_WAYS)] = 1u;
     return;
   }
@@ -398,7 +402,7 @@ k_control_integrate_hash_x2(float4 *__restrict__ pos, float4 *__restrict__ vel, 
   const int2 g0 = cell_of(p0.x, p0.y), g1 = cell_of(p1.x, p1.y);
   const uint32_t h0 = cell_hash(g0.x, g0.y), h1 = cell_hash(g1.x, g1.y);
   hash[t] = make_uint2(h0, h1);
-  const uint32_t k0 = atomicAdd(&cellCount[h0], 1u), k1 = atomicAdd(&cellCount[h1], 1u);
+  const uint32_t k0 = take(h0), k1 = take(h1);
   ticket[t] = make_uint2(k0, k1);
   if (tileMark) {
     const uint32_t tile0 = h0 / prs_bin::SCAN_TILE, tile1 = h1 / prs_bin::SCAN_TILE;
@@ -1252,7 +1256,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       if (g_prs.k1_x2 && (al & 15u) == 0 && n >= 65536u) {
         PRS_LAUNCH_PDL(k_control_integrate_hash_x2, div_up(div_up(n, 2), 256), 256, (float4 *)b->pos, (float4 *)b->vel, (float2 *)b->rad,
                        (const float2 *)b->phase, (const float2 *)b->absForce_a, (const float2 *)b->absForce_r, (const int2 *)b->dead,
-                       (uint2 *)b->hash, (uint2 *)ticket, time, dt, run_controller, n, B.cellCount, marks);
+                       (uint2 *)b->hash, (uint2 *)ticket, time, dt, run_controller, n, B.cellCount, marks, (const uint32_t *)nullptr, 0u,
+                       0xffffffffu, 0u);
       } else {
         PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                        b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,

@@ -420,9 +420,18 @@ void prs_slab_k1(const prs_slab *s, float time, float dt, int do_hash) {
     if (g_prs.slab_binned) {
       bin_ensure(s->cap, g_prs.h_prm.p.numCells);
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
-      PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
-                     s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, g_prs.sort_ws.vals[0], time, dt, run_controller, s->cap,
-                     (const uint32_t *)(s->counts + PRS_SC_N), B.cellCount, (uint32_t *)nullptr, s->row_lo, s->row_hi, slab_log2_gx());
+      const uintptr_t al = (uintptr_t)s->pos | (uintptr_t)s->vel | (((uintptr_t)s->rad | (uintptr_t)s->phase | (uintptr_t)s->absForce_a |
+                            (uintptr_t)s->absForce_r | (uintptr_t)s->dead | (uintptr_t)s->hash | (uintptr_t)g_prs.sort_ws.vals[0]) << 1);
+      if (g_prs.k1_x2 && (al & 15u) == 0) {
+        PRS_LAUNCH_PDL(k_control_integrate_hash_x2, div_up(div_up(s->cap, 2), 256), 256, (float4 *)s->pos, (float4 *)s->vel, (float2 *)s->rad,
+                       (const float2 *)s->phase, (const float2 *)s->absForce_a, (const float2 *)s->absForce_r, (const int2 *)s->dead,
+                       (uint2 *)s->hash, (uint2 *)g_prs.sort_ws.vals[0], time, dt, run_controller, s->cap, B.cellCount, (uint32_t *)nullptr,
+                       (const uint32_t *)(s->counts + PRS_SC_N), s->row_lo, s->row_hi, slab_log2_gx());
+      } else {
+        PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
+                       s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, g_prs.sort_ws.vals[0], time, dt, run_controller, s->cap,
+                       (const uint32_t *)(s->counts + PRS_SC_N), B.cellCount, (uint32_t *)nullptr, s->row_lo, s->row_hi, slab_log2_gx());
+      }
       g_prs.slab_tickets = true;
     } else {
       PRS_LAUNCH_PDL((k_control_integrate_hash<true, false>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,

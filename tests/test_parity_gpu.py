@@ -395,6 +395,37 @@ def test_integrate_controller_phase_noise(name):
     assert np.array_equal(words[:, :7], want[:, :7])
 
 
+def test_device_min_light_distance_vs_glibc_powf_loop():
+    """The fused path takes min_i |light - p_i| on the device (correctly rounded sqrt of dx*dx + dy*dy, no FMA); the reference's
+    host loop (particlebot.cpp:214-228) evaluates powf(powf(dx,2) + powf(dy,2), 0.5f) with glibc, whose powf is not correctly
+    rounded (documented to 0.82 ulp).  Over 300 random swarms: never more than one ulp apart, and the rate of last-bit
+    differences is recorded (it was 0 on every swarm tried; a non-zero rate would shift all phases by an ulp on such a swarm —
+    DESIGN.md section 4 states the caveat; the per-call backends keep the host loop)."""
+    libm = C.CDLL("libm.so.6")
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    L = prs.lib()
+    p, o = util.cfg("example")
+    rng = np.random.default_rng(7)
+    n, worst, differ = 512, 0, 0
+    d_out = Dev(np.zeros(16, np.float32))
+    for trial in range(300):
+        p.light_x, p.light_y = [float(v) for v in rng.uniform(-60, 60, 2).astype(np.float32)]
+        L.setParameters(C.byref(p))
+        pos = rng.uniform(-50, 50, (n, 2)).astype(np.float32)
+        d_pos = Dev(pos)
+        L.prs_min_light_distance(d_pos.ptr, n, d_out.ptr)
+        got = d_out.get()[0]
+        lx, ly = np.float32(p.light_x), np.float32(p.light_y)
+        want = min(libm.powf(np.float32(libm.powf(lx - x, 2.0) + np.float32(libm.powf(ly - y, 2.0))), 0.5) for x, y in pos)
+        ulps = abs(int(np.float32(got).view(np.int32)) - int(np.float32(want).view(np.int32)))
+        worst = max(worst, ulps)
+        differ += ulps != 0
+        d_pos.free()
+    assert worst <= 1, worst
+    assert differ <= 3, f"{differ} of 300 swarms differ in the last bit of min_d"
+
+
 def test_shadow_phase_modes():
     for name, mode in (("example_obstacle", 1), ("example_obstacle", 2), ("example_gap", 1)):
         p, o = util.cfg(name)
