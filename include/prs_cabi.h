@@ -215,6 +215,8 @@ typedef struct {
   unsigned cap, halo_cap, mig_cap;
   unsigned row_lo, row_hi, halo_rows;
   int has_dn, has_up;  /* neighbours below (rank - 1) / above (rank + 1) exist */
+  int wrap;            /* 1: the slabs form a RING in the row index (the cell hash wraps around the grid): the first
+                          slab's lower neighbour is the last one and vice versa; rows are compared cyclically */
 } prs_slab;
 /* exchange buffers are uint32 arrays: word 0 = record count, then structure-of-arrays records */
 size_t prs_slab_mig_words(unsigned mig_cap);

@@ -80,7 +80,7 @@ class Slab(C.Structure):
         "pos", "vel", "rad", "phase", "absForce_a", "absForce_r", "dead", "gid", "rng", "hash", "scratch",
         "sortedPR", "sortedVel", "hash_cat", "index_sorted", "cellStart", "cellEnd", "counts", "lists")] + [
         (n, C.c_uint) for n in ("cap", "halo_cap", "mig_cap", "row_lo", "row_hi", "halo_rows")] + [
-        ("has_dn", C.c_int), ("has_up", C.c_int)]
+        ("has_dn", C.c_int), ("has_up", C.c_int), ("wrap", C.c_int)]
 
 
 ALLREDUCE_MIN_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)

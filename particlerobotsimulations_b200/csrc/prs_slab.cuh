@@ -81,7 +81,15 @@ __global__ void __launch_bounds__(256) k_slab_select(prs_slab s, uint32_t *__res
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t row = s.hash[i] >> log2_gx;
-  const bool dn = row < s.row_lo, up = row >= s.row_hi;
+  bool dn = row < s.row_lo, up = row >= s.row_hi;
+  if (s.wrap && (dn || up)) {
+    /* ring of slabs: the row lies on the side it is cyclically nearer to (a robot leaving the top row of the grid re-enters at
+     * row 0, which belongs to the first slab: "up" from the last one) */
+    const uint32_t gy_mask = c_prm.p.gridSize.y - 1u;
+    const uint32_t d_up = (row - s.row_hi) & gy_mask, d_dn = (s.row_lo - 1u - row) & gy_mask;
+    up = d_up <= d_dn;
+    dn = !up;
+  }
   s.scratch[i] = (dn || up) ? 1u : 0u;
   if (!(dn || up)) return;
   if ((dn && !s.has_dn) || (up && !s.has_up)) { atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_LEFT_WORLD); s.scratch[i] = 0u; return; }
@@ -179,9 +187,15 @@ __device__ __forceinline__ void slab_drift_check(const prs_slab &s, float y) {
   const uint32_t gy = c_prm.p.gridSize.y;
   const uint32_t row = (uint32_t)((int)floorf((y - c_prm.p.worldOrigin.y) / c_prm.p.cellSize.y)) & (gy - 1u);
   const uint32_t slack = s.halo_rows >= 2u ? s.halo_rows - 2u : 0u;
-  const bool below = s.has_dn && row + slack < s.row_lo;
-  const bool above = s.has_up && row >= s.row_hi + slack;
-  if (below || above) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_DRIFT);
+  bool bad;
+  if (s.wrap) { /* cyclic distance beyond the owned rows on either side */
+    const uint32_t d_up = (row - s.row_hi) & (gy - 1u), d_dn = (s.row_lo - 1u - row) & (gy - 1u);
+    const bool owned = row >= s.row_lo && row < s.row_hi;
+    bad = !owned && min(d_up, d_dn) >= slack;
+  } else {
+    bad = (s.has_dn && row + slack < s.row_lo) || (s.has_up && row >= s.row_hi + slack);
+  }
+  if (bad) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_DRIFT);
 }
 /* packed sorted copy of the owned robots at [halo_cap, halo_cap + n); pr.w = GLOBAL id (the robot's identity: the
  * transported object is robot nCells - 1 wherever it lives); collide scatters its results through index_sorted */
@@ -522,13 +536,27 @@ void prs_slab_cell_table(const prs_slab *s) {
   const unsigned gx = g_prs.h_prm.p.gridSize.x, gy = g_prs.h_prm.p.gridSize.y;
   const unsigned r0 = s->row_lo > s->halo_rows ? s->row_lo - s->halo_rows : 0u;
   const unsigned r1 = min(s->row_hi + s->halo_rows, gy);
+  /* ring of slabs: the halo rows that lie beyond the grid edge are the rows at its other end */
+  auto clear_wrapped = [&]() {
+    if (!s->wrap) return;
+    if (s->row_lo < s->halo_rows) {
+      const unsigned rows = min(s->halo_rows - s->row_lo, gy);
+      PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)(gy - rows) * gx, 0xff, (size_t)rows * gx * sizeof(unsigned), g_prs.stream));
+    }
+    if (s->row_hi + s->halo_rows > gy) {
+      const unsigned rows = min(s->row_hi + s->halo_rows - gy, gy);
+      PRS_CUDA(cudaMemsetAsync(s->cellStart, 0xff, (size_t)rows * gx * sizeof(unsigned), g_prs.stream));
+    }
+  };
   if (g_prs.slab_binned && g_prs.slab_table_fresh) {
+    clear_wrapped();
     if (s->row_lo > r0) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(s->row_lo - r0) * gx * sizeof(unsigned), g_prs.stream));
     if (r1 > s->row_hi) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)s->row_hi * gx, 0xff, (size_t)(r1 - s->row_hi) * gx * sizeof(unsigned), g_prs.stream));
     PRS_LAUNCH_PDL(k_slab_halo_table, div_up(2 * s->halo_cap, 256), 256, *s);
     g_prs.slab_table_fresh = false;
     return;
   }
+  clear_wrapped();
   PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(r1 - r0) * gx * sizeof(unsigned), g_prs.stream));
   PRS_LAUNCH_PDL(k_slab_cell_table, div_up(s->cap + 2 * s->halo_cap, 256), 256, *s);
   if (g_prs.slab_sorted_onesweep && g_prs.bin.mode == 0 && !g_prs.bin.admitted) {

@@ -28,8 +28,8 @@ copy anywhere in it (overflow and "crossed two slabs" conditions set sticky erro
 `check()` reads when the caller asks).  The data path has no collective: neighbour transfers of a
 few MB (latency-bound on NVLink) and one 4-byte all_reduce per phase update.  Ownership changes
 only on sort steps (the table is frozen between sorts); HALO_ROWS = 3 = the 2-row
-stencil + 1 guard row for drift between sorts.  Limits of this version: the hash wrap-around (Q9)
-is not exchanged — the world must fit the grid — and a robot may cross at most one slab per sort.
+stencil + 1 guard row for drift between sorts.  `wrap=True` makes the slabs a ring in the row index
+(the cell hash wraps around the grid, Q9).  Limit: a robot may cross at most one slab per sort.
 Object transport (nDead == -1) works across slabs: sorted and halo records carry the robot's GLOBAL
 id as identity, so every rank recognises the object (robot nCells - 1) wherever it lives.  Robots of one cell are ordered by GLOBAL id
 after the local sort, which is the order the reference's stable sort gives them, so the forces are
@@ -141,7 +141,9 @@ class CudaBackend:
             setattr(sl, name, t.data_ptr())
         sl.cap, sl.halo_cap, sl.mig_cap = sim.cap, sim.halo_cap, sim.mig_cap
         sl.row_lo, sl.row_hi, sl.halo_rows = sim.R_lo, sim.R_hi, HALO_ROWS
-        sl.has_dn, sl.has_up = int(sim.rank > 0), int(sim.rank < sim.world - 1)
+        ring = bool(getattr(sim, "wrap", False)) and sim.world > 1
+        sl.has_dn, sl.has_up = int(sim.rank > 0 or ring), int(sim.rank < sim.world - 1 or ring)
+        sl.wrap = int(ring)
         self.slab = sl
         self._ref = C.byref(sl)
 
@@ -207,9 +209,14 @@ class SlabSim:
     stand-in); `group` is the torch.distributed process group (None = default)."""
 
     def __init__(self, params, opt, backend, rank, world, device, pos, gid, rows, capacity=None, halo_cap=None,
-                 mig_cap=None, group=None, exchange="nccl", native_step=True, overlap_exchange=True):
+                 mig_cap=None, group=None, exchange="nccl", native_step=True, overlap_exchange=True, wrap=False):
         self.p, self.opt, self.be = params, opt, backend
         self.rank, self.world, self.dev, self.group = rank, world, device, group
+        # wrap: the slabs form a ring in the row index (the cell hash wraps around the grid, SURVEY.md Q9 — e.g. the reference's
+        # own world, +-64 on a 512-row grid of 0.235: robots above y = 56.3 share rows 0.. with the bottom of the world)
+        self.wrap = bool(wrap) and world > 1
+        self.nb_dn = (rank - 1) % world if (self.wrap or rank > 0) else None
+        self.nb_up = (rank + 1) % world if (self.wrap or rank < world - 1) else None
         self.R_lo, self.R_hi = rows[rank], rows[rank + 1]
         self.GX, self.GY = int(params.gridSize.x), int(params.gridSize.y)
         n = int(len(gid))
@@ -297,19 +304,22 @@ class SlabSim:
         dist.all_gather_object(handles, handle.raw, group=self.group)
         self.peer = [None, None]     # [lower, upper] neighbour's mailbox in this process's address space
         ok = 1
-        for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
-            if 0 <= nb < self.world:
-                ptr = lib.prs_ipc_open(C.create_string_buffer(handles[nb], len(handles[nb])))
+        opened = {}
+        for side, nb in ((0, self.nb_dn), (1, self.nb_up)):
+            if nb is not None:
+                if nb not in opened:      # a ring of two: both neighbours are the same rank, its mailbox is mapped once
+                    opened[nb] = lib.prs_ipc_open(C.create_string_buffer(handles[nb], len(handles[nb])))
+                ptr = opened[nb]
                 self.peer[side] = int(ptr) if ptr else None
                 ok &= int(bool(ptr))
+        self._peer_maps = [int(p_) for p_ in opened.values() if p_]
         torch.cuda.synchronize()
         # every rank must use the same exchange: if any mapping failed, all fall back to NCCL
         flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
-            for pp in self.peer:
-                if pp:
-                    lib.prs_ipc_close(C.c_void_p(pp))
+            for pp in self._peer_maps:
+                lib.prs_ipc_close(C.c_void_p(pp))
             lib.prs_slab_mailbox_free(C.c_void_p(self.mailbox))
             self.mailbox, self.peer, self.exchange = None, [None, None], "nccl"
             if self.rank == 0:
@@ -348,9 +358,8 @@ class SlabSim:
         if self.exchange == "p2p" and getattr(self, "mailbox", None):
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
-            for pp in self.peer:
-                if pp:
-                    self.be.lib.prs_ipc_close(C.c_void_p(pp))
+            for pp in self._peer_maps:
+                self.be.lib.prs_ipc_close(C.c_void_p(pp))
             dist.barrier(group=self.group)
             self.be.lib.prs_slab_mailbox_free(C.c_void_p(self.mailbox))
             self.mailbox = None
@@ -364,15 +373,20 @@ class SlabSim:
     def _exchange(self, send, recv):
         """fixed-size buffers to / from the lower (index 0) and upper (index 1) neighbour, one batch;
         ordered on the device stream, the host does not wait for the data"""
-        dn = self.rank - 1 if self.rank > 0 else None
-        up = self.rank + 1 if self.rank < self.world - 1 else None
+        dn, up = self.nb_dn, self.nb_up
         ops = []
-        if dn is not None:
-            ops.append(dist.P2POp(dist.isend, send[0], dn, group=self.group))
-            ops.append(dist.P2POp(dist.irecv, recv[0], dn, group=self.group))
-        if up is not None:
-            ops.append(dist.P2POp(dist.isend, send[1], up, group=self.group))
-            ops.append(dist.P2POp(dist.irecv, recv[1], up, group=self.group))
+        if dn is not None and dn == up:
+            # a ring of two: both neighbours are the same rank, messages pair up by order — what I send down arrives as
+            # "from above" over there, so the receives are posted in the opposite order of the sends
+            ops = [dist.P2POp(dist.isend, send[0], dn, group=self.group), dist.P2POp(dist.irecv, recv[1], dn, group=self.group),
+                   dist.P2POp(dist.isend, send[1], dn, group=self.group), dist.P2POp(dist.irecv, recv[0], dn, group=self.group)]
+        else:
+            if dn is not None:
+                ops.append(dist.P2POp(dist.isend, send[0], dn, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, recv[0], dn, group=self.group))
+            if up is not None:
+                ops.append(dist.P2POp(dist.isend, send[1], up, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, recv[1], up, group=self.group))
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()

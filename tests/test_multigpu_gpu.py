@@ -29,6 +29,9 @@ def _config(scenario="plain"):
     return multigpu.selfcheck_config(os.path.join(util.EXAMPLES, "example.cfg"))
 
 
+WRAP_SHIFT = 42.3     # "wrap" scenario: the block sits under the top wall of the reference's world, where the row index wraps
+
+
 def _object_start(n_total):
     """the object (robot n_total - 1) is dropped into the middle of the block, just below the cut between the two middle
     slabs, moving up: it ploughs through the lattice and changes owner"""
@@ -57,6 +60,20 @@ def _worker(rank, world, port, out_path, bin_mode, exchange, scenario="plain"):
         keep = (r >= rows[rank]) & (r < rows[rank + 1])
         sim = multigpu.SlabSim(p, o, multigpu.CudaBackend(p, geom["half"]), rank, world, dev, pos[keep], ids[keep], rows,
                                capacity=int(NX * NY / world * 1.5) + 4096, halo_cap=16384, mig_cap=4096, exchange=exchange)
+    elif scenario == "wrap":
+        # The reference's own world: +-64 on 512 rows of 0.235 — rows 512.. of the robots above y = 56.3 alias rows 0.. (SURVEY.md
+        # Q9).  The block is pushed up under the top wall; the slabs form a ring, the first one owns the aliased rows: robots that
+        # cross y = 56.3 migrate from the LAST slab to the FIRST, and the two exchange halos across the seam.
+        ids = np.arange(NX * NY, dtype=np.int64)
+        pos = multigpu.hex_block_positions(ids, NX, NY, PITCH, 0.01 * p.max_radius, 5555)
+        pos[:, 1] += np.float32(WRAP_SHIFT)
+        r_un = multigpu.grid_row_of(pos[:, 1], p)                      # unwrapped: the top lattice rows lie beyond row 511
+        r = r_un & (int(p.gridSize.y) - 1)
+        lo, hi = int(r_un.min()), int(p.gridSize.y)
+        rows = [0] + [lo + ((hi - lo) * (b + 1)) // world for b in range(world - 1)] + [hi]   # the first slab also owns rows 0.. (the seam)
+        keep = (r >= rows[rank]) & (r < rows[rank + 1])
+        sim = multigpu.SlabSim(p, o, multigpu.CudaBackend(p, geom["half"]), rank, world, dev, pos[keep], ids[keep], rows,
+                               capacity=NX * NY + 4096, halo_cap=32768, mig_cap=8192, exchange=exchange, wrap=True)
     elif scenario == "rebalance":
         # lopsided cuts to start with: rebalance() (called twice below) has to move the boundaries and a large part of the swarm
         ids = np.arange(NX * NY, dtype=np.int64)
@@ -100,7 +117,7 @@ def _free_port():
 
 @pytest.mark.parametrize("world,bin_mode,exchange,scenario", [
     (2, 0, "p2p", "plain"), (2, 1, "nccl", "plain"), (2, 2, "p2p", "plain"), (2, 2, "nccl", "plain"), (2, 0, "p2p", "object"),
-    (2, 1, "nccl", "object"), (2, 0, "p2p", "rebalance"), (4, 0, "p2p", "rebalance"), (4, 0, "p2p", "plain"), (4, 0, "p2p", "object"), (8, 0, "p2p", "plain"), (8, 2, "nccl", "plain")])
+    (2, 1, "nccl", "object"), (2, 0, "p2p", "wrap"), (2, 1, "nccl", "wrap"), (4, 0, "p2p", "wrap"), (2, 0, "p2p", "rebalance"), (4, 0, "p2p", "rebalance"), (4, 0, "p2p", "plain"), (4, 0, "p2p", "object"), (8, 0, "p2p", "plain"), (8, 2, "nccl", "plain")])
 def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -116,6 +133,10 @@ def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_
     sim.srand(p.seed)                # main.cpp:929 — the dead draw continues this stream
     sim.init_hex(NX, NY, PITCH, 0.01 * p.max_radius, 5555)
     vel0 = _initial_velocity(np.arange(NX * NY))
+    if scenario == "wrap":
+        pos0 = sim.get(prs.POSITION)
+        pos0[:, 1] += np.float32(WRAP_SHIFT)
+        sim.set(prs.POSITION, pos0)
     if scenario == "object":
         obj_pos, obj_vel = _object_start(NX * NY)
         pos0 = sim.get(prs.POSITION)
@@ -134,6 +155,10 @@ def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_
             assert np.array_equal(got[f"phase_{k}"], sim.get(prs.PHASE)), k
             if scenario == "object":       # the object really is the heavy, never-oscillating robot on both sides
                 assert got[f"rad_{k}"][-1] == np.float32(p.min_radius) * np.float32(p.radFactor)
+    if scenario == "wrap":
+        rows_end = multigpu.grid_row_of(got[f"pos_{STEPS}"][:, 1], p)
+        assert (rows_end >= int(p.gridSize.y)).sum() > 100          # robots above the seam ...
+        assert np.all(got[f"owner_{STEPS}"][rows_end >= int(p.gridSize.y)] == 0)   # ... live on the FIRST slab
     if scenario == "rebalance":
         assert stats[:, 1].sum() > NX * NY // 8 and stats[:, 0].max() < 1.25 * NX * NY / world, stats     # moved a lot, ended balanced
     if scenario == "object" and world == 2:
