@@ -18,8 +18,10 @@ agg = collections.OrderedDict()
 for r in rows[hdr + 1:]:
     if len(r) > mv:
         agg.setdefault(r[kn], collections.defaultdict(list))[r[mn]].append(float(r[mv].replace(",", "")))
-binned = ["k_control_integrate_hash<1, 1>", "k_cell_tile_sums", "k_cell_scan_tiles", "k_cell_apply", "k_cell_scatter", "k_reorder_binned", "k_collide_exact"]
-onesweep = ["k_control_integrate_hash<1, 0>", "k_histogram", "k_onesweep", "k_reorder_packed", "k_max_population", "k_collide_exact"]
+binned = ["k_control_integrate_hash_x2", "k_control_integrate_hash<1, 1>", "k_cell_tile_sums", "k_cell_scan_tiles", "k_cell_apply", "k_cell_scatter",
+          "k_reorder_binned", "k_collide_exact<0, 0, prs::PackedLayout, 1>", "k_collide_exact<0, 0, PackedLayout, 1>"]
+onesweep = ["k_control_integrate_hash<1, 0>", "k_histogram", "k_onesweep", "k_reorder_packed", "k_max_population",
+            "k_collide_exact<0, 0, prs::PackedLayout, 0>", "k_collide_exact<0, 0, PackedLayout, 0>"]
 def short(k): return k.split("(")[0].replace("void ", "").replace("prs_bin::", "").replace("prs_sort::", "").replace("prs::", "")
 def table(names, passes):
     out, tot = [], 0.0
