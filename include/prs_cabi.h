@@ -283,6 +283,32 @@ void prs_unpack_sorted(const float *sortedPR, float *sortedPos, float *sortedRad
  * differs from __fdiv_rn (must be 0) */
 unsigned long long prs_selftest_div(const float *d_x, const float *d_d, unsigned n);
 
+/* ---- headless frames and video (csrc/prs_frame.cuh, csrc/prs_video.cpp) ----
+ * prs_render_frame replaces, without OpenGL, what one displayed frame of the reference consists of: the scene of
+ * main.cpp:366-466 (floor, light marker, obstacles), the point-sprite pass of render.cpp:53-125 / shaders.cpp:40-86 (one
+ * flat disc per entry of the position buffer in the colour updateCol gave it; entries with y > 1000 are the centroid
+ * trail, kernel_impl.cuh:343) and PostprocessKernel's read-back (postprocess.cu:32-55: rows top-down, bytes B, G, R).
+ * The view is the reference's camera looking straight down: world_per_pixel = 2 camera_y tan(30 deg) / height
+ * (prs_view_from_camera).  d_bgr: device, width*height*3 bytes; d_keys: device scratch, 2*width*height words;
+ * pos / rad / col: device, n_points entries (robots, then the trail; col is float4 per entry). */
+typedef struct {
+  unsigned width, height;
+  float center_x, center_y;
+  float world_per_pixel;
+  float light_radius;
+} prs_view;
+void prs_view_from_camera(prs_view *v, unsigned width, unsigned height, float camera_y, float light_radius);
+void prs_render_frame(unsigned char *d_bgr, unsigned *d_keys, const prs_view *view, const float *pos, const float *rad,
+                      const float *col, unsigned n_points);
+/* Video file of such frames — what cv::VideoWriter does in postprocess.cu:101-118 (20 frames per second, one frame every
+ * VIDEO_INTERVAL displayed frames), as an uncompressed AVI (BI_RGB, 24 bit) that needs no codec library.  Frames are host
+ * memory, top-down B, G, R rows as prs_render_frame produces them.  A RIFF file ends at 4 GiB: prs_video_write returns -1
+ * once the next frame would not fit (the file stays valid).  No GPU involved. */
+typedef struct prs_video prs_video;
+prs_video *prs_video_open(const char *path, unsigned width, unsigned height, double fps);
+int prs_video_write(prs_video *v, const unsigned char *bgr_top_down);
+int prs_video_close(prs_video *v); /* patches the header counts; returns the number of frames written, -1 on I/O error */
+
 /* ---- simulation object (class Particlebot, include/prs_particlebot.hpp) for C callers ---- */
 typedef struct prs_sim prs_sim;
 /* fills *p with the defaults of main.cpp:833-911 and the derived grid of :932-939; extras receive
@@ -341,6 +367,9 @@ void prs_sim_load(prs_sim *s, void *FILE_ptr);
  * shape continues bit for bit, on either sort cadence.  0 on success, -1 on I/O error or shape mismatch. */
 int prs_sim_checkpoint_save(prs_sim *s, const char *path);
 int prs_sim_checkpoint_load(prs_sim *s, const char *path);
+/* Particlebot::renderFrame: colours (updateCol) + prs_render_frame + copy to host memory owned by the object (valid until
+ * the next call); width*height*3 bytes, top-down B, G, R */
+const unsigned char *prs_sim_render_frame(prs_sim *s, const prs_view *view);
 
 #ifdef __cplusplus
 }

@@ -82,7 +82,7 @@ class Particlebot {
   unsigned int getColorBuffer() const { return 0; }
   unsigned int getRadBuffer() const { return 0; }
   void *getCudaPosVBO() const { return (void *)dPos; }
-  void *getCudaColorVBO() const { return 0; }
+  void *getCudaColorVBO() const { return (void *)dCol; } /* allocated by the first renderFrame */
   void *getCudaRadVBO() const { return (void *)dRad; }
 
   void dumpParticlebot(unsigned start, unsigned count, FILE *fp, float dump_interval, unsigned testing, float light_x,
@@ -101,6 +101,10 @@ class Particlebot {
   void getCellSize(float *xy) const { xy[0] = params.cellSize.x; xy[1] = params.cellSize.y; }
 
   /* additions */
+  /* One displayed frame without OpenGL: colours of the current state (updateCol, particlebot.cpp:254; the
+   * trail entries keep the reference's red, :125-135), the scene and the discs by prs_render_frame; returns host memory
+   * owned by the object (valid until the next call): width * height * 3 bytes, top-down B, G, R rows. */
+  const unsigned char *renderFrame(const prs_view &view);
   float getTime() const { return time; }
   void sync();
   void *devicePtr(int which);
@@ -125,6 +129,12 @@ class Particlebot {
   unsigned *dGridParticleHash, *dGridParticleIndex, *dCellStart, *dCellEnd;
   float *dMinD; /* device scalar for the fused path's light-distance reduction */
   float *dSortedPR; /* fused path: packed float4 sorted copy (see prs_step_buffers) */
+  /* headless frames: colour buffer (N + centroid_steps + 1 float4, the reference's colorVBO), device image + key planes,
+   * pinned host image; all allocated by the first renderFrame */
+  float *dCol = 0;
+  unsigned char *dFrame = 0, *hFrame = 0;
+  unsigned *dFrameKeys = 0;
+  size_t framePixels_ = 0;
 
   float time;
   SimParams params;

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libparticlebot_b200.so")
+# PRS_LIB: another build of the SAME library (A/B measurements of compile-time variants, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("PRS_LIB") or os.path.join(_HERE, "libparticlebot_b200.so")
 
 # array selectors of prs_sim_get/set/device_ptr (ParticlebotArray + additions, prs_cabi.h)
 POSITION, VELOCITY, RADII, PHASE, FREQUENCY, DEAD = range(6)
@@ -65,6 +66,13 @@ class RunOptions(C.Structure):
         ("init_hexblock", C.c_int), ("hexblock_nx", C.c_uint), ("hexblock_ny", C.c_uint), ("hexblock_seed", C.c_uint),
         ("hexblock_pitch", C.c_float), ("hexblock_jitter", C.c_float), ("world_half", C.c_float), ("grid_dim", C.c_uint),
     ]
+
+
+class View(C.Structure):
+    """Mirror of prs_view (include/prs_cabi.h): the straight-down camera of a headless frame."""
+
+    _fields_ = [("width", C.c_uint), ("height", C.c_uint), ("center_x", C.c_float), ("center_y", C.c_float),
+                ("world_per_pixel", C.c_float), ("light_radius", C.c_float)]
 
 
 class StepBuffers(C.Structure):
@@ -170,6 +178,11 @@ SIGNATURES = {
     "prs_h2d_async": (None, [_VP, _VP, C.c_size_t]), "prs_arm_k1_event": (None, [_I]),
     "prs_d2h_async": (None, [_VP, _VP, C.c_size_t, _I]), "prs_host_step_sync": (None, []),
     "prs_sim_checkpoint_save": (_I, [_VP, C.c_char_p]), "prs_sim_checkpoint_load": (_I, [_VP, C.c_char_p]),
+    # headless frames and video
+    "prs_view_from_camera": (None, [C.POINTER(View), _U, _U, _F, _F]),
+    "prs_render_frame": (None, [_VP, _VP, C.POINTER(View), _VP, _VP, _VP, _U]),
+    "prs_sim_render_frame": (_VP, [_VP, C.POINTER(View)]),
+    "prs_video_open": (_VP, [C.c_char_p, _U, _U, C.c_double]), "prs_video_write": (_I, [_VP, _VP]), "prs_video_close": (_I, [_VP]),
 }
 
 
@@ -193,6 +206,32 @@ def lib():
                 "(nvcc, sm_100a).  There is no CPU or PyTorch fallback.")
         _lib = bind_signatures(C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW))
     return _lib
+
+
+def view_from_camera(width, height, camera_y, light_radius):
+    v = View()
+    lib().prs_view_from_camera(C.byref(v), width, height, camera_y, light_radius)
+    return v
+
+
+class VideoWriter:
+    """prs_video_* (csrc/prs_video.cpp): uncompressed AVI of top-down B, G, R frames; host code only"""
+
+    def __init__(self, path, width, height, fps=20.0):
+        self._lib = lib()
+        self.shape = (height, width, 3)
+        self._h = self._lib.prs_video_open(os.fsencode(path), width, height, fps)
+        if not self._h:
+            raise OSError(f"cannot open {path}")
+
+    def write(self, frame):
+        f = np.ascontiguousarray(frame, np.uint8)
+        assert f.shape == self.shape, (f.shape, self.shape)
+        return self._lib.prs_video_write(self._h, f.ctypes.data)
+
+    def close(self):
+        n, self._h = self._lib.prs_video_close(self._h), None
+        return n
 
 
 def default_params():
@@ -266,6 +305,12 @@ class Simulation:
         """restore a checkpoint of a swarm of the same shape; the run continues bit for bit"""
         if self._lib.prs_sim_checkpoint_load(self._h, os.fsencode(path)) != 0:
             raise OSError(f"cannot restore checkpoint {path}")
+
+    def render_frame(self, view):
+        """one headless frame (Particlebot::renderFrame): uint8 array (height, width, 3), top-down rows, B, G, R"""
+        ptr = self._lib.prs_sim_render_frame(self._h, C.byref(view))
+        h, w = int(view.height), int(view.width)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(h, w, 3)).copy()
 
     @property
     def time(self):

@@ -16,7 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
-LIB_SOURCES = ["prs_kernels.cu", "prs_config.cpp", "prs_particlebot.cpp"]
+LIB_SOURCES = ["prs_kernels.cu", "prs_config.cpp", "prs_particlebot.cpp", "prs_video.cpp"]
 
 
 def _newer(target, deps):

@@ -1387,8 +1387,34 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
 }  // extern "C"
 
 #include "prs_slab.cuh"
+#include "prs_frame.cuh"
 
 extern "C" {
+
+/* headless frame (prs_frame.cuh): the reference's straight-down camera as a scale of the floor plane */
+void prs_view_from_camera(prs_view *v, unsigned width, unsigned height, float camera_y, float light_radius) {
+  v->width = width;
+  v->height = height;
+  v->center_x = 0.0f;
+  v->center_y = 0.0f;
+  v->world_per_pixel = 2.0f * camera_y * 0.57735026918962576f / (float)height; /* gluPerspective(60, ..), main.cpp:519 */
+  v->light_radius = light_radius;
+}
+void prs_render_frame(unsigned char *d_bgr, unsigned *d_keys, const prs_view *view, const float *pos, const float *rad,
+                      const float *col, unsigned n_points) {
+  if (!view->width || !view->height || !(view->world_per_pixel > 0.0f)) {
+    fprintf(stderr, "prs_render_frame: empty view\n");
+    exit(EXIT_FAILURE);
+  }
+  prs::FrameView v;
+  v.width = view->width; v.height = view->height;
+  v.center_x = view->center_x; v.center_y = view->center_y;
+  v.world_per_pixel = view->world_per_pixel; v.light_radius = view->light_radius;
+  const size_t npix = (size_t)v.width * v.height;
+  PRS_CUDA(cudaMemsetAsync(d_keys, 0xff, 2 * npix * sizeof(uint32_t), g_prs.stream));
+  if (n_points) PRS_LAUNCH(prs::k_frame_splat, div_up(n_points, 256), 256, 0, d_keys, v, (const float2 *)pos, rad, n_points);
+  PRS_LAUNCH(prs::k_frame_resolve, div_up((unsigned)npix, 256), 256, 0, d_bgr, (const uint32_t *)d_keys, v, (const float4 *)col);
+}
 
 void prs_init_hex_block(float *pos, float *vel, float *rad, float *phase, int *dead, unsigned n, unsigned nx, unsigned ny, float pitch,
                         float jitter, unsigned seed, float min_radius) {

@@ -1,9 +1,12 @@
 /*
  * prs_main.cpp — headless runner `ParticleBot <cfg> [--steps N] [--backend fused|percall|ext:<lib>]
- * [--no-csv] [--quiet] [--save-checkpoint FILE] [--resume-checkpoint FILE]`: the reference's main() (main.cpp:823-967) without GLUT/GL/OpenCV.  The
- * GLUT display callback that drives the reference (dumpParticlebot, then update, main.cpp:360-361)
- * becomes a plain loop; rendering and video are optional components that are not built here
- * (north_star (5)).
+ * [--no-csv] [--quiet] [--save-checkpoint FILE] [--resume-checkpoint FILE] [--video [FILE]] [--video-size WxH] [--frame-ppm FILE]`:
+ * the reference's main() (main.cpp:823-967) without GLUT/GL/OpenCV.  The GLUT display callback that drives the reference
+ * (dumpParticlebot, then update, main.cpp:360-361) becomes a plain loop.  Rendering is optional (north_star (5)): with
+ * --video a frame is drawn every DISPLAY_INTERVAL steps by the headless frame kernels (Particlebot::renderFrame) and every
+ * VIDEO_INTERVAL-th of them goes to the cfg's video_filename (or FILE) at 20 frames per second, as the reference's display()
+ * + PostprocessCUDA do (main.cpp:366, 469; postprocess.cu:113-116) — an uncompressed AVI instead of XVID.  The reference's
+ * window is 1920x1080 (main.cpp:65).  --frame-ppm writes the last frame as a binary PPM.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,6 +26,9 @@ int main(int argc, char **argv) {
   const char *ext = 0;
   bool csv = true, quiet = false;
   const char *ck_out = 0, *ck_in = 0;
+  bool video = false;
+  const char *video_path = 0, *ppm_path = 0;
+  unsigned vw = 1920, vh = 1080;
   int positional = 0;
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--steps") && i + 1 < argc) max_steps = atol(argv[++i]);
@@ -34,6 +40,12 @@ int main(int argc, char **argv) {
       else { fprintf(stderr, "unknown backend %s\n", b); return 2; }
     } else if (!strcmp(argv[i], "--save-checkpoint") && i + 1 < argc) ck_out = argv[++i];
     else if (!strcmp(argv[i], "--resume-checkpoint") && i + 1 < argc) ck_in = argv[++i];
+    else if (!strcmp(argv[i], "--video")) {
+      video = true;
+      if (i + 1 < argc && argv[i + 1][0] != '-' && strstr(argv[i + 1], ".avi")) video_path = argv[++i];
+    } else if (!strcmp(argv[i], "--video-size") && i + 1 < argc) {
+      if (sscanf(argv[++i], "%ux%u", &vw, &vh) != 2 || !vw || !vh) { fprintf(stderr, "--video-size WxH\n"); return 2; }
+    } else if (!strcmp(argv[i], "--frame-ppm") && i + 1 < argc) ppm_path = argv[++i];
     else if (!strcmp(argv[i], "--no-csv")) csv = false;
     else if (!strcmp(argv[i], "--quiet")) quiet = true;
     else if (!strcmp(argv[i], "--headless")) { /* default */ }
@@ -59,14 +71,41 @@ int main(int argc, char **argv) {
     fclose(ck);
   }
 
+  prs_view view;
+  prs_view_from_camera(&view, vw, vh, opt.camera_y, opt.light_radius);
+  prs_video *vid = 0;
+  if (video) {
+    vid = prs_video_open(video_path ? video_path : opt.video_filename, vw, vh, 20.0); /* FPS of postprocess.cu:24 */
+    if (!vid) { perror(video_path ? video_path : opt.video_filename); return 1; }
+  }
+  const int display_every = opt.display_interval > 0 ? opt.display_interval : 1;
+  const int video_every = opt.video_interval > 0 ? opt.video_interval : 1;
+  long displayed = 0, frames_written = 0;
+
   const auto t0 = std::chrono::steady_clock::now();
   long steps = 0;
   while (max_steps < 0 || steps < max_steps) {
     bot.dumpParticlebot(0, params.nCells, fp, opt.dump_interval, params.testing, params.light_x, params.light_y);
     if (bot.update(opt.timestep, opt.sort_interval)) break; /* time > max_time: the reference exit(0)s */
+    if (vid && steps % display_every == 0) { /* display(): frameCount % DISPLAY_INTERVAL == 0, then i % interval == 0 */
+      if (displayed % video_every == 0) {
+        if (prs_video_write(vid, bot.renderFrame(view)) != 0) { fprintf(stderr, "video file is full (4 GiB): no more frames\n"); prs_video_close(vid); vid = 0; }
+        else frames_written++;
+      }
+      displayed++;
+    }
     steps++;
   }
   bot.sync();
+  if (vid) prs_video_close(vid);
+  if (ppm_path) {
+    FILE *pf = fopen(ppm_path, "wb");
+    if (!pf) { perror(ppm_path); return 1; }
+    const unsigned char *f = bot.renderFrame(view);
+    fprintf(pf, "P6\n%u %u\n255\n", vw, vh);
+    for (size_t i = 0; i < (size_t)vw * vh; i++) { const unsigned char rgb[3] = {f[3 * i + 2], f[3 * i + 1], f[3 * i]}; fwrite(rgb, 1, 3, pf); }
+    fclose(pf);
+  }
   if (ck_out) {
     FILE *ck = fopen(ck_out, "wb");
     if (!ck || bot.saveCheckpoint(ck) != 0) { fprintf(stderr, "cannot write %s\n", ck_out); return 1; }
@@ -76,5 +115,6 @@ int main(int argc, char **argv) {
   fclose(fp);
   fprintf(stderr, "ParticleBot: %ld steps, %u robots, %.3f s, %.1f steps/s, %.3e particle-steps/s\n", steps,
           params.nCells, sec, steps / sec, (double)steps * params.nCells / sec);
+  if (video) fprintf(stderr, "ParticleBot: %ld video frames (%ux%u)\n", frames_written, vw, vh);
   return 0;
 }

@@ -187,7 +187,53 @@ void Particlebot::_finalize() {
                   dState, dMinD};
   for (void *b : bufs) be_.freeArray(b);
   if (dSortedPR) be_.freeArray(dSortedPR);
+  if (dCol) be_.freeArray(dCol);
+  if (dFrame) be_.freeArray(dFrame);
+  if (dFrameKeys) be_.freeArray(dFrameKeys);
+  delete[] hFrame;
   if (be_.dl_handle) dlclose(be_.dl_handle);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * headless frame (the reference's display(): main.cpp:352-476 -> renderer->display() -> Postprocess())
+ * ------------------------------------------------------------------------------------------ */
+const unsigned char *Particlebot::renderFrame(const prs_view &view) {
+  const size_t n = params.nCells, trail = (size_t)params.centroid_steps + 1;
+  if (!dCol) {
+    /* colorVBO of the reference (particlebot.cpp:110-135): white robots until updateCol runs, a red trail */
+    be_.allocateArray((void **)&dCol, (n + trail) * 4 * sizeof(float));
+    std::vector<float> c((n + trail) * 4, 1.0f);
+    for (size_t i = n; i < n + trail; i++) { c[4 * i + 1] = 0.0f; c[4 * i + 2] = 0.0f; c[4 * i + 3] = (i + 1 < n + trail) ? 0.8f : 1.0f; }
+    size_t done = 0;
+    const size_t bytes = c.size() * sizeof(float);
+    while (done < bytes) {
+      const size_t chunk = std::min<size_t>(bytes - done, (size_t)1 << 30);
+      be_.copyArrayToDevice((char *)dCol + done, (const char *)c.data() + done, 0, (int)chunk);
+      done += chunk;
+    }
+  }
+  if (backend_kind_ == PRS_BACKEND_EXTERNAL && !framePixels_) {
+    /* the step kernels are somebody else's: the frame kernels read THIS library's parameter block */
+    setParameters(&params);
+    prs_set_world_half_extent(world_half_);
+  }
+  const size_t npix = (size_t)view.width * view.height;
+  if (npix != framePixels_) {
+    if (dFrame) { be_.freeArray(dFrame); be_.freeArray(dFrameKeys); delete[] hFrame; }
+    be_.allocateArray((void **)&dFrame, npix * 3);
+    be_.allocateArray((void **)&dFrameKeys, npix * 2 * sizeof(unsigned));
+    hFrame = new unsigned char[npix * 3];
+    framePixels_ = npix;
+  }
+  if (n) updateCol(dRad, dCol, (int)n, dPos, dphase, dDead);
+  prs_render_frame(dFrame, dFrameKeys, &view, dPos, dRad, dCol, (unsigned)(n + params.centroid_steps));
+  size_t done = 0;
+  while (done < npix * 3) {
+    const size_t chunk = std::min<size_t>(npix * 3 - done, (size_t)1 << 30);
+    copyArrayFromDevice(hFrame + done, dFrame + done, 0, (int)chunk);
+    done += chunk;
+  }
+  return hFrame;
 }
 
 void Particlebot::sync() { be_.threadSync(); }
@@ -746,6 +792,7 @@ int prs_sim_checkpoint_load(prs_sim *s, const char *path) {
   fclose(fp);
   return rc;
 }
+const unsigned char *prs_sim_render_frame(prs_sim *s, const prs_view *view) { return s->bot->renderFrame(*view); }
 void prs_sim_load(prs_sim *s, void *fp) {
   const SimParams &P = s->bot->getParams();
   s->bot->loadFromFile(0, P.nCells, (FILE *)fp, 0.0f);

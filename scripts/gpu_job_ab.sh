@@ -1,0 +1,19 @@
+# GPU job: A/B of compile-time variants (scripts/build_variant.sh): parity tests with the default build, then the S1 line
+# of the default build and of every variant named on the command line, twice each, interleaved.
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -k "${PRS_AB_TESTS:-collide or trajectory or large_swarm or binning or s1_}" 2>&1 | tail -4
+for rep in 1 2; do
+  for v in default "$@"; do
+    lib=""; [ "$v" != default ] && lib="$PWD/particlerobotsimulations_b200/variants/libparticlebot_b200_$v.so"
+    PRS_LIB=$lib timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-ref-cuda --no-extras > gpurun_out/ab_${v}_$rep.json 2> gpurun_out/ab_${v}_$rep.err
+  done
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/ab_*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, round(d["ms_per_step"]*1e3,1), {k:round(v["avg_us"],1) for k,v in d["stages"].items()}, d["state_finite"])
+    except Exception as e:
+        print(f, "FAILED", e, open(f.replace(".json",".err")).read()[-600:])
+PY
