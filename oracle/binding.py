@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "_build", "libprs_oracle.so")
 REFCUDA_PATH = os.path.join(_HERE, "_ref", "libprs_refcuda.so")
 REFHOST_PATH = os.path.join(_HERE, "_ref", "libprs_refhost.so")
 DROPIN_PATH = os.path.join(_HERE, "_ref", "libprs_dropin.so")   # the reference's host class over the PRODUCT library
+# ... and over the product's OpenGL build (-DPRS_WITH_GL: its own VBO interop entry points, CUDA graphics API -> headless buffer objects)
+DROPIN_GL_PATH = os.path.join(_HERE, "_ref", "libprs_dropin_gl.so")
 
 
 def build():

@@ -14,6 +14,9 @@
  * need IEEE divides, the reference is built without it, Makefile:78-84).
  */
 #include <cuda_runtime.h>
+#ifdef PRS_WITH_GL
+#include <cuda_gl_interop.h> /* needs the platform's <GL/gl.h> */
+#endif
 #include <curand_kernel.h>
 #include <math.h>
 #include <algorithm>
@@ -839,19 +842,44 @@ void copyArrayToDevice(void *device, const void *host, int offset, int size) {
   PRS_CUDA(cudaMemcpyAsync((char *)device + offset, host, (size_t)size, cudaMemcpyHostToDevice, g_prs.stream));
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
 }
-static void no_gl(const char *fn) {
+[[maybe_unused]] static void no_gl(const char *fn) {
   fprintf(stderr, "%s: libparticlebot_b200 is built headless (no OpenGL interop); rendering is optional\n", fn);
   exit(EXIT_FAILURE);
 }
 void copyArrayFromDevice(void *host, const void *device, struct cudaGraphicsResource **res, int size) {
+#ifdef PRS_WITH_GL
+  if (res) device = mapGLBufferObject(res); /* particlebot_cuda.cu:97-100: the source is the mapped buffer object */
+#else
   if (res) no_gl("copyArrayFromDevice(mapped VBO)");
+#endif
   PRS_CUDA(cudaMemcpyAsync(host, device, (size_t)size, cudaMemcpyDeviceToHost, g_prs.stream));
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
+#ifdef PRS_WITH_GL
+  if (res) unmapGLBufferObject(*res);
+#endif
 }
+#ifdef PRS_WITH_GL
+/* OpenGL build (-DPRS_WITH_GL): buffer objects of a GL host — the reference's own main.cpp / render.cpp /
+ * particlebot.cpp — are registered with and mapped through the CUDA graphics API, what particlebot_cuda.cu:69-93 does, on
+ * this library's stream.  A GL context must be current on the calling thread (cudaGLInit, main.cpp:348). */
+void registerGLBufferObject(unsigned vbo, struct cudaGraphicsResource **res) {
+  PRS_CUDA(cudaGraphicsGLRegisterBuffer(res, vbo, cudaGraphicsMapFlagsNone));
+}
+void unregisterGLBufferObject(struct cudaGraphicsResource *res) { PRS_CUDA(cudaGraphicsUnregisterResource(res)); }
+void *mapGLBufferObject(struct cudaGraphicsResource **res) {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  PRS_CUDA(cudaGraphicsMapResources(1, res, g_prs.stream));
+  PRS_CUDA(cudaGraphicsResourceGetMappedPointer(&ptr, &bytes, *res));
+  return ptr;
+}
+void unmapGLBufferObject(struct cudaGraphicsResource *res) { PRS_CUDA(cudaGraphicsUnmapResources(1, &res, g_prs.stream)); }
+#else
 void registerGLBufferObject(unsigned, struct cudaGraphicsResource **) { no_gl("registerGLBufferObject"); }
 void unregisterGLBufferObject(struct cudaGraphicsResource *) { no_gl("unregisterGLBufferObject"); }
 void *mapGLBufferObject(struct cudaGraphicsResource **) { no_gl("mapGLBufferObject"); return nullptr; }
 void unmapGLBufferObject(struct cudaGraphicsResource *) { no_gl("unmapGLBufferObject"); }
+#endif
 
 void setParameters(SimParams *hp) {
   PrsDevParams &d = g_prs.h_prm;

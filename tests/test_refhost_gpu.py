@@ -123,19 +123,25 @@ def test_committed_goldens_equal_the_reference_class(name, tag, collide_kernel_d
 
 @pytest.mark.parametrize("name", util.CFGS)
 @pytest.mark.parametrize("sort_every_step", [False, True])
-def test_reference_class_linked_against_this_library(name, sort_every_step, collide_kernel_default):
+@pytest.mark.parametrize("gl_build", [False, True])
+def test_reference_class_linked_against_this_library(name, sort_every_step, gl_build, collide_kernel_default):
     """THE DROP-IN, EXECUTED: oracle/_ref/libprs_dropin.so is the reference's own
     particlebot.cpp, verbatim, linked against libparticlebot_b200.so instead of the reference's particlebot_cuda.o — every
     allocateArray / setParameters / curand_setup / updatePhase / updateRad_light_wave / integrateSystem / calcHash /
     sortParticlebots / reorderDataAndFindCellStart / collide / calcCOG / updateCol call of the class lands in this library.
-    Same placement, same 100 steps, bit for bit, as the class over its own kernels."""
+    Same placement, same 100 steps, bit for bit, as the class over its own kernels.
+    gl_build: the same class over the product's OPENGL BUILD (-DPRS_WITH_GL, oracle/_ref/libparticlebot_b200_glstub.so): the
+    register / map / unmapGLBufferObject the class calls every step for its position, radius and colour VBOs
+    (particlebot.cpp:105-113, 200-205) are the PRODUCT's, which go through the CUDA graphics API — redirected to the headless
+    buffer objects here, there being no OpenGL on these boxes."""
     _need_refhost()
-    if not os.path.exists(ob.DROPIN_PATH):
-        pytest.skip("oracle/_ref/libprs_dropin.so not built (needs /root/reference at build time)")
+    path = ob.DROPIN_GL_PATH if gl_build else ob.DROPIN_PATH
+    if not os.path.exists(path):
+        pytest.skip(f"{os.path.basename(path)} not built (needs /root/reference at build time)")
     prs.lib().prs_set_stream(None)
     prs.lib().prs_set_world_half_extent(64.0)
     p, o, ref = _reference_run(name, sort_every_step)
-    _, _, own = _reference_run(name, sort_every_step, ob.DROPIN_PATH)
+    _, _, own = _reference_run(name, sort_every_step, path)
     for key in ("pos", "rad", "dead", "phase"):
         assert np.array_equal(_bits(own[0][key]), _bits(ref[0][key])), ("after reset()", key)
     for k in STEPS:
