@@ -337,6 +337,28 @@ void prs_params_derive_grid(SimParams *p);
 /* synthetic worlds of SURVEY.md §8d: grid_dim cells per axis (power of two), world half extent */
 void prs_params_set_world(SimParams *p, unsigned grid_dim, float world_half);
 
+/* ---- slab runs without Python: one PROCESS per GPU, forked by the caller's process (csrc/prs_multi.cpp) ----
+ * What `ParticleBot <cfg> --gpus N` runs (the north_star's "host side is C++"): the calling process forks
+ * `gpus` ranks BEFORE any CUDA call; each rank picks its device, builds its slab of the swarm (initial state: the cfg's
+ * placement computed identically on every rank, or the init_config = hexblock generator for its own lattice rows; slab
+ * boundaries by equal robot count), maps its two neighbours' mailboxes through CUDA IPC and then calls prs_slab_step per
+ * step.  The control plane is a block of process-shared memory: a barrier, the IPC handles, the MIN of one float every
+ * phase_update_interval, and — at dump times only — the swarm gathered in robot order so that rank 0 writes the reference's
+ * CSV (particlebot.cpp:303-367) byte for byte as one GPU would.  No NCCL, no MPI, no interpreter on the path.
+ * Returns 0, or 1 if a rank failed (message on stderr). */
+typedef struct {
+  int gpus;                 /* number of ranks */
+  int oversubscribe;        /* 1: rank r runs on device r % (devices present) — several ranks per GPU (tests on one GPU) */
+  long steps;               /* number of steps; < 0: until time > max_time */
+  int csv;                  /* rank 0 writes opt->csv_filename */
+  int quiet;
+  const char *final_state;  /* optional file: rank 0 writes nCells, then pos, vel, rad, phase of the whole swarm in robot order */
+  int overlap_exchange;     /* prs_slab_ctx.overlap_exchange */
+} prs_multi_options;
+int prs_multi_run(const SimParams *p, const prs_run_options *opt, const prs_multi_options *m);
+/* position of robot i of the synthetic hex block (the generator of Particlebot::initHexBlock / prs_init_hex_block) */
+void prs_hex_block_position(unsigned long long i, unsigned nx, unsigned ny, float pitch, float jitter, unsigned seed, float *xy);
+
 /* backend: 0 = fused native path, 1 = native per-call path (the reference's call sequence on this
  * library's entry points), 2 = per-call path on an external library with the reference's ABI
  * (path given; used to drive oracle/_ref/libprs_refcuda.so from tests and bench.py) */

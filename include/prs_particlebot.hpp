@@ -72,6 +72,7 @@ class Particlebot {
                   float *rad_out, float deltaTime, float sort_interval);
   void reset();
   void srand(unsigned seed) { rng_.seed(seed); }
+  const PrsRand &randStream() const { return rng_; } /* where the glibc stream stands (the slab launcher continues it on every rank) */
   /* synthetic swarms: nx*ny hex lattice centred on the origin */
   void initHexBlock(unsigned nx, unsigned ny, float pitch, float jitter, unsigned seed);
 

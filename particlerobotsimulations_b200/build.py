@@ -16,7 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
-LIB_SOURCES = ["prs_kernels.cu", "prs_config.cpp", "prs_particlebot.cpp", "prs_video.cpp"]
+LIB_SOURCES = ["prs_kernels.cu", "prs_config.cpp", "prs_particlebot.cpp", "prs_video.cpp", "prs_multi.cpp"]
 
 
 def _newer(target, deps):
@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
     if force or _newer(LIB, deps):
         cmd = [NVCC] + ARCH + COMMON + ["-Xptxas", "-v"] * bool(verbose) + [
             "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xlinker", "-Bsymbolic", "-o", LIB,
-        ] + [os.path.join(CSRC, s) for s in LIB_SOURCES] + ["-ldl"]
+        ] + [os.path.join(CSRC, s) for s in LIB_SOURCES] + ["-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -1,6 +1,7 @@
 /*
  * prs_main.cpp — headless runner `ParticleBot <cfg> [--steps N] [--backend fused|percall|ext:<lib>]
- * [--no-csv] [--quiet] [--save-checkpoint FILE] [--resume-checkpoint FILE] [--video [FILE]] [--video-size WxH] [--frame-ppm FILE]`:
+ * [--no-csv] [--quiet] [--save-checkpoint FILE] [--resume-checkpoint FILE] [--video [FILE]] [--video-size WxH] [--frame-ppm FILE]
+ * [--gpus N [--oversubscribe] [--no-overlap]] [--final-state FILE]`:
  * the reference's main() (main.cpp:823-967) without GLUT/GL/OpenCV.  The GLUT display callback that drives the reference
  * (dumpParticlebot, then update, main.cpp:360-361) becomes a plain loop.  Rendering is optional (north_star (5)): with
  * --video a frame is drawn every DISPLAY_INTERVAL steps by the headless frame kernels (Particlebot::renderFrame) and every
@@ -29,6 +30,8 @@ int main(int argc, char **argv) {
   bool video = false;
   const char *video_path = 0, *ppm_path = 0;
   unsigned vw = 1920, vh = 1080;
+  int gpus = 1, oversubscribe = 0, overlap = 1;
+  const char *final_state = 0;
   int positional = 0;
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--steps") && i + 1 < argc) max_steps = atol(argv[++i]);
@@ -46,6 +49,10 @@ int main(int argc, char **argv) {
     } else if (!strcmp(argv[i], "--video-size") && i + 1 < argc) {
       if (sscanf(argv[++i], "%ux%u", &vw, &vh) != 2 || !vw || !vh) { fprintf(stderr, "--video-size WxH\n"); return 2; }
     } else if (!strcmp(argv[i], "--frame-ppm") && i + 1 < argc) ppm_path = argv[++i];
+    else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--oversubscribe")) oversubscribe = 1;
+    else if (!strcmp(argv[i], "--no-overlap")) overlap = 0;
+    else if (!strcmp(argv[i], "--final-state") && i + 1 < argc) final_state = argv[++i];
     else if (!strcmp(argv[i], "--no-csv")) csv = false;
     else if (!strcmp(argv[i], "--quiet")) quiet = true;
     else if (!strcmp(argv[i], "--headless")) { /* default */ }
@@ -53,6 +60,18 @@ int main(int argc, char **argv) {
   }
   if (prs_params_load_cfg(cfg, &params, &opt) != 0)
     fprintf(stderr, "warning: cannot open %s, running with defaults (as the reference does)\n", cfg);
+
+  if (gpus > 1) {
+    /* slab decomposition, one process per GPU: the ranks are forked before this process touches CUDA (prs_multi.cpp) */
+    if (backend != PRS_BACKEND_FUSED || ck_in || ck_out || video || ppm_path) {
+      fprintf(stderr, "--gpus N runs the fused slab engine: no --backend / checkpoint / video options\n");
+      return 2;
+    }
+    prs_multi_options mo;
+    mo.gpus = gpus; mo.oversubscribe = oversubscribe; mo.steps = max_steps; mo.csv = csv ? 1 : 0; mo.quiet = quiet ? 1 : 0;
+    mo.final_state = final_state; mo.overlap_exchange = overlap;
+    return prs_multi_run(&params, &opt, &mo);
+  }
 
   cudaInit(argc, argv);
   FILE *fp = csv ? fopen(opt.csv_filename, "w+") : fopen("/dev/null", "w");
@@ -113,6 +132,17 @@ int main(int argc, char **argv) {
   }
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   fclose(fp);
+  if (final_state) { /* nCells, then pos, vel, rad, phase in robot order: the format of prs_multi_run's final_state */
+    FILE *out = fopen(final_state, "wb");
+    if (!out) { perror(final_state); return 1; }
+    const unsigned long long n64 = params.nCells;
+    fwrite(&n64, 8, 1, out);
+    fwrite(bot.getArray(POSITION), 4, 2 * (size_t)n64, out);
+    fwrite(bot.getArray(VELOCITY), 4, 2 * (size_t)n64, out);
+    fwrite(bot.getArray(RADII), 4, (size_t)n64, out);
+    fwrite(bot.getArray(PHASE), 4, (size_t)n64, out);
+    fclose(out);
+  }
   fprintf(stderr, "ParticleBot: %ld steps, %u robots, %.3f s, %.1f steps/s, %.3e particle-steps/s\n", steps,
           params.nCells, sec, steps / sec, (double)steps * params.nCells / sec);
   if (video) fprintf(stderr, "ParticleBot: %ld video frames (%ux%u)\n", frames_written, vw, vh);

@@ -479,6 +479,21 @@ void Particlebot::reset() {
   uploadInitialState();
 }
 
+extern "C" void prs_hex_block_position(unsigned long long i, unsigned nx, unsigned ny, float pitch, float jitter, unsigned seed, float *xy) {
+  const float row = pitch * 0.8660254037844386f;
+  const float x0 = -0.5f * ((float)(nx - 1) * pitch + 0.5f * pitch), y0 = -0.5f * (float)(ny - 1) * row;
+  auto mix = [](uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31);
+  };
+  const unsigned iy = (unsigned)(i / nx), ix = (unsigned)(i % nx);
+  const uint64_t hsh = mix(((uint64_t)seed << 32) ^ (uint64_t)i);
+  const float jx = ((float)(hsh & 0xffffff) / 8388608.0f - 1.0f) * jitter;
+  const float jy = ((float)((hsh >> 24) & 0xffffff) / 8388608.0f - 1.0f) * jitter;
+  xy[0] = x0 + (float)ix * pitch + ((iy & 1u) ? 0.5f * pitch : 0.0f) + jx;
+  xy[1] = y0 + (float)iy * row + jy;
+}
+
 void Particlebot::initHexBlock(unsigned nx, unsigned ny, float pitch, float jitter, unsigned seed) {
   /* nx*ny robots on a hex lattice (row pitch = pitch*sqrt(3)/2, odd rows
    * shifted by pitch/2), centred on the origin, each coordinate jittered uniformly in +-jitter by
@@ -506,19 +521,8 @@ void Particlebot::initHexBlock(unsigned nx, unsigned ny, float pitch, float jitt
     }
     return;
   }
-  const float row = pitch * 0.8660254037844386f;
-  const float x0 = -0.5f * ((float)(nx - 1) * pitch + 0.5f * pitch), y0 = -0.5f * (float)(ny - 1) * row;
-  auto mix = [](uint64_t z) {
-    z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31);
-  };
   for (size_t i = 0; i < n; i++) {
-    const unsigned iy = (unsigned)(i / nx), ix = (unsigned)(i % nx);
-    const uint64_t hsh = mix(((uint64_t)seed << 32) ^ (uint64_t)i);
-    const float jx = ((float)(hsh & 0xffffff) / 8388608.0f - 1.0f) * jitter;
-    const float jy = ((float)((hsh >> 24) & 0xffffff) / 8388608.0f - 1.0f) * jitter;
-    hPos[2 * i] = x0 + (float)ix * pitch + ((iy & 1u) ? 0.5f * pitch : 0.0f) + jx;
-    hPos[2 * i + 1] = y0 + (float)iy * row + jy;
+    prs_hex_block_position(i, nx, ny, pitch, jitter, seed, hPos + 2 * i);
     hVel[2 * i] = hVel[2 * i + 1] = 0.0f;
   }
   (void)ny;

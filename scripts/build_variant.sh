@@ -8,5 +8,5 @@ mkdir -p particlerobotsimulations_b200/variants
 C=particlerobotsimulations_b200/csrc
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Iinclude -I$C "$@" \
   -shared -Xcompiler -fPIC,-fvisibility=hidden -Xlinker -Bsymbolic \
-  -o particlerobotsimulations_b200/variants/libparticlebot_b200_$name.so $C/prs_kernels.cu $C/prs_config.cpp $C/prs_particlebot.cpp $C/prs_video.cpp -ldl
+  -o particlerobotsimulations_b200/variants/libparticlebot_b200_$name.so $C/prs_kernels.cu $C/prs_config.cpp $C/prs_particlebot.cpp $C/prs_video.cpp $C/prs_multi.cpp -ldl -lpthread
 echo particlerobotsimulations_b200/variants/libparticlebot_b200_$name.so

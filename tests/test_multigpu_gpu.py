@@ -167,3 +167,93 @@ def test_slabs_bit_equal_to_single_gpu(world, bin_mode, exchange, scenario, tmp_
         owners = [int(got[f"owner_{k}"][-1]) for k in (1, 10, STEPS)]
         assert any(w != first_owner for w in owners), (first_owner, owners)    # the object changed hands across the cut
     sim.close()
+
+
+# ---- the C++ launcher: ParticleBot --gpus N (csrc/prs_multi.cpp), one process per rank, no Python on the path -----------------
+def _final_state(path):
+    raw = open(path, "rb").read()
+    n = int(np.frombuffer(raw, np.uint64, 1)[0])
+    f = np.frombuffer(raw, np.uint32, 6 * n, 8)
+    return {"pos": f[:2 * n], "vel": f[2 * n:4 * n], "rad": f[4 * n:5 * n], "phase": f[5 * n:6 * n]}
+
+
+def _run_launcher(tmp_path, cfg_text, ranks, steps, tag, extra=()):
+    import subprocess
+    cfg = tmp_path / f"{tag}.cfg"
+    cfg.write_text(cfg_text)
+    out = tmp_path / f"{tag}_{ranks}.bin"
+    exe = os.path.join(util.ROOT, "particlerobotsimulations_b200", "ParticleBot")
+    cmd = [exe, str(cfg), "--steps", str(steps), "--quiet", "--final-state", str(out)] + list(extra)
+    if ranks > 1:
+        cmd += ["--gpus", str(ranks)]
+        if torch.cuda.device_count() < ranks:
+            cmd.append("--oversubscribe")      # ranks share the device (time-sliced): slow, but the same code path
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return _final_state(out), r.stderr
+
+
+HEX_CFG = """nCells
+{n}
+nDead
+{dead}
+light_x
+-30
+light_y
+0
+max_time
+1e30
+seed
+5555
+sort_interval
+{sort}
+csv_filename
+launcher_{tag}.csv
+testing
+{testing}
+dump_interval
+0.1
+init_config
+hexblock
+hexblock_nx
+{nx}
+hexblock_ny
+{ny}
+hexblock_pitch
+0.17
+hexblock_jitter
+0.01
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_cpp_launcher_hexblock_equals_one_gpu(tmp_path, ranks):
+    """`ParticleBot cfg --gpus N` (forked ranks, CUDA IPC mailboxes, shared-memory control plane) == `ParticleBot cfg` on one
+    GPU, bit for bit, after 60 steps of a 49 152-robot block with 150 dead robots drawn at step 0 — positions, velocities,
+    radii, phases in robot order — and the CSV of rank 0 equals the single-GPU CSV byte for byte (centroid summed in robot
+    order).  On a box with fewer GPUs than ranks the ranks share the device."""
+    text = HEX_CFG.format(n=256 * 192, dead=150, sort=0.01, tag="hex", testing=0, nx=256, ny=192)
+    one, _ = _run_launcher(tmp_path, text, 1, 60, "hex")
+    csv_one = (tmp_path / "launcher_hex.csv").read_bytes()
+    many, err = _run_launcher(tmp_path, text, ranks, 60, "hex")
+    csv_many = (tmp_path / "launcher_hex.csv").read_bytes()
+    assert f"on {ranks} ranks" in err
+    for k in ("pos", "vel", "rad", "phase"):
+        assert np.array_equal(one[k], many[k]), k
+    assert csv_one == csv_many and csv_one.count(b"\n") >= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["example.cfg", "example_dead_cells.cfg", "example_object_transport.cfg"])
+def test_cpp_launcher_reference_cfgs_equal_one_gpu(tmp_path, name):
+    """the reference's own cfgs (aggregation placement on the glibc stream, dead draw continuing it, the transported object,
+    the reference's +-64 world whose hash wraps: ring of slabs) on 2 ranks, reference cadence, 300 steps, per-robot CSV"""
+    text = open(os.path.join(util.ROOT, "examples", name)).read() + "\ntesting\n1\ndump_interval\n0.5\ncsv_filename\nlauncher_ref.csv\n"
+    one, _ = _run_launcher(tmp_path, text, 1, 300, "ref")
+    csv_one = (tmp_path / "launcher_ref.csv").read_bytes()
+    two, _ = _run_launcher(tmp_path, text, 2, 300, "ref")
+    csv_two = (tmp_path / "launcher_ref.csv").read_bytes()
+    for k in ("pos", "vel", "rad", "phase"):
+        assert np.array_equal(one[k], two[k]), k
+    assert csv_one == csv_two and len(csv_one) > 1000
