@@ -127,6 +127,17 @@ void prs_h2d_async(void *device, const void *host, size_t bytes);
 void prs_arm_k1_event(int on);
 void prs_d2h_async(void *host, const void *device, size_t bytes, int after_k1);
 void prs_host_step_sync(void);
+/* The host-buffer step as a PIPELINE (binned sort steps of swarms of 2^18 robots and more): the next prs_fused_step takes
+ * positions, velocities and radii of robots [0, n) from the given pinned host buffers in two chunks — upload of chunk c,
+ * K1 on chunk c, and on the second stream the way back of chunk c's new positions and radii — so that the device-to-host
+ * direction of the link is busy while the host-to-device direction still is.  A step on another route (first steps,
+ * crowded swarms, steps without a sort, small swarms) uploads everything first and sends positions and radii back after K1
+ * as prs_d2h_async(.., 1) would.  Either way positions and radii are on their way when prs_fused_step returns; the caller
+ * adds the velocities (prs_d2h_async(vel, .., 0)) and prs_host_step_sync.  These uploads are the evolving state of the SAME
+ * swarm: unlike prs_h2d_async / setArray they do not withdraw the binned route's admission (the device-side guard of the
+ * in-cell ranking stays in force).  Cleared by the step that consumes it. */
+void prs_host_step_plan(const float *pos_in, const float *vel_in, const float *rad_in, float *pos_out, float *rad_out);
+void prs_set_plan_chunks(unsigned chunks); /* chunks of that pipeline (0 = default 2; 1 = no overlap of the two directions) */
 /* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
 unsigned long long prs_launch_count(int reset);
 

@@ -177,6 +177,7 @@ SIGNATURES = {
     "prs_sim_update_host": (_I, [_VP] * 7 + [_F, _F]),
     "prs_h2d_async": (None, [_VP, _VP, C.c_size_t]), "prs_arm_k1_event": (None, [_I]),
     "prs_d2h_async": (None, [_VP, _VP, C.c_size_t, _I]), "prs_host_step_sync": (None, []),
+    "prs_host_step_plan": (None, [_VP] * 5), "prs_set_plan_chunks": (None, [_U]),
     "prs_sim_checkpoint_save": (_I, [_VP, C.c_char_p]), "prs_sim_checkpoint_load": (_I, [_VP, C.c_char_p]),
     # headless frames and video
     "prs_view_from_camera": (None, [C.POINTER(View), _U, _U, _F, _F]),

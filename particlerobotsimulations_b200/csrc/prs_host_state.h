@@ -55,6 +55,17 @@ struct PrsHostState {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t k1_event = nullptr;
   bool k1_event_armed = false;
+  /* host-buffer step as a pipeline (prs_host_step_plan): where the next fused step takes its inputs from / sends positions
+   * and radii back to; chunk_events: one event per chunk of K1 */
+  struct HostPlan {
+    bool active = false;
+    const float *pos_in = nullptr, *vel_in = nullptr, *rad_in = nullptr;
+    float *pos_out = nullptr, *rad_out = nullptr;
+  } plan;
+  std::vector<cudaEvent_t> chunk_events, upload_events;
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t step_event = nullptr;
+  unsigned plan_chunks = 0;           /* chunks of the pipelined host-buffer step (0: default 2) */
   int collide_dense = 1;              /* binned sort steps of plain swarms: collide reads the dense start table of the scan */
   int k1_x2 = 1;                      /* K1 of the fused binned step: two robots per thread, vector accesses */
   int pdl = 1;                        /* 1: the fused step's kernels are launched with programmatic dependent launch */

@@ -1069,6 +1069,13 @@ void prs_d2h_async(void *host, const void *device, size_t bytes, int after_k1) {
     PRS_CUDA(cudaMemcpyAsync(host, device, bytes, cudaMemcpyDeviceToHost, g_prs.stream));
   }
 }
+void prs_host_step_plan(const float *pos_in, const float *vel_in, const float *rad_in, float *pos_out, float *rad_out) {
+  if (!g_prs.copy_stream) PRS_CUDA(cudaStreamCreateWithFlags(&g_prs.copy_stream, cudaStreamNonBlocking));
+  g_prs.plan.active = true;
+  g_prs.plan.pos_in = pos_in; g_prs.plan.vel_in = vel_in; g_prs.plan.rad_in = rad_in;
+  g_prs.plan.pos_out = pos_out; g_prs.plan.rad_out = rad_out;
+}
+void prs_set_plan_chunks(unsigned chunks) { g_prs.plan_chunks = chunks; }
 void prs_host_step_sync(void) {
   if (g_prs.copy_stream) PRS_CUDA(cudaStreamSynchronize(g_prs.copy_stream));
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
@@ -1245,13 +1252,43 @@ static void launch_collide_patch(float2 *newVel, float *fr, const float4 *pr, co
   if (e != cudaSuccess) prs_fail("k_collide_patch", e, __FILE__, __LINE__);
 }
 
+static void plan_download(const prs_step_buffers *b, uint32_t first, uint32_t count, size_t chunk);
+static const prs_step_buffers *g_plan_after_k1 = nullptr; /* planned host-buffer step on a route without the pipeline */
 static inline void k1_done() {
   if (g_prs.k1_event_armed) PRS_CUDA(cudaEventRecord(g_prs.k1_event, g_prs.stream));
+  if (g_plan_after_k1) {
+    plan_download(g_plan_after_k1, 0u, g_plan_after_k1->nCells, 0);
+    g_plan_after_k1 = nullptr;
+  }
+}
+
+/* host-buffer step (prs_host_step_plan) on a route that is not pipelined: everything up first ... */
+static void plan_upload_all(const prs_step_buffers *b, uint32_t n) {
+  const PrsHostState::HostPlan &H = g_prs.plan;
+  PRS_CUDA(cudaMemcpyAsync(b->pos, H.pos_in, (size_t)n * 8, cudaMemcpyHostToDevice, g_prs.stream));
+  PRS_CUDA(cudaMemcpyAsync(b->vel, H.vel_in, (size_t)n * 8, cudaMemcpyHostToDevice, g_prs.stream));
+  PRS_CUDA(cudaMemcpyAsync(b->rad, H.rad_in, (size_t)n * 4, cudaMemcpyHostToDevice, g_prs.stream));
+}
+/* ... and positions and radii of robots [first, first + count) back on the second stream once K1 has written them */
+static void plan_download(const prs_step_buffers *b, uint32_t first, uint32_t count, size_t chunk) {
+  PrsHostState &G = g_prs;
+  while (G.chunk_events.size() <= chunk) {
+    cudaEvent_t e;
+    PRS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    G.chunk_events.push_back(e);
+  }
+  PRS_CUDA(cudaEventRecord(G.chunk_events[chunk], G.stream));
+  PRS_CUDA(cudaStreamWaitEvent(G.copy_stream, G.chunk_events[chunk], 0));
+  PRS_CUDA(cudaMemcpyAsync(G.plan.pos_out + 2 * (size_t)first, b->pos + 2 * (size_t)first, (size_t)count * 8, cudaMemcpyDeviceToHost, G.copy_stream));
+  PRS_CUDA(cudaMemcpyAsync(G.plan.rad_out + first, b->rad + first, (size_t)count * 4, cudaMemcpyDeviceToHost, G.copy_stream));
 }
 
 void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort) {
   const uint32_t n = b->nCells;
-  if (!n) return;
+  if (!n) { g_prs.plan.active = false; return; }
+  /* the plan is this step's: whatever route the step takes, it is consumed here */
+  struct PlanScope { ~PlanScope() { g_prs.plan.active = false; g_plan_after_k1 = nullptr; } } plan_scope;
+  const bool planned = g_prs.plan.active;
   const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
   const bool need_fa = g_prs.h_prm.p.constrained_contraction != 0;
   PrsBinState &B = g_prs.bin;
@@ -1263,6 +1300,11 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
   }
   const bool patch = patch_eligible(n, need_fa, do_sort != 0) && b->sortedPR;
   const prs_bin::PatchListArgs pl = patch ? patch_begin_step() : prs_bin::PatchListArgs();
+  const bool pipelined = planned && binned && n >= (1u << 18);
+  if (planned && !pipelined) {
+    plan_upload_all(b, n);
+    g_plan_after_k1 = b;
+  }
   if (binned) {
     /* K1 + tickets -> scan (= cell table) -> scatter -> in-cell order + gather */
     bin_ensure(n, b->numCells);
@@ -1281,15 +1323,53 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
       const uintptr_t al = (uintptr_t)b->pos | (uintptr_t)b->vel | (((uintptr_t)b->rad | (uintptr_t)b->phase | (uintptr_t)b->absForce_a |
                             (uintptr_t)b->absForce_r | (uintptr_t)b->dead | (uintptr_t)b->hash | (uintptr_t)ticket) << 1);
-      if (g_prs.k1_x2 && (al & 15u) == 0 && n >= 65536u) {
-        PRS_LAUNCH_PDL(k_control_integrate_hash_x2, div_up(div_up(n, 2), 256), 256, (float4 *)b->pos, (float4 *)b->vel, (float2 *)b->rad,
-                       (const float2 *)b->phase, (const float2 *)b->absForce_a, (const float2 *)b->absForce_r, (const int2 *)b->dead,
-                       (uint2 *)b->hash, (uint2 *)ticket, time, dt, run_controller, n, B.cellCount, marks, (const uint32_t *)nullptr, 0u,
-                       0xffffffffu, 0u);
+      const bool x2 = g_prs.k1_x2 && (al & 15u) == 0 && n >= 65536u;
+      /* robots [first, first + count): the whole swarm, or one chunk of the pipelined host-buffer step (multiples of 1024
+       * robots: the vector accesses of the x2 kernel stay aligned) */
+      auto k1_range = [&](uint32_t first, uint32_t count) {
+        if (x2) {
+          PRS_LAUNCH_PDL(k_control_integrate_hash_x2, div_up(div_up(count, 2), 256), 256, (float4 *)(b->pos + 2 * (size_t)first),
+                         (float4 *)(b->vel + 2 * (size_t)first), (float2 *)(b->rad + first), (const float2 *)(b->phase + first),
+                         (const float2 *)(b->absForce_a + first), (const float2 *)(b->absForce_r + first), (const int2 *)(b->dead + first),
+                         (uint2 *)(b->hash + first), (uint2 *)(ticket + first), time, dt, run_controller, count, B.cellCount, marks,
+                         (const uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
+        } else {
+          PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(count, 256), 256, (float2 *)(b->pos + 2 * (size_t)first),
+                         (float2 *)(b->vel + 2 * (size_t)first), b->rad + first, b->phase + first, b->absForce_a + first,
+                         b->absForce_r + first, b->dead + first, b->hash + first, ticket + first, time, dt, run_controller, count,
+                         (const uint32_t *)nullptr, B.cellCount, marks, 0u, 0xffffffffu, 0u);
+        }
+      };
+      if (pipelined) {
+        /* three queues: the uploads run back to back on their own stream (a copy queue that alternates with kernels pays a
+         * hand-over per alternation), K1 of chunk c waits for its three uploads, the way back of chunk c waits for K1 */
+        const PrsHostState::HostPlan &H = g_prs.plan;
+        PrsHostState &G = g_prs;
+        const uint32_t nchunks = G.plan_chunks ? G.plan_chunks : 2u; /* measured at 2^20 robots: 1: 0.816, 2: 0.799, 4: 0.867, 8: 0.98 ms */
+        const uint32_t chunk = std::max<uint32_t>(1u << 16, ((n / nchunks) + 1023u) & ~1023u);
+        if (!G.upload_stream) PRS_CUDA(cudaStreamCreateWithFlags(&G.upload_stream, cudaStreamNonBlocking));
+        if (!G.step_event) PRS_CUDA(cudaEventCreateWithFlags(&G.step_event, cudaEventDisableTiming));
+        /* the uploads overwrite what the previous step's kernels (and copies) still read: start after them */
+        PRS_CUDA(cudaEventRecord(G.step_event, G.stream));
+        PRS_CUDA(cudaStreamWaitEvent(G.upload_stream, G.step_event, 0));
+        size_t c = 0;
+        for (uint32_t first = 0; first < n; first += chunk, c++) {
+          const uint32_t count = std::min<uint32_t>(chunk, n - first);
+          PRS_CUDA(cudaMemcpyAsync(b->pos + 2 * (size_t)first, H.pos_in + 2 * (size_t)first, (size_t)count * 8, cudaMemcpyHostToDevice, G.upload_stream));
+          PRS_CUDA(cudaMemcpyAsync(b->vel + 2 * (size_t)first, H.vel_in + 2 * (size_t)first, (size_t)count * 8, cudaMemcpyHostToDevice, G.upload_stream));
+          PRS_CUDA(cudaMemcpyAsync(b->rad + first, H.rad_in + first, (size_t)count * 4, cudaMemcpyHostToDevice, G.upload_stream));
+          while (G.upload_events.size() <= c) {
+            cudaEvent_t e;
+            PRS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            G.upload_events.push_back(e);
+          }
+          PRS_CUDA(cudaEventRecord(G.upload_events[c], G.upload_stream));
+          PRS_CUDA(cudaStreamWaitEvent(G.stream, G.upload_events[c], 0));
+          k1_range(first, count);
+          plan_download(b, first, count, c);
+        }
       } else {
-        PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
-                       b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, ticket, time, dt, run_controller, n,
-                       (const uint32_t *)nullptr, B.cellCount, marks, 0u, 0xffffffffu, 0u);
+        k1_range(0u, n);
       }
       k1_done();
     }

@@ -326,15 +326,29 @@ bool Particlebot::updateHost(const float *pos_in, const float *vel_in, const flo
     be_.copyArrayFromDevice(rad_out, dRad, 0, (int)(n * 4));
     return done;
   }
-  prs_h2d_async(dPos, pos_in, n * 8);
-  prs_h2d_async(dVel, vel_in, n * 8);
-  prs_h2d_async(dRad, rad_in, n * 4);
-  prs_arm_k1_event(1);
+  /* Steps on which update() itself reads the state before the fused step (phase update: light-distance reduction over the
+   * positions; centroid trail; dead-cell draw) or that end the run: everything up first.  All other steps hand the buffers
+   * to the fused step, which pipelines upload, K1 and the way back of positions and radii where its route allows
+   * (prs_host_step_plan). */
+  const bool reads_first = (params.control == LIGHT_WAVE && gate(time, params.phase_update_interval, deltaTime)) ||
+                           gate(time, params.centroid_int, deltaTime) ||
+                           (time >= params.time_to_dead && time < params.time_to_dead + deltaTime) || time > params.max_time;
+  if (reads_first) {
+    prs_h2d_async(dPos, pos_in, n * 8);
+    prs_h2d_async(dVel, vel_in, n * 8);
+    prs_h2d_async(dRad, rad_in, n * 4);
+    prs_arm_k1_event(1);
+    const bool done = update(deltaTime, sort_interval);
+    prs_arm_k1_event(0);
+    /* positions and radii are final once K1 ran: their way back overlaps sort, reorder and collide */
+    prs_d2h_async(pos_out, dPos, n * 8, done ? 0 : 1);
+    prs_d2h_async(rad_out, dRad, n * 4, done ? 0 : 1);
+    prs_d2h_async(vel_out, dVel, n * 8, 0);
+    prs_host_step_sync();
+    return done;
+  }
+  prs_host_step_plan(pos_in, vel_in, rad_in, pos_out, rad_out);
   const bool done = update(deltaTime, sort_interval);
-  prs_arm_k1_event(0);
-  /* positions and radii are final once K1 ran: their way back overlaps sort, reorder and collide */
-  prs_d2h_async(pos_out, dPos, n * 8, done ? 0 : 1);
-  prs_d2h_async(rad_out, dRad, n * 4, done ? 0 : 1);
   prs_d2h_async(vel_out, dVel, n * 8, 0);
   prs_host_step_sync();
   return done;

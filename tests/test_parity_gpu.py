@@ -972,6 +972,37 @@ def test_update_host_equals_set_update_get(backend, sort_every_step):
     a.close(); b.close()
 
 
+def test_update_host_pipelined_large_swarm():
+    """the host-buffer step as a pipeline (prs_host_step_plan: chunked upload / K1 / way back of positions and radii on the
+    binned route, swarms of 2^18 robots and more) == the device-resident run, bit for bit, over 30 steps that include the
+    first steps on the onesweep route (everything up first), the admission of the binned route, a phase update with noise
+    (update() reads the positions first) and the dead-cell draw"""
+    p, o = util.cfg("example")
+    nx, ny = 640, 512                      # 327 680 robots: two chunks, the second one shorter
+    p.nCells, p.nDead = nx * ny, 5000
+    p.phase_update_interval = 0.12         # phase updates at steps 0, 12, 24
+    L = prs.lib()
+    L.prs_params_set_world(C.byref(p), 1024, 128.0)
+    sims = []
+    for _ in range(2):
+        s_ = prs.Simulation(p, 128.0, prs.BACKEND_FUSED)
+        s_.srand(p.seed)
+        s_.init_hex(nx, ny, 0.17, 0.01 * p.max_radius, 5555)
+        sims.append(s_)
+    a, b = sims
+    hp, hv, hr = (np.ascontiguousarray(b.get(w)) for w in (prs.POSITION, prs.VELOCITY, prs.RADII))
+    binned_steps = 0
+    for k in range(30):
+        a.update(o.timestep, o.timestep)
+        b.update_host(hp, hv, hr, o.timestep, o.timestep)
+        binned_steps += L.prs_bin_active()
+        for w, y, name in ((prs.POSITION, hp, "pos"), (prs.VELOCITY, hv, "vel"), (prs.RADII, hr, "rad")):
+            assert np.array_equal(a.get(w).view(np.uint32), y.view(np.uint32)), (name, k)
+    assert binned_steps >= 20              # the uploads of the evolving swarm do not withdraw the binned route's admission
+    assert np.array_equal(a.get(prs.DEAD), b.get(prs.DEAD)) and int(a.get(prs.DEAD).sum()) == 5000
+    a.close(); b.close()
+
+
 def test_runner_checkpoint_files_identical(tmp_path):
     """headless runner: 75 steps in one go and 30 + (resume) 45 steps leave byte-identical checkpoints"""
     exe = os.path.join(util.ROOT, "particlerobotsimulations_b200", "ParticleBot")
