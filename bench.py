@@ -644,8 +644,11 @@ def run_sort_only(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     reps = max(5, min(args.steps, 30))
     rows = []
-    for log2n in (20, 23, 26):
-        p, o, geom = swarm_config(prs, log2n)
+    for log2n in (0, 20, 23, 26):
+        # 0: R1, 640^2 robots in the reference's own +-64 world (512^2 cells: 18-bit keys, the size every shipped cfg sorts at)
+        p, o, geom = swarm_config(prs, 0, world64=True, nx=640, ny=640) if log2n == 0 else swarm_config(prs, log2n)
+        if log2n == 0:
+            geom["name"] = "R1"
         n = int(p.nCells)
         pos = torch.from_numpy(hex_positions(p, geom)).cuda()
         # cell keys of the lattice (calcHash through the C-ABI), robots in index order: the distribution the step sorts
@@ -654,7 +657,8 @@ def run_sort_only(args):
         lib.setParameters(C.byref(p))
         lib.calcHash(keys.data_ptr(), vals.data_ptr(), pos.data_ptr(), n)
         bits = int(np.ceil(np.log2(p.numCells)))
-        passes = (bits + 7) // 8
+        plan = (C.c_int * 6)()
+        passes = int(lib.prs_sort_plan(bits, n, plan))           # digits of this sort: 8 bits, or 9 where that saves a pass
         ok, ov = torch.empty_like(keys), torch.empty_like(vals)
         ck, cv = torch.empty_like(keys), torch.empty_like(vals)
 
@@ -674,6 +678,7 @@ def run_sort_only(args):
         own()
         t_own = timed(own)
         row = {"pairs": n, "workload": workload_text(geom, n), "key_bits": bits, "radix_passes": passes,
+               "digit_bits": [int(plan[i]) for i in range(passes)], "pairs_per_thread": int(plan[4]),
                "alg_bytes_per_pair": 4 + 16 * passes,
                "onesweep": {"ms": t_own, "GBps": (4 + 16 * passes) * n / (t_own * 1e-3) / 1e9,
                             "frac_of_hbm_peak": (4 + 16 * passes) * n / (t_own * 1e-3) / 1e9 / peak}}

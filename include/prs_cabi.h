@@ -160,7 +160,10 @@ void prs_sort_pairs(const unsigned *in_keys, const unsigned *in_vals, unsigned *
 
 /* tuning aid: per-tile phase stamps of the sort kernels (8 x uint64 nanoseconds per tile and pass) */
 void prs_sort_set_timeline(unsigned long long *device_buf);
-unsigned prs_sort_tile_size(void);
+unsigned prs_sort_tile_size(void); /* pairs per tile of the last sort */
+/* the digits prs_sort_pairs uses for n pairs of key_bits-bit keys: returns the number of passes; out[0..3] = bits per
+ * pass (8, or 9 where 9-bit digits save a whole pass), out[4] = pairs per thread, out[5] = 0 */
+int prs_sort_plan(int key_bits, unsigned n, int *out);
 void prs_sort_set_threads(int threads_per_tile); /* 512, 1024, or 0 = chosen by size (default) */
 
 /* Fused whole step on the reference's buffers (same observable results as the call sequence

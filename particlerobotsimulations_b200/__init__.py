@@ -146,7 +146,7 @@ SIGNATURES = {
     "prs_min_light_distance": (None, [_VP, _I, _VP]), "prs_update_phase_dev": (None, [_VP, _VP, _F, _VP, _I]),
     "prs_centroid": (None, [_VP, _I, _VP, _VP]),
     "prs_sort_pairs": (None, [_VP, _VP, _VP, _VP, _U, _I]),
-    "prs_sort_set_timeline": (None, [_VP]), "prs_sort_tile_size": (_U, []), "prs_sort_set_threads": (None, [_I]),
+    "prs_sort_set_timeline": (None, [_VP]), "prs_sort_tile_size": (_U, []), "prs_sort_plan": (_I, [_I, _U, _VP]), "prs_sort_set_threads": (None, [_I]),
     "prs_slab_mig_words": (C.c_size_t, [_U]), "prs_slab_halo_words": (C.c_size_t, [_U]),
     "prs_slab_rng_setup": (None, [_VP, _U]), "prs_slab_k1": (None, [_VP, _F, _F, _I]),
     "prs_slab_migrate_pack": (None, [_VP, _VP, _VP]), "prs_slab_migrate_unpack": (None, [_VP, _VP, _VP]),

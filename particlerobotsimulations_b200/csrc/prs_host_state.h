@@ -80,6 +80,7 @@ struct PrsHostState {
   bool slab_binned = false, slab_table_fresh = false; /* slab engine: route of the last sort / its table not consumed yet */
   bool slab_tickets = false;          /* slab engine: this sort step's K1 took the cell tickets (binned route) */
   int sort_threads = 0;               /* tile shape of k_onesweep: 512 / 1024 threads, 0 = by size */
+  unsigned sort_tile_pairs = 0;       /* pairs per tile of the last sort (threads x pairs per thread) */
   unsigned long long *sort_timeline = nullptr; /* tuning aid, see prs_sort_set_timeline */
   /* optional per-stage CUDA-event timing of the fused step (bench.py's roofline numbers) */
   bool stage_timing = false;

@@ -730,18 +730,18 @@ static void ensure_sort_workspace(uint32_t n, int npass, int tile_pairs) {
   }
 }
 
-template <int NT>
+template <int NT, int BITS, int IT>
 static void launch_onesweep(unsigned tiles, const uint32_t *src_k, const uint32_t *src_v, uint32_t *dst_k, uint32_t *dst_v,
                             uint32_t n, int shift, const uint32_t *ghist, uint32_t *status, uint32_t *counter,
                             unsigned long long *timeline, const uint32_t *n_dev) {
+  using S = prs_sort::Smem<NT, BITS, IT>;
   static bool smem_opt_in = false;
   if (!smem_opt_in) {
-    PRS_CUDA(cudaFuncSetAttribute(prs_sort::k_onesweep<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(prs_sort::Smem<NT>)));
+    PRS_CUDA(cudaFuncSetAttribute(prs_sort::k_onesweep<NT, BITS, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
     smem_opt_in = true;
   }
-  PRS_LAUNCH(prs_sort::k_onesweep<NT>, tiles, NT, sizeof(prs_sort::Smem<NT>), src_k, src_v, dst_k, dst_v, n, shift, ghist,
-             status, counter, timeline, n_dev);
+  PRS_LAUNCH((prs_sort::k_onesweep<NT, BITS, IT>), tiles, NT, sizeof(S), src_k, src_v, dst_k, dst_v, n, shift, ghist, status, counter,
+             timeline, n_dev);
 }
 
 /* stable sort of n pairs by the low key_bits of the key; result in out_* (may alias in_*).
@@ -754,20 +754,24 @@ static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out
   if (n == 0) return;
   if (key_bits < 1) key_bits = 1;
   if (key_bits > 32) key_bits = 32;
-  const int npass = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
-  /* tile shape: 1024 threads x 8 pairs while all tiles fit one wave (one per SM), else 512 x 8 with two
-   * tiles resident per SM; prs_sort_set_threads() pins one of them */
-  const int nt = g_prs.sort_threads ? g_prs.sort_threads : ((n <= 148u * 8192u) ? 1024 : 512);
-  const int tile_pairs = nt * ITEMS;
+  /* digits of this sort: 8 bits, or 9 where that saves a pass; 8 or 12 pairs per thread (prs_onesweep.cuh) */
+  const PassPlan plan = plan_passes(key_bits, n);
+  const int npass = plan.npass;
+  /* tile shape: 1024 threads while all tiles fit one wave (one per SM), else 512 with two tiles resident per SM;
+   * prs_sort_set_threads() pins one of them.  12 pairs per thread only exist for 512 threads. */
+  int nt = g_prs.sort_threads ? g_prs.sort_threads : ((n <= 148u * 8192u) ? 1024 : 512);
+  const int items = (nt == 512) ? plan.items : 8;
+  const int tile_pairs = nt * items;
+  g_prs.sort_tile_pairs = (unsigned)tile_pairs;
   ensure_sort_workspace(n, npass, tile_pairs);
   Workspace &w = g_prs.sort_ws;
   const uint32_t tiles = div_up(n, tile_pairs);
   uint32_t *ghist = w.meta;
-  uint32_t *counters = w.meta + MAX_PASSES * RADIX;
+  uint32_t *counters = w.meta + MAX_PASSES * MAX_RADIX;
   uint32_t *status = counters + MAX_PASSES;
   PRS_CUDA(cudaMemsetAsync(w.meta, 0, meta_words(n, npass, tile_pairs) * 4, g_prs.stream));
   const unsigned hist_blocks = min(div_up(n, HIST_THREADS * 8), 148u * 8u);
-  PRS_LAUNCH(k_histogram, hist_blocks, HIST_THREADS, 0, in_k, n, ghist, npass, n_dev);
+  PRS_LAUNCH(k_histogram, hist_blocks, HIST_THREADS, 0, in_k, n, ghist, plan, n_dev);
   const uint32_t *src_k = in_k, *src_v = vals_are_iota ? nullptr : in_v;
   /* a single pass (key_bits <= 8) would scatter into the buffer its other tiles still read when out_* aliases
    * in_*: it then lands in scratch and is copied back */
@@ -778,12 +782,18 @@ static void sort_pairs(const uint32_t *in_k, const uint32_t *in_v, uint32_t *out
     if (p == npass - 1 && !bounce) { dst_k = out_k; dst_v = out_v; }
     else { dst_k = w.keys[p & 1]; dst_v = w.vals[p & 1]; }
     unsigned long long *tl = g_prs.sort_timeline ? g_prs.sort_timeline + (size_t)p * tiles * 8 : nullptr;
-    if (nt == 512)
-      launch_onesweep<512>(tiles, src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
-                           status + (size_t)p * tiles * RADIX, counters + p, tl, n_dev);
-    else
-      launch_onesweep<1024>(tiles, src_k, src_v, dst_k, dst_v, n, p * RADIX_BITS, ghist + p * RADIX,
-                            status + (size_t)p * tiles * RADIX, counters + p, tl, n_dev);
+    const uint32_t *gh = ghist + p * MAX_RADIX;
+    uint32_t *st = status + (size_t)p * tiles * MAX_RADIX;
+    const int shift = plan.shift[p];
+    const bool wide = plan.bits[p] == 9;
+    if (nt == 512) {
+      if (wide) launch_onesweep<512, 9, 8>(tiles, src_k, src_v, dst_k, dst_v, n, shift, gh, st, counters + p, tl, n_dev);
+      else if (items == 12) launch_onesweep<512, 8, 12>(tiles, src_k, src_v, dst_k, dst_v, n, shift, gh, st, counters + p, tl, n_dev);
+      else launch_onesweep<512, 8, 8>(tiles, src_k, src_v, dst_k, dst_v, n, shift, gh, st, counters + p, tl, n_dev);
+    } else {
+      if (wide) launch_onesweep<1024, 9, 8>(tiles, src_k, src_v, dst_k, dst_v, n, shift, gh, st, counters + p, tl, n_dev);
+      else launch_onesweep<1024, 8, 8>(tiles, src_k, src_v, dst_k, dst_v, n, shift, gh, st, counters + p, tl, n_dev);
+    }
     src_k = dst_k;
     src_v = dst_v;
   }
@@ -1109,7 +1119,16 @@ void prs_centroid(const float *pos, int n, float *d_scratch, float *d_out) {
 /* tuning aid: when set, the next sorts write 8 %globaltimer stamps per tile and pass into buf
  * (device memory, passes * tiles * 8 words); nullptr switches it off */
 void prs_sort_set_timeline(unsigned long long *buf) { g_prs.sort_timeline = buf; }
-unsigned prs_sort_tile_size(void) { return (unsigned)((g_prs.sort_threads ? g_prs.sort_threads : 512) * prs_sort::ITEMS); }
+int prs_sort_plan(int key_bits, unsigned n, int *out) {
+  if (key_bits < 1) key_bits = 1;
+  if (key_bits > 32) key_bits = 32;
+  const prs_sort::PassPlan plan = prs_sort::plan_passes(key_bits, n);
+  for (int p = 0; p < 4; p++) out[p] = p < plan.npass ? plan.bits[p] : 0;
+  out[4] = plan.items;
+  out[5] = 0;
+  return plan.npass;
+}
+unsigned prs_sort_tile_size(void) { return g_prs.sort_tile_pairs ? g_prs.sort_tile_pairs : 4096u; } /* pairs per tile of the last sort */
 /* tile shape of the sort: 512 (several tiles per SM) or 1024 threads x 8 pairs */
 void prs_sort_set_threads(int nt) { g_prs.sort_threads = (nt == 1024) ? 1024 : (nt == 512 ? 512 : 0); }
 

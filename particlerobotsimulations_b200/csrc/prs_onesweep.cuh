@@ -46,9 +46,13 @@ __device__ __forceinline__ void stamp(unsigned long long *timeline, uint32_t til
   }
 }
 
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int ITEMS = 8;
+/* Digit width and pairs per thread are template parameters of the pass kernel, chosen per sort by plan_passes():
+ * 8-bit digits (256 bins) by default; 9-bit digits (512 bins) where they save a whole pass over the pairs — 26-bit cell
+ * keys of the 8192^2 grid in (9, 9, 8) instead of four passes, 18-bit keys of the reference's 512^2 grid in (9, 9) instead
+ * of three — a 512-bin pass costs ~10 % more than a 256-bin one, a pass saved is worth 100 %; 12 pairs per thread instead
+ * of 8 for large inputs with 8-bit digits (fewer tiles: fewer look-backs and barriers per pair). */
+constexpr int MAX_RADIX_BITS = 9;
+constexpr int MAX_RADIX = 1 << MAX_RADIX_BITS;
 constexpr int MAX_PASSES = 4;
 constexpr int HIST_THREADS = 256;
 
@@ -56,41 +60,71 @@ constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PREFIX = 2u << 30;
 constexpr uint32_t VALUE_MASK = (1u << 30) - 1;
 
-template <int NT>
+template <int NT, int BITS, int IT>
 struct Cfg {
+  static_assert(BITS == 8 || BITS == 9, "supported digit widths");
+  static constexpr int RADIX_BITS = BITS;
+  static constexpr int RADIX = 1 << BITS;
+  static constexpr int SCAN_WARPS = RADIX / 32;        /* warps whose threads hold one digit each in the block-wide scans */
+  static constexpr int ITEMS = IT;
   static constexpr int THREADS = NT;
   static constexpr int WARPS = NT / 32;
   static constexpr int TILE = NT * ITEMS;
-  static constexpr int GROUPS = NT / RADIX;            /* groups of 8 warps in the cross-warp prefix */
+  static constexpr int GROUPS = NT / RADIX;            /* threads per digit in the cross-warp prefix: each sums a group of warps */
+  static constexpr int WPG = WARPS / GROUPS;           /* warps per group: 8 (256 bins) or 16 (512 bins) */
   static constexpr int DIGITS_PER_WARP = RADIX / WARPS; /* look-back: digits owned by a warp */
   static constexpr int LANES_PER_DIGIT = 32 / DIGITS_PER_WARP;
-  static_assert(WARPS / GROUPS == 8 && (NT == 512 || NT == 1024), "supported tile shapes");
+  static_assert(GROUPS >= 1 && WPG * GROUPS == WARPS && (NT == 512 || NT == 1024), "supported tile shapes");
 };
 
-/* dynamic shared memory of k_onesweep (NT = 512: 68 KB, NT = 1024: 133 KB) */
-template <int NT>
+/* dynamic shared memory of k_onesweep (NT = 512, 8 bits, 8 items: 68 KB; NT = 1024: 133 KB) */
+template <int NT, int BITS, int IT>
 struct __align__(16) Smem {
-  uint32_t cnt[Cfg<NT>::WARPS][RADIX]; /* per-warp digit counters -> exclusive offsets across warps */
-  uint32_t part[Cfg<NT>::GROUPS][RADIX]; /* digit totals of each group of 8 warps */
+  static constexpr int RADIX = Cfg<NT, BITS, IT>::RADIX;
+  uint32_t cnt[Cfg<NT, BITS, IT>::WARPS][RADIX]; /* per-warp digit counters -> exclusive offsets across warps */
+  uint32_t part[Cfg<NT, BITS, IT>::GROUPS][RADIX]; /* digit totals of each group of WPG warps */
   uint32_t tile_base[RADIX];          /* first slot of each digit inside the tile */
   uint32_t gbase[RADIX];              /* output position of slot 0 of each digit minus its tile slot */
   uint32_t count[RADIX];              /* this tile's digit counts (padding removed) */
-  uint32_t mask[Cfg<NT>::WARPS][RADIX]; /* (warp, digit) match words of the ranking loop */
-  uint32_t keys[Cfg<NT>::TILE];       /* staging of the tile in sorted order */
-  uint32_t vals[Cfg<NT>::TILE];
-  uint32_t warp_tot[2][8];
+  uint32_t mask[Cfg<NT, BITS, IT>::WARPS][RADIX]; /* (warp, digit) match words of the ranking loop */
+  uint32_t keys[Cfg<NT, BITS, IT>::TILE];       /* staging of the tile in sorted order */
+  uint32_t vals[Cfg<NT, BITS, IT>::TILE];
+  uint32_t warp_tot[2][Cfg<NT, BITS, IT>::SCAN_WARPS];
   uint32_t tile;
 };
 
 /* Digit histograms of every pass in one sweep.  Cell keys of neighbouring robots share their
  * high digits, so a warp whose 32 keys agree on a digit adds 32 with one atomic; mixed warps use
  * plain shared-memory atomics (few-way conflicts). */
+/* the digits of one sort: pass p takes `bits[p]` bits from bit `shift[p]` on (plan_passes) */
+struct PassPlan {
+  int npass;
+  int shift[MAX_PASSES], bits[MAX_PASSES];
+  int items; /* pairs per thread of the pass kernels */
+};
+/* 8-bit digits unless 9-bit ones save a pass; then as few 9-bit passes as cover the key */
+inline PassPlan plan_passes(int key_bits, uint32_t n) {
+  PassPlan P;
+  const int n8 = (key_bits + 7) / 8, n9 = (key_bits + 8) / 9;
+  P.npass = n9 < n8 ? n9 : n8;
+  const int wide = n9 < n8 ? (key_bits - 8 * P.npass > 0 ? key_bits - 8 * P.npass : 0) : 0; /* passes that need the ninth bit */
+  int at = 0;
+  for (int p = 0; p < MAX_PASSES; p++) {
+    P.shift[p] = at;
+    P.bits[p] = (p < wide) ? 9 : 8;
+    if (p < P.npass) at += P.bits[p];
+  }
+  P.items = (wide == 0 && n >= (1u << 22)) ? 12 : 8;
+  return P;
+}
+
 __global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t *__restrict__ keys, uint32_t n,
-                                                            uint32_t *__restrict__ ghist, int npass,
+                                                            uint32_t *__restrict__ ghist, const PassPlan plan,
                                                             const uint32_t *__restrict__ n_dev) {
   if (n_dev) n = *n_dev;
-  __shared__ uint32_t sh[MAX_PASSES][RADIX];
-  for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&sh[0][0])[i] = 0;
+  const int npass = plan.npass;
+  __shared__ uint32_t sh[MAX_PASSES][MAX_RADIX];
+  for (int i = threadIdx.x; i < MAX_PASSES * MAX_RADIX; i += HIST_THREADS) (&sh[0][0])[i] = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t n_round = (n + 31u) & ~31u;
@@ -99,21 +133,29 @@ __global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t *__re
     const uint32_t k = valid ? keys[i] : 0u;
     const uint32_t active = __ballot_sync(0xffffffffu, valid);
     const int src = __ffs(active) - 1;
-    for (int p = 0; p < npass; p++) {
-      const uint32_t d = (k >> (p * RADIX_BITS)) & (RADIX - 1);
-      const uint32_t d0 = __shfl_sync(0xffffffffu, d, src);
-      const bool uniform = __all_sync(0xffffffffu, !valid || d == d0);
-      if (uniform) {
-        if ((int)lane == src) atomicAdd(&sh[p][d0], (uint32_t)__popc(active));
-      } else if (valid) {
-        atomicAdd(&sh[p][d], 1u);
+#pragma unroll
+    for (int p = 0; p < MAX_PASSES; p++) { /* unrolled: the plan is read from the parameter bank with constant indices */
+      if (p < npass) {
+        const uint32_t d = (k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
+        const uint32_t d0 = __shfl_sync(0xffffffffu, d, src);
+        const bool uniform = __all_sync(0xffffffffu, !valid || d == d0);
+        if (uniform) {
+          if ((int)lane == src) atomicAdd(&sh[p][d0], (uint32_t)__popc(active));
+        } else if (valid) {
+          atomicAdd(&sh[p][d], 1u);
+        }
       }
     }
   }
   __syncthreads();
-  for (int p = 0; p < npass; p++) {
-    const uint32_t c = sh[p][threadIdx.x];
-    if (c) atomicAdd(&ghist[p * RADIX + threadIdx.x], c);
+#pragma unroll
+  for (int p = 0; p < MAX_PASSES; p++) {
+    if (p < npass) {
+      for (int d = threadIdx.x; d < (1 << plan.bits[p]); d += HIST_THREADS) {
+        const uint32_t c = sh[p][d];
+        if (c) atomicAdd(&ghist[p * MAX_RADIX + d], c);
+      }
+    }
   }
 }
 
@@ -128,20 +170,21 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
   return inc - v;
 }
 
-/* exclusive scans over digits 0..255 of TWO values held by threads 0..255 (one set of barriers);
+/* exclusive scans over digits 0..RADIX-1 of TWO values held by threads 0..RADIX-1 (one set of barriers);
  * every thread of the block must call it */
-__device__ __forceinline__ void excl_scan2_256(uint32_t &a, uint32_t &b, uint32_t (*s_tot)[8]) {
+template <int SCAN_WARPS>
+__device__ __forceinline__ void excl_scan2(uint32_t &a, uint32_t &b, uint32_t (*s_tot)[SCAN_WARPS]) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t ta = 0, tb = 0, ea = 0, eb = 0;
-  if (warp < 8) {
+  if (warp < SCAN_WARPS) {
     ea = warp_excl_scan(a, lane, &ta);
     eb = warp_excl_scan(b, lane, &tb);
     if (lane == 0) { s_tot[0][warp] = ta; s_tot[1][warp] = tb; }
   }
   __syncthreads();
-  if (warp < 8) {
+  if (warp < SCAN_WARPS) {
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
+    for (int w = 0; w < SCAN_WARPS; w++) {
       ea += (w < (int)warp) ? s_tot[0][w] : 0u;
       eb += (w < (int)warp) ? s_tot[1][w] : 0u;
     }
@@ -152,17 +195,18 @@ __device__ __forceinline__ void excl_scan2_256(uint32_t &a, uint32_t &b, uint32_
 
 /* One digit pass.  vin == nullptr means "values are the input positions" (first pass after
  * calcHash, where index[i] = i), which saves reading 4 B per pair. */
-template <int NT>
+template <int NT, int BITS, int IT>
 __global__ void __launch_bounds__(NT, (NT == 512) ? 2 : 1)
 k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
            uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ ghist,
            volatile uint32_t *status, uint32_t *tile_counter, unsigned long long *timeline,
            const uint32_t *__restrict__ n_dev) {
-  using C = Cfg<NT>;
+  using C = Cfg<NT, BITS, IT>;
   if (n_dev) n = *n_dev; /* slab ranks: launched for the capacity, tiles past the real count exit */
   constexpr int THREADS = C::THREADS, WARPS = C::WARPS, TILE = C::TILE, GROUPS = C::GROUPS;
+  constexpr int RADIX = C::RADIX, RADIX_BITS = C::RADIX_BITS, ITEMS = C::ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<NT> &S = *reinterpret_cast<Smem<NT> *>(smem_raw);
+  Smem<NT, BITS, IT> &S = *reinterpret_cast<Smem<NT, BITS, IT> *>(smem_raw);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
@@ -206,14 +250,15 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
   __syncthreads();
   stamp(timeline, tile, 1);
 
-  /* 3. warp counts -> exclusive offsets across the warps: thread (digit, group of 8 warps) */
+  /* 3. warp counts -> exclusive offsets across the warps: thread (digit, group of WPG warps) */
   const uint32_t dg = tid & (RADIX - 1), grp = tid >> RADIX_BITS;
   {
-    uint32_t c[8], run = 0;
+    constexpr int WPG = C::WPG;
+    uint32_t c[WPG], run = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) c[w] = S.cnt[grp * 8 + w][dg];
+    for (int w = 0; w < WPG; w++) c[w] = S.cnt[grp * WPG + w][dg];
 #pragma unroll
-    for (int w = 0; w < 8; w++) { const uint32_t cw = c[w]; c[w] = run; run += cw; }
+    for (int w = 0; w < WPG; w++) { const uint32_t cw = c[w]; c[w] = run; run += cw; }
     S.part[grp][dg] = run;
     __syncthreads();
     uint32_t before = 0, total = 0;
@@ -226,13 +271,13 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
     uint32_t tbase = 0, gex = 0;
     if (grp == 0) {
       uint32_t count = total;
-      if (dg == RADIX - 1) count -= (uint32_t)TILE - tile_valid; /* padding is not data */
+      if (dg == ((0xffffffffu >> shift) & (RADIX - 1))) count -= (uint32_t)TILE - tile_valid; /* padding (key 0xffffffff: the last entries of the largest digit) is not data */
       S.count[dg] = count;
       if (tile != 0) status[(size_t)tile * RADIX + dg] = count | FLAG_AGG;
       tbase = total;
       gex = gh;
     }
-    excl_scan2_256(tbase, gex, S.warp_tot); /* digit start inside the tile / in the output */
+    excl_scan2<C::SCAN_WARPS>(tbase, gex, S.warp_tot); /* digit start inside the tile / in the output */
     if (tid < RADIX) {
       S.tile_base[tid] = tbase;
       S.gbase[tid] = gex - tbase;
@@ -241,7 +286,7 @@ k_onesweep(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, u
     /* cnt[w][d] becomes the first staging slot of warp w's keys with digit d */
     const uint32_t off = S.tile_base[dg] + before;
 #pragma unroll
-    for (int w = 0; w < 8; w++) S.cnt[grp * 8 + w][dg] = off + c[w];
+    for (int w = 0; w < WPG; w++) S.cnt[grp * WPG + w][dg] = off + c[w];
   }
   __syncthreads();
   stamp(timeline, tile, 2);
@@ -363,9 +408,10 @@ struct Workspace {
   size_t cap_pairs = 0, cap_meta = 0;
 };
 
+/* meta: [histograms MAX_PASSES * MAX_RADIX][tile counters MAX_PASSES][status: passes * tiles * MAX_RADIX] */
 inline size_t meta_words(uint32_t n, int npass, int tile_pairs) {
   const size_t tiles = (n + tile_pairs - 1) / tile_pairs;
-  return (size_t)MAX_PASSES * RADIX + MAX_PASSES + (size_t)npass * tiles * RADIX;
+  return (size_t)MAX_PASSES * MAX_RADIX + MAX_PASSES + (size_t)npass * tiles * MAX_RADIX;
 }
 
 }  // namespace prs_sort

@@ -99,9 +99,15 @@ def test_calc_hash_bit_exact(n):
 
 
 @pytest.mark.parametrize("n,bits", [(1, 18), (31, 18), (4096, 18), (4097, 18), (300, 18), (100_003, 22), (1 << 20, 22),
-                                    (50_000, 32), (70_000, 7)])
+                                    (50_000, 32), (70_000, 7),
+                                    # digit plans of prs_onesweep.cuh: (9, 8), (9, 9) in tiles of 512 threads, (9, 9, 8), (9, 9, 9),
+                                    # 12 pairs per thread (8-bit digits, 2^22 pairs and more), a ragged last tile each
+                                    (33_333, 17), (2_000_003, 18), (3_000_001, 26), (1_300_007, 27), (4_200_011, 24)])
 def test_sort_bit_exact_and_stable(n, bits):
     L = prs.lib()
+    plan = (C.c_int * 6)()
+    npass = L.prs_sort_plan(bits, n, plan)
+    assert sum(plan[:npass]) >= bits and npass == min((bits + 7) // 8, (bits + 8) // 9) and all(b in (8, 9) for b in plan[:npass])
     rng = np.random.default_rng(n + bits)
     keys = (rng.integers(0, 2 ** bits, n, dtype=np.uint64)).astype(np.uint32)
     if n > 1000:
