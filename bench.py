@@ -706,6 +706,26 @@ def run_sort_only(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(gpu_index):
+    """Pins this process to the CPUs NVML lists as local to its GPU, so that the pinned host buffers of the e2e block are
+    first-touched on the GPU's own NUMA node (torchrun binds nothing: with 8 ranks on two sockets half of the host <-> device
+    traffic otherwise crosses the socket link).  Returns the number of CPUs bound to, or 0 if nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_slabs(args, rank, world, local_rank):
     """--gpus N (N > 1): S2 (2^26 robots, or --robots-log2) slab-decomposed over the ranks.  Before timing, the slab
     engine is checked bit for bit against the single-GPU path on the live ranks (multigpu.selfcheck_vs_single_gpu);
@@ -715,6 +735,7 @@ def run_slabs(args, rank, world, local_rank):
     import particlerobotsimulations_b200 as prs
     from particlerobotsimulations_b200 import multigpu
 
+    bound_cpus = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if not dist.is_initialized():
@@ -792,6 +813,12 @@ def run_slabs(args, rank, world, local_rank):
             stages[name] = {"us_per_step": per_step_us, "alg_bytes_per_robot": per_bytes[name], "achieved_GBps": gbs,
                             "frac_of_hbm_peak": (gbs / peak) if gbs else None}
 
+    # every rank's stage times: the ranks run in lock step through the halo waits, so imbalance shows up as `exchange`
+    # time (waiting for a slower neighbour) on the faster ranks
+    all_stages = [None] * world
+    dist.all_gather_object(all_stages, {k: round(v["us_per_step"], 1) for k, v in stages.items()})
+    stages_per_rank = {k: [st_.get(k) for st_ in all_stages] for k in stages}
+
     # ---- e2e: every rank's pos/vel/rad come from pinned host memory and go back to it every step ----
     e2e_steps = max(3, min(args.steps, 20))
     e2e_s = sim.time_host_steps(o.timestep, sort_interval, e2e_steps)
@@ -829,12 +856,13 @@ def run_slabs(args, rank, world, local_rank):
             "parity_check": parity,
             "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 20 * n_total,
                     "d2h_bytes_per_step": 20 * n_total, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "what": "per rank: pos/vel/rad of the owned robots from pinned host -> device, SlabSim.step, device -> pinned host"},
+                    "what": "per rank: pos/vel/rad of the owned robots from pinned host -> device, SlabSim.step, device -> pinned host",
+                    "cpus_bound_rank0": bound_cpus},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": ({"bound": "hbm", "kernel": "collide (rank 0)", "achieved": stages["collide"]["achieved_GBps"], "peak": peak,
                           "unit": "GB/s", "frac": stages["collide"]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
                           "note": "collide is FP32/MUFU-issue-bound, not HBM-bound; see roofline_step"} if "collide" in stages else None),
-            "stages_rank0": stages, "cpu_baseline": None,
+            "stages_rank0": stages, "stages_us_per_rank": stages_per_rank, "cpu_baseline": None,
             "roofline_step": {"bound": "hbm", "alg_bytes_per_particle_step": b_alg, "radix_passes": passes,
                               "achieved": b_alg * value / 1e9, "peak": peak * world, "unit": "GB/s",
                               "frac": b_alg * value / 1e9 / (peak * world), "peak_source": peak_src + f" x {world} GPUs"},

@@ -116,6 +116,10 @@ void prs_set_k1_x2(int on);
 /* 1 (default) = on binned sort steps of plain swarms collide takes the slot range of a stencil row from the dense start table
  * the scan writes next to cellStart / cellEnd (two words per row instead of six); 0 = always from cellStart / cellEnd.  Same results. */
 void prs_set_collide_dense(int on);
+/* slab ranks, binned sort: 1 (default) the scan over the owned rows' cells skips the tiles outside the range the slab's
+ * robots occupied after the previous sort, widened by a row of movement and the reach of a stencil; tickets taken outside
+ * it make that step scan everything (device-side, csrc/prs_cellbin.cuh).  Same results. */
+void prs_set_slab_scan_range(int on);
 /* steps without a sort: swarms of up to max_robots run controller+integrate and the gather into the sorted
  * copy as ONE kernel (one launch less per step; default 65536, 0 = never).  Same bits. */
 void prs_set_fuse_gather_max(unsigned max_robots);
@@ -283,6 +287,11 @@ typedef struct {
   int sorted_once;
   unsigned seq_halo, seq_mig, split_fallbacks;
   unsigned *h_err;
+  /* 1: the exchange kernels of the step in their fused forms — the rest of the migration after the leavers are packed as
+   * ONE single-block kernel, the flags published by the last block of the halo pack kernel, the wait for the neighbours
+   * folded into the unpack kernel together with the clearing of the table's halo rows (15 launches per sort step instead
+   * of 25); 0: one kernel per operation.  Same results. */
+  int fused_exchange;
 } prs_slab_ctx;
 size_t prs_slab_mailbox_words(unsigned mig_cap, unsigned halo_cap);
 unsigned prs_slab_step(prs_slab_ctx *c, float dt, float sort_interval);
@@ -368,6 +377,7 @@ typedef struct {
   int quiet;
   const char *final_state;  /* optional file: rank 0 writes nCells, then pos, vel, rad, phase of the whole swarm in robot order */
   int overlap_exchange;     /* prs_slab_ctx.overlap_exchange */
+  int fused_exchange;       /* prs_slab_ctx.fused_exchange */
 } prs_multi_options;
 int prs_multi_run(const SimParams *p, const prs_run_options *opt, const prs_multi_options *m);
 /* position of robot i of the synthetic hex block (the generator of Particlebot::initHexBlock / prs_init_hex_block) */

@@ -101,7 +101,7 @@ class SlabCtx(C.Structure):
                 ("mw", C.c_uint), ("hw", C.c_uint), ("scratch_mig", C.c_void_p * 2), ("scratch_halo", C.c_void_p * 2),
                 ("d_min_d", C.c_void_p), ("allreduce_min", ALLREDUCE_MIN_FN), ("user", C.c_void_p), ("overlap_exchange", C.c_int),
                 ("time", C.c_float), ("sorted_once", C.c_int), ("seq_halo", C.c_uint), ("seq_mig", C.c_uint),
-                ("split_fallbacks", C.c_uint), ("h_err", C.c_void_p)]
+                ("split_fallbacks", C.c_uint), ("h_err", C.c_void_p), ("fused_exchange", C.c_int)]
 
 
 # words of Slab.counts (PRS_SC_*) and error bits (PRS_SLAB_ERR_*)
@@ -139,7 +139,7 @@ SIGNATURES = {
     "prs_set_collide_warp_max": (None, [_U]),
     "prs_set_collide_tile": (None, [_I]), "prs_get_collide_tile": (_I, []),
     "prs_set_patch_rows": (None, [_U]), "prs_patch_stats": (None, [_I, _VP]),
-    "prs_set_pdl": (None, [_I]), "prs_get_pdl": (_I, []), "prs_set_k1_x2": (None, [_I]), "prs_set_collide_dense": (None, [_I]),
+    "prs_set_pdl": (None, [_I]), "prs_get_pdl": (_I, []), "prs_set_k1_x2": (None, [_I]), "prs_set_collide_dense": (None, [_I]), "prs_set_slab_scan_range": (None, [_I]),
     "prs_set_fuse_gather_max": (None, [_U]),
     "prs_launch_count": (C.c_ulonglong, [_I]),
     "prs_stage_timing": (None, [_I]), "prs_stage_times": (None, [_VP, _VP]),

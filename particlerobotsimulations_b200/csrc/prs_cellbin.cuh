@@ -46,6 +46,32 @@ struct PatchListArgs {
   uint32_t epoch = 0, log2_gx = 0, PH = 0;
 };
 
+/* Slab ranks (prs_slab.cuh): tile RANGE of the scan.  A slab owns whole grid rows, of which its robots may occupy a small
+ * part (the first and the last slab of a swarm own every row down to / up to the grid's edge): `range` = {first tile, last
+ * tile, violated} — the tiles (relative to the slab's first cell) between which the slab's sorted keys lay after the
+ * previous sort; the scan processes those tiles widened by `dil` (a grid row of movement between two sorts + the reach of a
+ * stencil) and skips the rest, whose table entries are empty and stay so.  Every ticket taken more than a grid row outside
+ * the range (K1, the arrivals of the migration) sets `violated`, and the scan of that step processes every tile: always
+ * correct, never dependent on the host. */
+__device__ __forceinline__ uint32_t range_margin() { /* tiles a robot may move between two sorts without notice: one grid row */
+  return max(1u, c_prm.p.gridSize.x / (uint32_t)(512 * 8));
+}
+__device__ __forceinline__ void range_check(uint32_t *range, uint32_t tile) {
+  const uint32_t m = range_margin();
+  if (tile + m < range[0] || tile > range[1] + m) atomicOr(range + 2, 1u);
+}
+struct RangeArgs {
+  const uint32_t *range = nullptr;
+  uint32_t dil = 0;
+};
+__device__ __forceinline__ bool range_skips(const RangeArgs &ra, uint32_t tile) {
+  if (!ra.range) return false;
+  const uint32_t lo = ra.range[0], hi = ra.range[1], violated = ra.range[2];
+  if (violated) return false;
+  if (lo > hi) return true; /* an empty slab */
+  return tile + ra.dil < lo || tile > hi + ra.dil;
+}
+
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -81,11 +107,11 @@ __device__ __forceinline__ void load_counts(const uint32_t *cellCount, uint32_t 
  * done" counter, per-robot tile sums from K1, a running maximum — each cost 10-100 us in L2) */
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_tile_sums(const uint32_t *__restrict__ cellCount, uint32_t C, uint32_t *scratch, const uint32_t *marks = nullptr,
-                 const DenseArgs dn = DenseArgs()) {
+                 const DenseArgs dn = DenseArgs(), const RangeArgs ra = RangeArgs()) {
   prs::pdl_sync();
   __shared__ uint32_t s_sum[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  bool own = true;
+  bool own = !range_skips(ra, blockIdx.x);
   if (marks && dn.live) {
     /* liveness for the dense table: this tile or one within dil tiles (cyclically: the hash wraps) was hashed into.  All mark
      * words are requested at once (one round trip), the first warp decides */
@@ -162,11 +188,12 @@ template <bool SELF_PREFIX>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_apply(uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart, uint32_t *__restrict__ cellEnd, uint32_t C,
              uint32_t *scratch, uint32_t slot_offset, uint32_t *marks = nullptr, uint32_t *prev_marks = nullptr,
-             const PatchListArgs pl = PatchListArgs(), const DenseArgs dn = DenseArgs()) {
+             const PatchListArgs pl = PatchListArgs(), const DenseArgs dn = DenseArgs(), const RangeArgs ra = RangeArgs()) {
   prs::pdl_sync();
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c0 = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
+  if (range_skips(ra, blockIdx.x)) return; /* outside the slab's tile range: empty before, empty now */
   if (marks) {
     /* Tiles no robot hashed into (K1 marks the tile of every hash): their counters are all zero.  If the
      * tile was also empty in the previous step its cellStart words are 0xffffffff already and nothing is

@@ -20,6 +20,9 @@ struct PrsBinState {
   int mode = 0;               /* 0 auto, 1 never, 2 always */
   bool admitted = false;      /* the swarm is known to be sparse enough */
   unsigned generation = 0;    /* bumped whenever positions are rewritten behind the library's back */
+  uint32_t *range = nullptr;  /* slab ranks: {first tile, last tile, violated, -} of the scan (prs_cellbin.cuh: range_check) */
+  const void *range_table = nullptr; /* the slab geometry those words were written for: cellStart, row_lo, row_hi */
+  unsigned range_row_lo = 0, range_row_hi = 0;
   uint32_t *h_report = nullptr; /* pinned: [0] largest cell population, [1] error flag */
   cudaEvent_t report_event = nullptr;
   bool report_pending = false;
@@ -66,6 +69,7 @@ struct PrsHostState {
   cudaStream_t upload_stream = nullptr;
   cudaEvent_t step_event = nullptr;
   unsigned plan_chunks = 0;           /* chunks of the pipelined host-buffer step (0: default 2) */
+  int slab_scan_range = 1;            /* slab ranks: the scan skips the tiles outside the range the slab's robots occupy */
   int collide_dense = 1;              /* binned sort steps of plain swarms: collide reads the dense start table of the scan */
   int k1_x2 = 1;                      /* K1 of the fused binned step: two robots per thread, vector accesses */
   int pdl = 1;                        /* 1: the fused step's kernels are launched with programmatic dependent launch */
@@ -78,6 +82,7 @@ struct PrsHostState {
   PrsPatchState patch;
   bool slab_sorted_onesweep = false;
   bool slab_binned = false, slab_table_fresh = false; /* slab engine: route of the last sort / its table not consumed yet */
+  bool slab_range_in_use = false;     /* slab engine: this sort step's tickets are checked against the scan's tile range */
   bool slab_tickets = false;          /* slab engine: this sort step's K1 took the cell tickets (binned route) */
   int sort_threads = 0;               /* tile shape of k_onesweep: 512 / 1024 threads, 0 = by size */
   unsigned sort_tile_pairs = 0;       /* pairs per tile of the last sort (threads x pairs per thread) */

@@ -301,7 +301,8 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
                          const int *__restrict__ dead, uint32_t *__restrict__ hash, uint32_t *__restrict__ index,
                          float time, float dt, int run_controller, uint32_t n, const uint32_t *__restrict__ n_dev,
                          uint32_t *__restrict__ cellCount = nullptr, uint32_t *__restrict__ tileMark = nullptr,
-                         uint32_t row_lo = 0u, uint32_t row_hi = 0xffffffffu, uint32_t log2_gx = 0u) {
+                         uint32_t row_lo = 0u, uint32_t row_hi = 0xffffffffu, uint32_t log2_gx = 0u,
+                         uint32_t *range = nullptr, uint32_t range_tile0 = 0u) {
   prs::pdl_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
@@ -333,7 +334,9 @@ k_control_integrate_hash(float2 *__restrict__ pos, float2 *__restrict__ vel, flo
     if (COUNT) {
       /* slab ranks: a robot whose new row left [row_lo, row_hi) migrates and takes its ticket where it arrives */
       const uint32_t row = h >> log2_gx;
-      index[i] = (row >= row_lo && row < row_hi) ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu;
+      const bool mine = row >= row_lo && row < row_hi;
+      index[i] = mine ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu;
+      if (range && mine) prs_bin::range_check(range, h / prs_bin::SCAN_TILE - range_tile0);
     } else {
       index[i] = i;
     }
@@ -357,14 +360,21 @@ k_control_integrate_hash_x2(float4 *__restrict__ pos, float4 *__restrict__ vel, 
                             const float2 *__restrict__ phase, const float2 *__restrict__ fa, const float2 *__restrict__ fr,
                             const int2 *__restrict__ dead, uint2 *__restrict__ hash, uint2 *__restrict__ ticket, float time, float dt,
                             int run_controller, uint32_t n, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ tileMark,
-                            const uint32_t *__restrict__ n_dev, uint32_t row_lo, uint32_t row_hi, uint32_t log2_gx) {
+                            const uint32_t *__restrict__ n_dev, uint32_t row_lo, uint32_t row_hi, uint32_t log2_gx,
+                            uint32_t *range, uint32_t range_tile0) {
   prs::pdl_sync();
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i0 = 2u * t;
   if (n_dev) n = *n_dev; /* slab ranks keep their robot count on the device */
   if (i0 >= n) return;
-  /* slab ranks: a robot whose new row left [row_lo, row_hi) migrates and takes its ticket where it arrives */
-  auto take = [&](uint32_t h) { const uint32_t row = h >> log2_gx; return (row >= row_lo && row < row_hi) ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu; };
+  /* slab ranks: a robot whose new row left [row_lo, row_hi) migrates and takes its ticket where it arrives; a ticket outside
+   * the scan's tile range of this step widens the scan to every tile (prs_bin::range_check) */
+  auto take = [&](uint32_t h) {
+    const uint32_t row = h >> log2_gx;
+    if (!(row >= row_lo && row < row_hi)) return 0xffffffffu;
+    if (range) prs_bin::range_check(range, h / prs_bin::SCAN_TILE - range_tile0);
+    return atomicAdd(&cellCount[h], 1u);
+  };
   const bool cc = c_prm.p.constrained_contraction != 0;
   if (i0 + 1u >= n) { /* odd tail: one robot, scalar accesses */
     float2 p = reinterpret_cast<float2 *>(pos)[i0], v = reinterpret_cast<float2 *>(vel)[i0];
@@ -1052,6 +1062,7 @@ void prs_set_k1_x2(int on) { g_prs.k1_x2 = on ? 1 : 0; }
 /* 1 (default): on binned sort steps of plain swarms collide finds its stencil rows in the dense start table the scan writes (10 table
  * words per robot instead of 30); 0: always through cellStart / cellEnd */
 void prs_set_collide_dense(int on) { g_prs.collide_dense = on ? 1 : 0; }
+void prs_set_slab_scan_range(int on) { g_prs.slab_scan_range = on ? 1 : 0; g_prs.bin.range_table = nullptr; }
 
 /* ---- host-buffer step (Particlebot::updateHost): asynchronous copies around prs_fused_step ----
  * prs_h2d_async: pinned host -> device on the launching stream (counts as an upload: the binned route re-earns
@@ -1182,6 +1193,11 @@ static void bin_ensure(uint32_t n, uint32_t C) {
     PRS_CUDA(cudaMalloc(&B.scratch, prs_bin::scan_scratch_words(C) * 4));
     PRS_CUDA(cudaMemsetAsync(B.scratch, 0, prs_bin::scan_scratch_words(C) * 4, g_prs.stream));
     if (B.marks) PRS_CUDA(cudaFree(B.marks));
+    if (!B.range) {
+      PRS_CUDA(cudaMalloc(&B.range, 4 * 4));
+      PRS_CUDA(cudaMemsetAsync(B.range, 0, 4 * 4, g_prs.stream));
+    }
+    B.range_table = nullptr;
     const size_t tiles = (C + prs_bin::SCAN_TILE - 1) / prs_bin::SCAN_TILE;
     /* [0, tiles * MARK_WAYS) marks of this step, then one word per tile for the previous step */
     PRS_CUDA(cudaMalloc(&B.marks, (tiles * prs_bin::MARK_WAYS + tiles) * 4));
@@ -1351,12 +1367,12 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
                          (float4 *)(b->vel + 2 * (size_t)first), (float2 *)(b->rad + first), (const float2 *)(b->phase + first),
                          (const float2 *)(b->absForce_a + first), (const float2 *)(b->absForce_r + first), (const int2 *)(b->dead + first),
                          (uint2 *)(b->hash + first), (uint2 *)(ticket + first), time, dt, run_controller, count, B.cellCount, marks,
-                         (const uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
+                         (const uint32_t *)nullptr, 0u, 0xffffffffu, 0u, (uint32_t *)nullptr, 0u);
         } else {
           PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(count, 256), 256, (float2 *)(b->pos + 2 * (size_t)first),
                          (float2 *)(b->vel + 2 * (size_t)first), b->rad + first, b->phase + first, b->absForce_a + first,
                          b->absForce_r + first, b->dead + first, b->hash + first, ticket + first, time, dt, run_controller, count,
-                         (const uint32_t *)nullptr, B.cellCount, marks, 0u, 0xffffffffu, 0u);
+                         (const uint32_t *)nullptr, B.cellCount, marks, 0u, 0xffffffffu, 0u, (uint32_t *)nullptr, 0u);
         }
       };
       if (pipelined) {
@@ -1401,14 +1417,14 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     }
     {
       StageScope t(PRS_STAGE_SORT);
-      PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch, (const uint32_t *)marks, dn);
+      PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->numCells, B.scratch, (const uint32_t *)marks, dn, prs_bin::RangeArgs());
       if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u, marks, prev_marks, pl, dn);
+                       B.scratch, 0u, marks, prev_marks, pl, dn, prs_bin::RangeArgs());
       } else {
         PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
         PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount, b->cellStart, b->cellEnd, b->numCells,
-                       B.scratch, 0u, marks, prev_marks, pl, dn);
+                       B.scratch, 0u, marks, prev_marks, pl, dn, prs_bin::RangeArgs());
       }
       PRS_LAUNCH_PDL(prs_bin::k_cell_scatter, div_up(n, 256), 256, b->hash, ticket, b->cellStart, hash_by_slot, index_by_slot, n);
     }
@@ -1462,7 +1478,7 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
     StageScope t(PRS_STAGE_K1);
     PRS_LAUNCH_PDL((k_control_integrate_hash<false, false>), div_up(n, 256), 256, (float2 *)b->pos, (float2 *)b->vel, b->rad,
                    b->phase, b->absForce_a, b->absForce_r, b->dead, b->hash, b->index, time, dt, run_controller, n,
-                   (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
+                   (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u, (uint32_t *)nullptr, 0u);
     k1_done();
   }
   if (b->sortedPR) {

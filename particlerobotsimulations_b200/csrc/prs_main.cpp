@@ -30,7 +30,7 @@ int main(int argc, char **argv) {
   bool video = false;
   const char *video_path = 0, *ppm_path = 0;
   unsigned vw = 1920, vh = 1080;
-  int gpus = 1, oversubscribe = 0, overlap = 1;
+  int gpus = 1, oversubscribe = 0, overlap = 1, fused_exchange = 1;
   const char *final_state = 0;
   int positional = 0;
   for (int i = 1; i < argc; i++) {
@@ -52,6 +52,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--oversubscribe")) oversubscribe = 1;
     else if (!strcmp(argv[i], "--no-overlap")) overlap = 0;
+    else if (!strcmp(argv[i], "--no-fused-exchange")) fused_exchange = 0;
     else if (!strcmp(argv[i], "--final-state") && i + 1 < argc) final_state = argv[++i];
     else if (!strcmp(argv[i], "--no-csv")) csv = false;
     else if (!strcmp(argv[i], "--quiet")) quiet = true;
@@ -69,7 +70,7 @@ int main(int argc, char **argv) {
     }
     prs_multi_options mo;
     mo.gpus = gpus; mo.oversubscribe = oversubscribe; mo.steps = max_steps; mo.csv = csv ? 1 : 0; mo.quiet = quiet ? 1 : 0;
-    mo.final_state = final_state; mo.overlap_exchange = overlap;
+    mo.final_state = final_state; mo.overlap_exchange = overlap; mo.fused_exchange = fused_exchange;
     return prs_multi_run(&params, &opt, &mo);
   }
 

@@ -129,6 +129,7 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
   std::vector<unsigned> gid;
   std::vector<unsigned> rows(world + 1, 0);
   PrsRand stream; /* the glibc stream after the placement: the dead draw continues it */
+  size_t row_max = 0; /* robots in the fullest grid row of the initial state (the same number on every rank) */
   if (opt.init_hexblock) {
     const unsigned nx = opt.hexblock_nx, ny = opt.hexblock_ny;
     if ((size_t)nx * ny != n_total) die(rank, "hexblock_nx * hexblock_ny != nCells");
@@ -155,6 +156,7 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
       dead.push_back(object ? 1 : 0);
     }
     stream.seed(p.seed); /* main.cpp:929; a generated swarm draws nothing from the stream */
+    row_max = (size_t)((double)nx * p.cellSize.y / row) + 1; /* lattice rows per grid row x robots per lattice row */
   } else {
     /* the cfg's placement: the same host code and the same stream on every rank */
     std::vector<float> hp(2 * n_total), hr(n_total), hph(n_total);
@@ -172,6 +174,7 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
     /* slab boundaries by equal robot count: cuts on the cumulative histogram of robots per grid row */
     std::vector<size_t> hist(GY, 0);
     for (size_t i = 0; i < n_total; i++) hist[(size_t)grid_row(hp[2 * i + 1], p)]++;
+    row_max = *std::max_element(hist.begin(), hist.end());
     size_t cum = 0;
     unsigned row_i = 0;
     for (int b = 1; b < world; b++) {
@@ -195,9 +198,10 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
   prs_set_world_half_extent(half);
   setParameters(&p);
   const size_t n_expected = n_total / world + 1;
-  const unsigned cap = (unsigned)(n_expected * 5 / 4 + n_expected / 2) + 65536u; /* head room for unequal slabs and migration */
-  const unsigned halo_cap = std::max<unsigned>(65536u, cap / 10);
-  const unsigned mig_cap = std::max<unsigned>(4096u, cap / 128);
+  const unsigned cap = (unsigned)(n_expected * 5 / 4) + 65536u; /* head room for unequal slabs and migration */
+  /* a halo is halo_rows grid rows, a step's migrants a fraction of one: sized from the fullest grid row (1.6x head room) */
+  const unsigned halo_cap = (unsigned)std::min<size_t>((size_t)(1.6 * HALO_ROWS * (double)row_max) + 4096u, (size_t)cap);
+  const unsigned mig_cap = std::max<unsigned>(4096u, (unsigned)std::min<size_t>(row_max / 2, (size_t)cap));
   if (n_own > cap) die(rank, "slab capacity exceeded by the initial state");
   const size_t ncat = (size_t)cap + 2 * (size_t)halo_cap;
   prs_slab s;
@@ -259,6 +263,7 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
   c.allreduce_min = allreduce_min_cb;
   c.user = &me;
   c.overlap_exchange = m.overlap_exchange;
+  c.fused_exchange = m.fused_exchange;
 
   /* ---- the run ---- */
   FILE *fp = nullptr;
@@ -291,13 +296,22 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
     me.barrier();
   };
   const float dt = opt.timestep;
+  const bool want_dump = m.csv || !m.quiet; /* the CSV row, or its echo on stdout (particlebot.cpp:366); neither: no gather */
   long steps = 0;
   const auto t0 = std::chrono::steady_clock::now();
+  auto t_steady = t0;
+  long steady_from = -1;
   while (m.steps < 0 || steps < m.steps) {
     const float time = c.time;
+    if (steps == 20) { /* steady state: the first sorts (onesweep route, scratch allocations) are behind */
+      threadSync();
+      me.barrier();
+      t_steady = std::chrono::steady_clock::now();
+      steady_from = steps;
+    }
     if (time > p.max_time) break; /* Particlebot::update: the reference exit(0)s here */
     /* dumpParticlebot (particlebot.cpp:303-367) on rank 0 from the gathered swarm */
-    if (!(time - opt.dump_interval * floorf(time / opt.dump_interval) > 0.01f)) {
+    if (want_dump && !(time - opt.dump_interval * floorf(time / opt.dump_interval) > 0.01f)) {
       gather(p.testing != 0);
       if (rank == 0) {
         const unsigned count = (unsigned)n_total;
@@ -360,7 +374,8 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
     _exit(1);
   }
   me.barrier();
-  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  const auto t_end = std::chrono::steady_clock::now();
+  const double sec = std::chrono::duration<double>(t_end - t0).count();
   if (m.final_state) {
     gather(true);
     if (rank == 0) {
@@ -380,6 +395,11 @@ int rank_main(int rank, int world, Shared *sh, float *g_state, SimParams p, cons
     fclose(fp);
     fprintf(stderr, "ParticleBot: %ld steps, %zu robots on %d ranks, %.3f s, %.1f steps/s, %.3e particle-steps/s\n", steps, n_total,
             world, sec, steps / sec, (double)steps * n_total / sec);
+    if (steady_from >= 0 && steps > steady_from) {
+      const double s2 = std::chrono::duration<double>(t_end - t_steady).count();
+      fprintf(stderr, "ParticleBot: steps %ld..%ld: %.3f ms/step, %.3e particle-steps/s\n", steady_from, steps,
+              1e3 * s2 / (steps - steady_from), (double)(steps - steady_from) * n_total / s2);
+    }
   }
   prs_slab_ctx_release(&c);
   me.barrier(); /* nobody unmaps a mailbox a neighbour may still write to */

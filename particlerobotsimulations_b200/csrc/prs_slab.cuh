@@ -66,10 +66,11 @@ __device__ __forceinline__ void slab_move_record(const prs_slab &s, uint32_t dst
 }
 
 /* resets the per-step counters (everything except n and the statistics) */
-__global__ void k_slab_begin_step(uint32_t *counts) {
+__global__ void k_slab_begin_step(uint32_t *counts, uint32_t *range) {
   prs::pdl_sync();
   const int i = threadIdx.x;
   if (i >= PRS_SC_NLO && i <= PRS_SC_KEEPERS) counts[i] = 0;
+  if (i == 0 && range) range[2] = 0u; /* "a ticket was taken outside the scan's tile range": per step */
 }
 
 /* M1: robots whose new grid row left [row_lo, row_hi) are packed for the neighbour that owns it
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(256) k_slab_fill_holes(prs_slab s, uint32_t *_
   if (ticket) ticket[dst] = ticket[src]; /* the cell ticket K1 took travels with the robot */
 }
 __global__ void __launch_bounds__(256) k_slab_append(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up,
-                                                     uint32_t log2_gx, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ ticket) {
+                                                     uint32_t log2_gx, uint32_t *__restrict__ cellCount, uint32_t *__restrict__ ticket,
+                                                     uint32_t *range, uint32_t range_tile0) {
   prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N], L = s.counts[PRS_SC_LEAVERS];
   const uint32_t c_dn = s.has_dn ? min(recv_dn[0], s.mig_cap) : 0u, c_up = s.has_up ? min(recv_up[0], s.mig_cap) : 0u;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) k_slab_append(prs_slab s, const uint32_t 
   const bool mine = row >= s.row_lo && row < s.row_hi;
   if (!mine) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_TWO_SLABS);
   if (ticket) ticket[dst] = mine ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu; /* binned sort: the arrival's cell ticket */
+  if (ticket && mine && range) prs_bin::range_check(range, h / prs_bin::SCAN_TILE - range_tile0);
 }
 __global__ void k_slab_commit_count(prs_slab s, const uint32_t *__restrict__ recv_dn, const uint32_t *__restrict__ recv_up) {
   prs::pdl_sync();
@@ -222,7 +225,7 @@ __device__ __forceinline__ uint32_t slab_lower_bound(const uint32_t *hash, uint3
 /* The first / last halo_rows grid rows of the owned sorted range are contiguous slices; thread 0
  * finds them, then the block copies them into the outgoing buffers (count word first). */
 __global__ void __launch_bounds__(256) k_slab_halo_pack(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up,
-                                                        uint32_t gx) {
+                                                        uint32_t gx, uint32_t *range, uint32_t range_tile0) {
   prs::pdl_sync();
   const uint32_t n = s.counts[PRS_SC_N];
   const uint32_t *hs = s.hash_cat + s.halo_cap; /* owned keys, sorted */
@@ -236,7 +239,13 @@ __global__ void __launch_bounds__(256) k_slab_halo_pack(prs_slab s, uint32_t *__
       k_dn = min(k_dn, s.halo_cap); k_up = min(k_up, s.halo_cap);
     }
     sh[0] = k_dn; sh[1] = k_up;
-    if (blockIdx.x == 0) { send_dn[0] = k_dn; send_up[0] = k_up; s.counts[PRS_SC_KDN] = k_dn; s.counts[PRS_SC_KUP] = k_up; }
+    if (blockIdx.x == 0) {
+      send_dn[0] = k_dn; send_up[0] = k_up; s.counts[PRS_SC_KDN] = k_dn; s.counts[PRS_SC_KUP] = k_up;
+      if (range) { /* tiles between which the owned sorted keys lie: the range of the NEXT sort's scan (prs_cellbin.cuh) */
+        range[0] = n ? hs[0] / prs_bin::SCAN_TILE - range_tile0 : 1u;
+        range[1] = n ? hs[n - 1] / prs_bin::SCAN_TILE - range_tile0 : 0u;
+      }
+    }
   }
   __syncthreads();
   const uint32_t k_dn = sh[0], k_up = sh[1];
@@ -395,6 +404,188 @@ __global__ void __launch_bounds__(256) k_slab_halo_table(prs_slab s) {
 }
 
 /* -------------------------------------------------------------------------------------------- */
+/* fused forms used by prs_slab_step (peer-to-peer exchange): fewer, fatter launches               */
+/* -------------------------------------------------------------------------------------------- */
+#define PRS_SC_PACK_DONE 13 /* counts[13]: blocks of the halo pack kernel that have finished (reset by the last one) */
+
+__device__ __forceinline__ bool slab_spin(const volatile unsigned *flag, unsigned seq) {
+  unsigned long long spins = 0;
+  while ((int)(*flag - seq) < 0) {
+    __nanosleep(64);
+    if (++spins > (1ull << 24)) return false; /* never hang the GPU */
+  }
+  return true;
+}
+
+/* The rest of the migration after k_slab_select, in ONE block (a step moves a few dozen robots across a slab cut; six
+ * launches — list_holes, signal, wait, fill_holes, append, commit — cost more than the work): count words of the outgoing
+ * buffers and the flags that publish them; holes and movers; movers into holes; wait for the neighbours' records; arrivals
+ * appended (with their cell tickets on the binned route); robot count committed. */
+__global__ void __launch_bounds__(1024)
+k_slab_mig_finish(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up, unsigned *flag_out_dn,
+                  unsigned *flag_out_up, const unsigned *flag_in_dn, const unsigned *flag_in_up, unsigned seq,
+                  uint32_t *recv_dn, uint32_t *recv_up, uint32_t log2_gx, uint32_t *__restrict__ cellCount,
+                  uint32_t *__restrict__ ticket, uint32_t *range, uint32_t range_tile0) {
+  prs::pdl_sync();
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n = s.counts[PRS_SC_N], L = s.counts[PRS_SC_LEAVERS];
+  if (tid == 0) {
+    send_dn[0] = min(s.counts[PRS_SC_MIGDN], s.mig_cap);
+    send_up[0] = min(s.counts[PRS_SC_MIGUP], s.mig_cap);
+    __threadfence_system(); /* the records (k_slab_select, complete) and the counts before the flags */
+    if (flag_out_dn) *reinterpret_cast<volatile unsigned *>(flag_out_dn) = seq;
+    if (flag_out_up) *reinterpret_cast<volatile unsigned *>(flag_out_up) = seq;
+    __threadfence_system();
+  }
+  const uint32_t new_n = n - L;
+  uint32_t *holes = s.lists + 2 * s.mig_cap, *movers = s.lists + 4 * s.mig_cap;
+  for (uint32_t q = tid; q < L; q += blockDim.x) {
+    const uint32_t li = s.lists[q];
+    if (li < new_n) holes[atomicAdd(&s.counts[PRS_SC_HOLES], 1u)] = li;
+    const uint32_t j = new_n + q; /* the L slots of the tail */
+    if (!s.scratch[j]) movers[atomicAdd(&s.counts[PRS_SC_KEEPERS], 1u)] = j;
+  }
+  __syncthreads();
+  const uint32_t H = *reinterpret_cast<volatile uint32_t *>(&s.counts[PRS_SC_HOLES]);
+  for (uint32_t q = tid; q < H; q += blockDim.x) {
+    const uint32_t dst = holes[q], src = movers[q];
+    slab_move_record(s, dst, src);
+    if (ticket) ticket[dst] = ticket[src]; /* the cell ticket K1 took travels with the robot */
+  }
+  /* the neighbours' records */
+  if (tid < 2) {
+    const unsigned *f = tid == 0 ? flag_in_dn : flag_in_up;
+    if (f && !slab_spin(f, seq)) {
+      atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_PEER_TIMEOUT);
+      *(tid == 0 ? recv_dn : recv_up) = 0u; /* nothing stale is consumed */
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const uint32_t c_dn = s.has_dn ? min(*reinterpret_cast<volatile uint32_t *>(recv_dn), s.mig_cap) : 0u;
+  const uint32_t c_up = s.has_up ? min(*reinterpret_cast<volatile uint32_t *>(recv_up), s.mig_cap) : 0u;
+  for (uint32_t q = tid; q < c_dn + c_up; q += blockDim.x) {
+    const uint32_t dst = new_n + q;
+    if (dst >= s.cap) { atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_CAPACITY); continue; }
+    if (q < c_dn) slab_load_record(recv_dn, s.mig_cap, q, s, dst);
+    else slab_load_record(recv_up, s.mig_cap, q - c_dn, s, dst);
+    const uint32_t h = s.hash[dst];
+    const uint32_t row = h >> log2_gx; /* a robot may cross one slab per sort at most */
+    const bool mine = row >= s.row_lo && row < s.row_hi;
+    if (!mine) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_TWO_SLABS);
+    if (ticket) ticket[dst] = mine ? atomicAdd(&cellCount[h], 1u) : 0xffffffffu; /* binned sort: the arrival's cell ticket */
+    if (ticket && mine && range) prs_bin::range_check(range, h / prs_bin::SCAN_TILE - range_tile0);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t nn = new_n + c_dn + c_up;
+    if (nn > s.cap) nn = s.cap;
+    s.counts[PRS_SC_N] = nn;
+    s.counts[PRS_SC_STAT_MIG] += L;
+  }
+}
+
+/* k_slab_halo_pack whose LAST block publishes the exchange's sequence number in the neighbours' flag words */
+__global__ void __launch_bounds__(256) k_slab_halo_pack_signal(prs_slab s, uint32_t *__restrict__ send_dn, uint32_t *__restrict__ send_up,
+                                                               uint32_t gx, unsigned *flag_dn, unsigned *flag_up, unsigned seq, uint32_t *range,
+                                                               uint32_t range_tile0) {
+  prs::pdl_sync();
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t *hs = s.hash_cat + s.halo_cap; /* owned keys, sorted */
+  __shared__ uint32_t sh[2];
+  if (threadIdx.x == 0) {
+    uint32_t k_dn = 0, k_up = 0;
+    if (s.has_dn) k_dn = slab_lower_bound(hs, n, min(s.row_lo + s.halo_rows, s.row_hi) * gx);
+    if (s.has_up) k_up = n - slab_lower_bound(hs, n, (s.row_hi > s.row_lo + s.halo_rows ? s.row_hi - s.halo_rows : s.row_lo) * gx);
+    if (k_dn > s.halo_cap || k_up > s.halo_cap) {
+      if (blockIdx.x == 0) atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_HALO_CAP);
+      k_dn = min(k_dn, s.halo_cap); k_up = min(k_up, s.halo_cap);
+    }
+    sh[0] = k_dn; sh[1] = k_up;
+    if (blockIdx.x == 0) {
+      send_dn[0] = k_dn; send_up[0] = k_up; s.counts[PRS_SC_KDN] = k_dn; s.counts[PRS_SC_KUP] = k_up;
+      if (range) { /* tiles between which the owned sorted keys lie: the range of the NEXT sort's scan (prs_cellbin.cuh) */
+        range[0] = n ? hs[0] / prs_bin::SCAN_TILE - range_tile0 : 1u;
+        range[1] = n ? hs[n - 1] / prs_bin::SCAN_TILE - range_tile0 : 0u;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t k_dn = sh[0], k_up = sh[1];
+  const float4 *pr = (const float4 *)s.sortedPR + s.halo_cap;
+  const float2 *sv = (const float2 *)s.sortedVel + s.halo_cap;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < k_dn + k_up; q += gridDim.x * blockDim.x) {
+    const bool lower = q < k_dn;
+    const uint32_t r = lower ? q : q - k_dn;              /* record number in its buffer */
+    const uint32_t k = lower ? q : n - k_up + r;           /* owned sorted slot */
+    uint32_t *o = (lower ? send_dn : send_up) + 1 + r;
+    const float4 a = pr[k];
+    const float2 v = sv[k];
+    o[0 * s.halo_cap] = __float_as_uint(a.x); o[1 * s.halo_cap] = __float_as_uint(a.y);
+    o[2 * s.halo_cap] = __float_as_uint(a.z); o[3 * s.halo_cap] = __float_as_uint(a.w);
+    o[4 * s.halo_cap] = __float_as_uint(v.x); o[5 * s.halo_cap] = __float_as_uint(v.y);
+    o[6 * s.halo_cap] = hs[k];
+  }
+  /* every thread's peer stores ordered at system scope, then the block checks in; the last block publishes */
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&s.counts[PRS_SC_PACK_DONE], 1u);
+    if (done == gridDim.x - 1) {
+      s.counts[PRS_SC_PACK_DONE] = 0u;
+      __threadfence_system();
+      if (flag_dn) *reinterpret_cast<volatile unsigned *>(flag_dn) = seq;
+      if (flag_up) *reinterpret_cast<volatile unsigned *>(flag_up) = seq;
+      __threadfence_system();
+    }
+  }
+}
+
+/* up to four ranges of cellStart words to be set to "empty" (the halo rows around the slab, wrapped ones included) */
+struct SlabClears { uint32_t *ptr[4]; uint32_t words[4]; };
+
+/* k_slab_halo_unpack that waits for the neighbours' flags itself (every block polls: the grid is resident) and clears
+ * the halo rows of the cell table on the way */
+__global__ void __launch_bounds__(256) k_slab_halo_unpack_wait(prs_slab s, uint32_t *recv_dn, uint32_t *recv_up, const unsigned *flag_dn,
+                                                               const unsigned *flag_up, unsigned seq, const SlabClears cl) {
+  prs::pdl_sync();
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < cl.words[r]; w += gridDim.x * blockDim.x) cl.ptr[r][w] = 0xffffffffu;
+  __shared__ uint32_t s_drop[2];
+  if (threadIdx.x < 2) {
+    const unsigned *f = threadIdx.x == 0 ? flag_dn : flag_up;
+    bool ok = true;
+    if (f && !slab_spin(f, seq)) {
+      ok = false;
+      atomicOr(&s.counts[PRS_SC_ERR], PRS_SLAB_ERR_PEER_TIMEOUT);
+    }
+    s_drop[threadIdx.x] = ok ? 0u : 1u;
+    __threadfence_system();
+  }
+  __syncthreads();
+  const uint32_t n = s.counts[PRS_SC_N];
+  const uint32_t n_lo = (s.has_dn && !s_drop[0]) ? min(*reinterpret_cast<volatile uint32_t *>(recv_dn), s.halo_cap) : 0u;
+  const uint32_t n_hi = (s.has_up && !s_drop[1]) ? min(*reinterpret_cast<volatile uint32_t *>(recv_up), s.halo_cap) : 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    s.counts[PRS_SC_NLO] = n_lo; s.counts[PRS_SC_NHI] = n_hi;
+    s.counts[PRS_SC_STAT_HALO] += n_lo + n_hi;
+  }
+  float4 *pr = (float4 *)s.sortedPR;
+  float2 *sv = (float2 *)s.sortedVel;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_lo + n_hi; q += gridDim.x * blockDim.x) {
+    const bool lower = q < n_lo;
+    const uint32_t r = lower ? q : q - n_lo;
+    const uint32_t k = lower ? s.halo_cap - n_lo + r : s.halo_cap + n + r;
+    const uint32_t *o = (lower ? recv_dn : recv_up) + 1 + r;
+    pr[k] = make_float4(__uint_as_float(o[0 * s.halo_cap]), __uint_as_float(o[1 * s.halo_cap]),
+                        __uint_as_float(o[2 * s.halo_cap]), __uint_as_float(o[3 * s.halo_cap]));
+    sv[k] = make_float2(__uint_as_float(o[4 * s.halo_cap]), __uint_as_float(o[5 * s.halo_cap]));
+    s.hash_cat[k] = o[6 * s.halo_cap];
+  }
+}
+
+/* -------------------------------------------------------------------------------------------- */
 /* C entry points                                                                                 */
 /* -------------------------------------------------------------------------------------------- */
 extern "C" {
@@ -406,6 +597,26 @@ static uint32_t slab_log2_gx() {
 }
 static void slab_check(const prs_slab *s) {
   if (!s->cap || !s->halo_cap || !s->mig_cap) { fprintf(stderr, "prs_slab: zero capacity\n"); exit(EXIT_FAILURE); }
+}
+
+/* tile range of the slab's scan (prs_cellbin.cuh RangeArgs): usable when the slab's first cell starts a scan tile.
+ * slab_range_ptr: the device words, or nullptr when the feature is off / not applicable;
+ * slab_range_valid: the words describe THIS slab (a halo pack kernel wrote them for this geometry) */
+static uint32_t slab_range_tile0(const prs_slab *s) {
+  return (uint32_t)(((size_t)s->row_lo * g_prs.h_prm.p.gridSize.x) / prs_bin::SCAN_TILE);
+}
+static uint32_t *slab_range_ptr(const prs_slab *s) {
+  if (!g_prs.slab_scan_range || !g_prs.bin.range) return nullptr;
+  if (((size_t)s->row_lo * g_prs.h_prm.p.gridSize.x) % prs_bin::SCAN_TILE) return nullptr;
+  return g_prs.bin.range;
+}
+static bool slab_range_valid(const prs_slab *s) {
+  const PrsBinState &B = g_prs.bin;
+  return slab_range_ptr(s) && B.range_table == (const void *)s->cellStart && B.range_row_lo == s->row_lo && B.range_row_hi == s->row_hi;
+}
+static void slab_range_written(const prs_slab *s) {
+  PrsBinState &B = g_prs.bin;
+  B.range_table = s->cellStart; B.range_row_lo = s->row_lo; B.range_row_hi = s->row_hi;
 }
 
 size_t prs_slab_mig_words(unsigned mig_cap) { return 1 + (size_t)SLAB_MIG_WORDS * mig_cap; }
@@ -423,7 +634,7 @@ void prs_slab_k1(const prs_slab *s, float time, float dt, int do_hash) {
   slab_check(s);
   const int run_controller = (g_prs.h_prm.p.control == LIGHT_WAVE && time >= 0) ? 1 : 0;
   StageScope t(PRS_STAGE_K1);
-  PRS_LAUNCH_PDL(k_slab_begin_step, 1, 32, s->counts);
+  PRS_LAUNCH_PDL(k_slab_begin_step, 1, 32, s->counts, g_prs.bin.range);
   g_prs.slab_tickets = false;
   if (do_hash) {
     PrsBinState &B = g_prs.bin;
@@ -434,28 +645,32 @@ void prs_slab_k1(const prs_slab *s, float time, float dt, int do_hash) {
     if (g_prs.slab_binned) {
       bin_ensure(s->cap, g_prs.h_prm.p.numCells);
       PRS_CUDA(cudaMemsetAsync(B.scratch, 0, 16, g_prs.stream));
+      /* tickets outside the tile range of this step's scan are noticed where they are taken (only while the range is in use) */
+      g_prs.slab_range_in_use = slab_range_valid(s);
+      uint32_t *k1_range = g_prs.slab_range_in_use ? slab_range_ptr(s) : nullptr;
       const uintptr_t al = (uintptr_t)s->pos | (uintptr_t)s->vel | (((uintptr_t)s->rad | (uintptr_t)s->phase | (uintptr_t)s->absForce_a |
                             (uintptr_t)s->absForce_r | (uintptr_t)s->dead | (uintptr_t)s->hash | (uintptr_t)g_prs.sort_ws.vals[0]) << 1);
       if (g_prs.k1_x2 && (al & 15u) == 0) {
         PRS_LAUNCH_PDL(k_control_integrate_hash_x2, div_up(div_up(s->cap, 2), 256), 256, (float4 *)s->pos, (float4 *)s->vel, (float2 *)s->rad,
                        (const float2 *)s->phase, (const float2 *)s->absForce_a, (const float2 *)s->absForce_r, (const int2 *)s->dead,
                        (uint2 *)s->hash, (uint2 *)g_prs.sort_ws.vals[0], time, dt, run_controller, s->cap, B.cellCount, (uint32_t *)nullptr,
-                       (const uint32_t *)(s->counts + PRS_SC_N), s->row_lo, s->row_hi, slab_log2_gx());
+                       (const uint32_t *)(s->counts + PRS_SC_N), s->row_lo, s->row_hi, slab_log2_gx(), k1_range, slab_range_tile0(s));
       } else {
         PRS_LAUNCH_PDL((k_control_integrate_hash<true, true>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
                        s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, g_prs.sort_ws.vals[0], time, dt, run_controller, s->cap,
-                       (const uint32_t *)(s->counts + PRS_SC_N), B.cellCount, (uint32_t *)nullptr, s->row_lo, s->row_hi, slab_log2_gx());
+                       (const uint32_t *)(s->counts + PRS_SC_N), B.cellCount, (uint32_t *)nullptr, s->row_lo, s->row_hi, slab_log2_gx(),
+                       k1_range, slab_range_tile0(s));
       }
       g_prs.slab_tickets = true;
     } else {
       PRS_LAUNCH_PDL((k_control_integrate_hash<true, false>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
                      s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap,
-                     (const uint32_t *)(s->counts + PRS_SC_N), (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
+                     (const uint32_t *)(s->counts + PRS_SC_N), (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u, (uint32_t *)nullptr, 0u);
     }
   } else {
     PRS_LAUNCH_PDL((k_control_integrate_hash<false, false>), div_up(s->cap, 256), 256, (float2 *)s->pos, (float2 *)s->vel, s->rad,
                    s->phase, s->absForce_a, s->absForce_r, s->dead, s->hash, s->scratch, time, dt, run_controller, s->cap,
-                   (const uint32_t *)(s->counts + PRS_SC_N), (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u);
+                   (const uint32_t *)(s->counts + PRS_SC_N), (uint32_t *)nullptr, (uint32_t *)nullptr, 0u, 0xffffffffu, 0u, (uint32_t *)nullptr, 0u);
   }
 }
 void prs_slab_migrate_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up) {
@@ -468,7 +683,8 @@ void prs_slab_migrate_unpack(const prs_slab *s, const unsigned *recv_dn, const u
   uint32_t *ticket = g_prs.slab_tickets ? g_prs.sort_ws.vals[0] : nullptr;
   PRS_LAUNCH_PDL(k_slab_fill_holes, div_up(2 * s->mig_cap, 256), 256, *s, ticket);
   PRS_LAUNCH_PDL(k_slab_append, div_up(2 * s->mig_cap, 256), 256, *s, recv_dn, recv_up, slab_log2_gx(),
-                 g_prs.slab_tickets ? g_prs.bin.cellCount : (uint32_t *)nullptr, ticket);
+                 g_prs.slab_tickets ? g_prs.bin.cellCount : (uint32_t *)nullptr, ticket,
+                 (g_prs.slab_tickets && g_prs.slab_range_in_use) ? slab_range_ptr(s) : (uint32_t *)nullptr, slab_range_tile0(s));
   PRS_LAUNCH_PDL(k_slab_commit_count, 1, 1, *s, recv_dn, recv_up);
 }
 /* (hash, local slot) of the owned robots sorted by hash into hash_cat[halo_cap ..] / index_sorted,
@@ -492,15 +708,23 @@ void prs_slab_sort(const prs_slab *s) {
     /* dense start table over the owned rows' cells (same slot offset as the table): read by the collide of the interior rows */
     prs_bin::DenseArgs dn;
     if (g_prs.collide_dense) dn.dense = B.dense + c_lo;
+    /* tiles outside the range the slab's robots occupy are skipped (empty before, empty now); the range was in use in K1 and
+     * for the arrivals, so a ticket outside it has set the violation word and the kernels process everything */
+    prs_bin::RangeArgs ra;
+    if (g_prs.slab_tickets && g_prs.slab_range_in_use) {
+      ra.range = slab_range_ptr(s);
+      /* a row of movement between two sorts + the rows a stencil reaches (2, and the five-cell spill into the next) */
+      ra.dil = (4u * gx + prs_bin::SCAN_TILE - 1u) / prs_bin::SCAN_TILE + 1u;
+    }
     PRS_LAUNCH_PDL(prs_bin::k_cell_tile_sums, tiles, prs_bin::SCAN_THREADS, (const uint32_t *)(B.cellCount + c_lo), cells, B.scratch,
-                   (const uint32_t *)nullptr, prs_bin::DenseArgs());
+                   (const uint32_t *)nullptr, prs_bin::DenseArgs(), ra);
     if (tiles <= prs_bin::SELF_PREFIX_MAX_TILES) {
       PRS_LAUNCH_PDL(prs_bin::k_cell_apply<true>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), dn);
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), dn, ra);
     } else {
       PRS_LAUNCH_PDL(prs_bin::k_cell_scan_tiles, 1, 1024, B.scratch, tiles);
       PRS_LAUNCH_PDL(prs_bin::k_cell_apply<false>, tiles, prs_bin::SCAN_THREADS, B.cellCount + c_lo, s->cellStart + c_lo, s->cellEnd + c_lo,
-                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), dn);
+                     cells, B.scratch, s->halo_cap, (uint32_t *)nullptr, (uint32_t *)nullptr, prs_bin::PatchListArgs(), dn, ra);
     }
     PRS_LAUNCH_PDL(k_slab_scatter, div_up(s->cap, 256), 256, *s, (const uint32_t *)w.vals[0], w.vals[1]);
     g_prs.slab_table_fresh = true; /* consumed by this step's gather and cell_table */
@@ -522,7 +746,9 @@ void prs_slab_gather(const prs_slab *s) {
 }
 void prs_slab_halo_pack(const prs_slab *s, unsigned *send_dn, unsigned *send_up) {
   StageScope t(PRS_STAGE_EXCHANGE);
-  PRS_LAUNCH_PDL(k_slab_halo_pack, min(div_up(2 * s->halo_cap, 256), 592u), 256, *s, send_dn, send_up, g_prs.h_prm.p.gridSize.x);
+  PRS_LAUNCH_PDL(k_slab_halo_pack, min(div_up(2 * s->halo_cap, 256), 592u), 256, *s, send_dn, send_up, g_prs.h_prm.p.gridSize.x,
+                 slab_range_ptr(s), slab_range_tile0(s));
+  if (slab_range_ptr(s)) slab_range_written(s);
 }
 void prs_slab_halo_unpack(const prs_slab *s, const unsigned *recv_dn, const unsigned *recv_up) {
   StageScope t(PRS_STAGE_EXCHANGE);
@@ -530,34 +756,35 @@ void prs_slab_halo_unpack(const prs_slab *s, const unsigned *recv_dn, const unsi
 }
 /* cell table over [halo | owned | halo].  After a binned sort the owned rows' entries already exist
  * (the scan wrote them): only the halo rows are cleared and filled.  Otherwise (onesweep route, or
- * a step without sort: stale table) everything this rank can see is rebuilt. */
-void prs_slab_cell_table(const prs_slab *s) {
-  StageScope t(PRS_STAGE_REORDER);
-  const unsigned gx = g_prs.h_prm.p.gridSize.x, gy = g_prs.h_prm.p.gridSize.y;
+ * a step without sort: stale table) everything this rank can see is rebuilt.
+ * slab_table_clears: which words of cellStart must be set to "empty" first; slab_table_fill: the kernel that writes
+ * the entries (and, on the onesweep route, the report that can admit the binned route). */
+static SlabClears slab_table_clears(const prs_slab *s) {
+  SlabClears cl;
+  for (int r = 0; r < 4; r++) { cl.ptr[r] = nullptr; cl.words[r] = 0u; }
+  int k = 0;
+  auto add = [&](size_t first_row, size_t rows) { if (rows) { cl.ptr[k] = s->cellStart + first_row * g_prs.h_prm.p.gridSize.x; cl.words[k] = (uint32_t)(rows * g_prs.h_prm.p.gridSize.x); k++; } };
+  const unsigned gy = g_prs.h_prm.p.gridSize.y;
   const unsigned r0 = s->row_lo > s->halo_rows ? s->row_lo - s->halo_rows : 0u;
   const unsigned r1 = min(s->row_hi + s->halo_rows, gy);
-  /* ring of slabs: the halo rows that lie beyond the grid edge are the rows at its other end */
-  auto clear_wrapped = [&]() {
-    if (!s->wrap) return;
-    if (s->row_lo < s->halo_rows) {
-      const unsigned rows = min(s->halo_rows - s->row_lo, gy);
-      PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)(gy - rows) * gx, 0xff, (size_t)rows * gx * sizeof(unsigned), g_prs.stream));
-    }
-    if (s->row_hi + s->halo_rows > gy) {
-      const unsigned rows = min(s->row_hi + s->halo_rows - gy, gy);
-      PRS_CUDA(cudaMemsetAsync(s->cellStart, 0xff, (size_t)rows * gx * sizeof(unsigned), g_prs.stream));
-    }
-  };
+  if (s->wrap) { /* ring of slabs: the halo rows that lie beyond the grid edge are the rows at its other end */
+    if (s->row_lo < s->halo_rows) { const unsigned rows = min(s->halo_rows - s->row_lo, gy); add(gy - rows, rows); }
+    if (s->row_hi + s->halo_rows > gy) add(0, min(s->row_hi + s->halo_rows - gy, gy));
+  }
   if (g_prs.slab_binned && g_prs.slab_table_fresh) {
-    clear_wrapped();
-    if (s->row_lo > r0) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(s->row_lo - r0) * gx * sizeof(unsigned), g_prs.stream));
-    if (r1 > s->row_hi) PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)s->row_hi * gx, 0xff, (size_t)(r1 - s->row_hi) * gx * sizeof(unsigned), g_prs.stream));
+    if (s->row_lo > r0) add(r0, s->row_lo - r0);
+    if (r1 > s->row_hi) add(s->row_hi, r1 - s->row_hi);
+  } else {
+    add(r0, r1 - r0);
+  }
+  return cl;
+}
+static void slab_table_fill(const prs_slab *s) {
+  if (g_prs.slab_binned && g_prs.slab_table_fresh) {
     PRS_LAUNCH_PDL(k_slab_halo_table, div_up(2 * s->halo_cap, 256), 256, *s);
     g_prs.slab_table_fresh = false;
     return;
   }
-  clear_wrapped();
-  PRS_CUDA(cudaMemsetAsync(s->cellStart + (size_t)r0 * gx, 0xff, (size_t)(r1 - r0) * gx * sizeof(unsigned), g_prs.stream));
   PRS_LAUNCH_PDL(k_slab_cell_table, div_up(s->cap + 2 * s->halo_cap, 256), 256, *s);
   if (g_prs.slab_sorted_onesweep && g_prs.bin.mode == 0 && !g_prs.bin.admitted) {
     /* report the fullest cell so that the binned route can be admitted */
@@ -567,6 +794,13 @@ void prs_slab_cell_table(const prs_slab *s) {
     bin_send_report(g_prs.bin.scratch + 1);
   }
   g_prs.slab_sorted_onesweep = false;
+}
+void prs_slab_cell_table(const prs_slab *s) {
+  StageScope t(PRS_STAGE_REORDER);
+  const SlabClears cl = slab_table_clears(s);
+  for (int r = 0; r < 4; r++)
+    if (cl.words[r]) PRS_CUDA(cudaMemsetAsync(cl.ptr[r], 0xff, (size_t)cl.words[r] * sizeof(unsigned), g_prs.stream));
+  slab_table_fill(s);
 }
 /* collide for the owned sorted slots [halo_cap, halo_cap + n); results go to the local slots.
  * band 0: all of them; 1: the interior rows only (their stencils stay inside the owned rows: needs no halo);
@@ -728,11 +962,25 @@ unsigned prs_slab_step(prs_slab_ctx *c, float dt, float sort_interval) {
     const unsigned q = ++c->seq_mig, par = q & 1u;
     unsigned *dn = c->peer_dn ? mb_buf(c->peer_dn, c, 1, 0, par) : c->scratch_mig[0]; /* I am the lower rank's UPPER neighbour */
     unsigned *up = c->peer_up ? mb_buf(c->peer_up, c, 0, 0, par) : c->scratch_mig[1];
-    prs_slab_migrate_pack(s, dn, up);
-    prs_slab_signal(c->peer_dn ? mb_flag(c->peer_dn, c, 1, 0) : nullptr, c->peer_up ? mb_flag(c->peer_up, c, 0, 0) : nullptr, q);
-    slab_wait_drop(s, c->peer_dn ? mb_flag(c->mailbox, c, 0, 0) : nullptr, c->peer_up ? mb_flag(c->mailbox, c, 1, 0) : nullptr, q,
-                   mb_buf(c->mailbox, c, 0, 0, par), mb_buf(c->mailbox, c, 1, 0, par));
-    prs_slab_migrate_unpack(s, mb_buf(c->mailbox, c, 0, 0, par), mb_buf(c->mailbox, c, 1, 0, par));
+    if (c->fused_exchange) {
+      /* leavers packed straight into the neighbours' mailboxes, then ONE single-block kernel for the rest of the migration:
+       * count words + flags out, holes filled, flags in, arrivals appended, count committed */
+      StageScope t(PRS_STAGE_EXCHANGE);
+      PRS_LAUNCH_PDL(k_slab_select, div_up(s->cap, 256), 256, *s, dn, up, slab_log2_gx());
+      uint32_t *ticket = g_prs.slab_tickets ? g_prs.sort_ws.vals[0] : nullptr;
+      PRS_LAUNCH_PDL(k_slab_mig_finish, 1, 1024, *s, dn, up, c->peer_dn ? mb_flag(c->peer_dn, c, 1, 0) : (unsigned *)nullptr,
+                     c->peer_up ? mb_flag(c->peer_up, c, 0, 0) : (unsigned *)nullptr,
+                     (const unsigned *)(c->peer_dn ? mb_flag(c->mailbox, c, 0, 0) : nullptr),
+                     (const unsigned *)(c->peer_up ? mb_flag(c->mailbox, c, 1, 0) : nullptr), q, mb_buf(c->mailbox, c, 0, 0, par),
+                     mb_buf(c->mailbox, c, 1, 0, par), slab_log2_gx(), g_prs.slab_tickets ? g_prs.bin.cellCount : (uint32_t *)nullptr, ticket,
+                     (g_prs.slab_tickets && g_prs.slab_range_in_use) ? slab_range_ptr(s) : (uint32_t *)nullptr, slab_range_tile0(s));
+    } else {
+      prs_slab_migrate_pack(s, dn, up);
+      prs_slab_signal(c->peer_dn ? mb_flag(c->peer_dn, c, 1, 0) : nullptr, c->peer_up ? mb_flag(c->peer_up, c, 0, 0) : nullptr, q);
+      slab_wait_drop(s, c->peer_dn ? mb_flag(c->mailbox, c, 0, 0) : nullptr, c->peer_up ? mb_flag(c->mailbox, c, 1, 0) : nullptr, q,
+                     mb_buf(c->mailbox, c, 0, 0, par), mb_buf(c->mailbox, c, 1, 0, par));
+      prs_slab_migrate_unpack(s, mb_buf(c->mailbox, c, 0, 0, par), mb_buf(c->mailbox, c, 1, 0, par));
+    }
     prs_slab_sort(s);
     c->sorted_once = 1;
   }
@@ -742,8 +990,16 @@ unsigned prs_slab_step(prs_slab_ctx *c, float dt, float sort_interval) {
     const unsigned q = ++c->seq_halo, par = q & 1u;
     unsigned *dn = c->peer_dn ? mb_buf(c->peer_dn, c, 1, 1, par) : c->scratch_halo[0];
     unsigned *up = c->peer_up ? mb_buf(c->peer_up, c, 0, 1, par) : c->scratch_halo[1];
-    prs_slab_halo_pack(s, dn, up);
-    prs_slab_signal(c->peer_dn ? mb_flag(c->peer_dn, c, 1, 1) : nullptr, c->peer_up ? mb_flag(c->peer_up, c, 0, 1) : nullptr, q);
+    if (c->fused_exchange) { /* the last block of the pack kernel publishes the flags */
+      StageScope t(PRS_STAGE_EXCHANGE);
+      PRS_LAUNCH_PDL(k_slab_halo_pack_signal, min(div_up(2 * s->halo_cap, 256), 592u), 256, *s, dn, up, g_prs.h_prm.p.gridSize.x,
+                     c->peer_dn ? mb_flag(c->peer_dn, c, 1, 1) : (unsigned *)nullptr,
+                     c->peer_up ? mb_flag(c->peer_up, c, 0, 1) : (unsigned *)nullptr, q, slab_range_ptr(s), slab_range_tile0(s));
+      if (slab_range_ptr(s)) slab_range_written(s);
+    } else {
+      prs_slab_halo_pack(s, dn, up);
+      prs_slab_signal(c->peer_dn ? mb_flag(c->peer_dn, c, 1, 1) : nullptr, c->peer_up ? mb_flag(c->peer_up, c, 0, 1) : nullptr, q);
+    }
     const bool split = c->overlap_exchange && (c->peer_dn || c->peer_up);
     if (split) {
       /* interior first: after a binned sort the owned rows' table entries exist already; otherwise (onesweep route,
@@ -756,10 +1012,22 @@ unsigned prs_slab_step(prs_slab_ctx *c, float dt, float sort_interval) {
       }
     }
     const bool interior_done = split && g_prs.slab_binned && g_prs.slab_table_fresh;
-    slab_wait_drop(s, c->peer_dn ? mb_flag(c->mailbox, c, 0, 1) : nullptr, c->peer_up ? mb_flag(c->mailbox, c, 1, 1) : nullptr, q,
-                   mb_buf(c->mailbox, c, 0, 1, par), mb_buf(c->mailbox, c, 1, 1, par));
-    prs_slab_halo_unpack(s, mb_buf(c->mailbox, c, 0, 1, par), mb_buf(c->mailbox, c, 1, 1, par));
-    prs_slab_cell_table(s);
+    if (c->fused_exchange) { /* one kernel waits for the flags, unpacks the halos and clears the halo rows of the table */
+      {
+        StageScope t(PRS_STAGE_EXCHANGE);
+        const SlabClears cl = slab_table_clears(s);
+        PRS_LAUNCH_PDL(k_slab_halo_unpack_wait, min(div_up(2 * s->halo_cap, 256), 592u), 256, *s, mb_buf(c->mailbox, c, 0, 1, par),
+                       mb_buf(c->mailbox, c, 1, 1, par), (const unsigned *)(c->peer_dn ? mb_flag(c->mailbox, c, 0, 1) : nullptr),
+                       (const unsigned *)(c->peer_up ? mb_flag(c->mailbox, c, 1, 1) : nullptr), q, cl);
+      }
+      StageScope t(PRS_STAGE_REORDER);
+      slab_table_fill(s);
+    } else {
+      slab_wait_drop(s, c->peer_dn ? mb_flag(c->mailbox, c, 0, 1) : nullptr, c->peer_up ? mb_flag(c->mailbox, c, 1, 1) : nullptr, q,
+                     mb_buf(c->mailbox, c, 0, 1, par), mb_buf(c->mailbox, c, 1, 1, par));
+      prs_slab_halo_unpack(s, mb_buf(c->mailbox, c, 0, 1, par), mb_buf(c->mailbox, c, 1, 1, par));
+      prs_slab_cell_table(s);
+    }
     StageScope t(PRS_STAGE_COLLIDE);
     if (interior_done) {
       slab_collide_band(s, dt, 2);

@@ -209,7 +209,8 @@ class SlabSim:
     stand-in); `group` is the torch.distributed process group (None = default)."""
 
     def __init__(self, params, opt, backend, rank, world, device, pos, gid, rows, capacity=None, halo_cap=None,
-                 mig_cap=None, group=None, exchange="nccl", native_step=True, overlap_exchange=True, wrap=False):
+                 mig_cap=None, group=None, exchange="nccl", native_step=True, overlap_exchange=True, wrap=False,
+                 fused_exchange=True):
         self.p, self.opt, self.be = params, opt, backend
         self.rank, self.world, self.dev, self.group = rank, world, device, group
         # wrap: the slabs form a ring in the row index (the cell hash wraps around the grid, SURVEY.md Q9 — e.g. the reference's
@@ -265,10 +266,10 @@ class SlabSim:
         elif exchange != "nccl":
             raise ValueError(exchange)
         if self.exchange == "p2p" and native_step and isinstance(backend, CudaBackend):
-            self._setup_native_step(mw, hw, overlap_exchange)
+            self._setup_native_step(mw, hw, overlap_exchange, fused_exchange)
 
     # ---- the whole step in the library (prs_slab_step): this class only keeps the process-group plumbing ------------
-    def _setup_native_step(self, mw, hw, overlap_exchange):
+    def _setup_native_step(self, mw, hw, overlap_exchange, fused_exchange=True):
         c = prs.SlabCtx()
         c.slab = self.be.slab
         c.mailbox, c.peer_dn, c.peer_up = self.mailbox, self.peer[0], self.peer[1]
@@ -285,6 +286,7 @@ class SlabSim:
         self._allreduce_cb = prs.ALLREDUCE_MIN_FN(allreduce_min)     # keep the callback object alive
         c.allreduce_min = self._allreduce_cb
         c.overlap_exchange = 1 if overlap_exchange else 0
+        c.fused_exchange = 1 if fused_exchange else 0
         c.time, c.sorted_once = 0.0, 0
         self.ctx = c
 

@@ -227,8 +227,8 @@ hexblock_jitter
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ranks", [2, 3])
-def test_cpp_launcher_hexblock_equals_one_gpu(tmp_path, ranks):
+@pytest.mark.parametrize("ranks,extra", [(2, ()), (3, ()), (2, ("--no-fused-exchange",)), (2, ("--no-overlap",))])
+def test_cpp_launcher_hexblock_equals_one_gpu(tmp_path, ranks, extra):
     """`ParticleBot cfg --gpus N` (forked ranks, CUDA IPC mailboxes, shared-memory control plane) == `ParticleBot cfg` on one
     GPU, bit for bit, after 60 steps of a 49 152-robot block with 150 dead robots drawn at step 0 — positions, velocities,
     radii, phases in robot order — and the CSV of rank 0 equals the single-GPU CSV byte for byte (centroid summed in robot
@@ -236,7 +236,7 @@ def test_cpp_launcher_hexblock_equals_one_gpu(tmp_path, ranks):
     text = HEX_CFG.format(n=256 * 192, dead=150, sort=0.01, tag="hex", testing=0, nx=256, ny=192)
     one, _ = _run_launcher(tmp_path, text, 1, 60, "hex")
     csv_one = (tmp_path / "launcher_hex.csv").read_bytes()
-    many, err = _run_launcher(tmp_path, text, ranks, 60, "hex")
+    many, err = _run_launcher(tmp_path, text, ranks, 60, "hex", extra)   # extra: one kernel per exchange operation / no overlap
     csv_many = (tmp_path / "launcher_hex.csv").read_bytes()
     assert f"on {ranks} ranks" in err
     for k in ("pos", "vel", "rad", "phase"):
