@@ -11,15 +11,19 @@ L = prs.lib()
 L.prs_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
 nt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 L.prs_sort_set_threads(nt)
-tile = L.prs_sort_tile_size()
-tiles = (n + tile - 1) // tile
-npass = (bits + 7) // 8
+plan = (C.c_int * 6)()
+npass = L.prs_sort_plan(bits, n, plan)          # digits of this sort: 8 bits, or 9 where that saves a pass (prs_onesweep.cuh)
 g = torch.Generator(device="cuda").manual_seed(1)
 # cell-key-like input: lattice order, keys mostly ascending with local disorder
 base = (torch.arange(n, device="cuda", dtype=torch.int64) * (1 << bits) // n)
 keys = ((base + torch.randint(0, 1 << (bits // 2), (n,), device="cuda", generator=g)) % (1 << bits)).to(torch.int32)
 vals = torch.arange(n, device="cuda", dtype=torch.int32)
 ok, ov = torch.empty_like(keys), torch.empty_like(vals)
+L.prs_sort_pairs(keys.data_ptr(), vals.data_ptr(), ok.data_ptr(), ov.data_ptr(), n, bits)
+torch.cuda.synchronize()
+tile = L.prs_sort_tile_size()                   # pairs per tile of that sort
+tiles = (n + tile - 1) // tile
+print(f"n=2^{log2n}, {bits}-bit keys: digits {[plan[i] for i in range(npass)]}, {tile} pairs per tile, {tiles} tiles")
 tl = torch.zeros(npass * tiles * 8, dtype=torch.int64, device="cuda")
 for it in range(3):
     L.prs_sort_set_timeline(C.c_void_p(tl.data_ptr()) if it == 2 else None)
