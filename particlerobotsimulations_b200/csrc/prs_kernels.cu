@@ -920,6 +920,7 @@ void setParameters(SimParams *hp) {
   d.world_half = g_prs.world_half;
   g_prs.params_set = true;
   PRS_CUDA(cudaMemcpyToSymbolAsync(c_prm, &d, sizeof(d), 0, cudaMemcpyHostToDevice, g_prs.stream));
+  PRS_LAUNCH(prs::k_collide_constants, 1, 1, 0); /* per-parameter-set constants of collide (prs_collide.cuh) */
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
 }
 
@@ -1441,7 +1442,8 @@ void prs_fused_step(const prs_step_buffers *b, float time, float dt, int do_sort
       prs::PackedLayout in{(const float4 *)b->sortedPR, (const float2 *)b->sortedVel};
       if (patch) launch_collide_patch((float2 *)b->vel, b->absForce_r, in.pr, in.vel, b->cellStart, b->cellEnd, dt);
       else prs_launch_collide_t((float2 *)b->vel, b->absForce_a, b->absForce_r, in, b->cellStart, b->cellEnd, n, dt, need_fa, 0u,
-                                (const uint32_t *)nullptr, 0, (const uint32_t *)nullptr, use_dense ? (const uint32_t *)B.dense : nullptr);
+                                (const uint32_t *)nullptr, 0, (const uint32_t *)nullptr, use_dense ? (const uint32_t *)B.dense : nullptr,
+                                use_dense ? (const uint32_t *)b->hash : nullptr);
     }
     /* fullest cell of this sort -> pinned host memory (nobody touches the two words before the next step's
      * memset); issued after collide so that the kernels of the step stay adjacent in the stream */

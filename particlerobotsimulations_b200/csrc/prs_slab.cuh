@@ -812,7 +812,8 @@ static void slab_collide_band(const prs_slab *s, float dt, int band) {
   /* interior rows right after a binned sort: their stencils stay inside the owned rows, whose dense start table the scan has written */
   const uint32_t *dense = (band == 1 && g_prs.collide_dense && g_prs.slab_binned && g_prs.slab_table_fresh) ? g_prs.bin.dense : nullptr;
   prs_launch_collide_t((float2 *)s->vel, s->absForce_a, s->absForce_r, in, s->cellStart, s->cellEnd, s->halo_cap + span, dt,
-                       need_fa, s->halo_cap, s->counts + PRS_SC_N, band, s->index_sorted - s->halo_cap, dense);
+                       need_fa, s->halo_cap, s->counts + PRS_SC_N, band, s->index_sorted - s->halo_cap, dense,
+                       dense ? (const uint32_t *)s->hash_cat : nullptr);
 }
 void prs_slab_collide(const prs_slab *s, float dt) {
   slab_check(s);
