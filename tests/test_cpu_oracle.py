@@ -288,3 +288,41 @@ def test_oracle_against_reference_kernel_goldens(name, tag):
             assert np.abs(pos.mean(0) - g[f"pos_{step}"].mean(0)).max() < 2e-3, step
             assert np.abs(pos - g[f"pos_{step}"]).max() < 0.05, step
         assert util.rel_err(s.get("phase"), g[f"phase_{step}"], 1.0) < 2e-5, step
+
+
+# --------------------------------------------------------------------------------------------
+# host-side pieces of the product that need no GPU
+# --------------------------------------------------------------------------------------------
+def test_sort_digit_plan():
+    """prs_sort_plan (csrc/prs_onesweep.cuh plan_passes): 8-bit digits unless 9-bit ones save a whole pass over the pairs,
+    then as few 9-bit passes as cover the key; 12 pairs per thread only for large sorts with 8-bit digits"""
+    L = prs.lib()
+    plan = (C.c_int * 6)()
+    want = {7: [8], 8: [8], 9: [9], 16: [8, 8], 17: [9, 8], 18: [9, 9], 19: [8, 8, 8], 22: [8, 8, 8], 24: [8, 8, 8],
+            25: [9, 8, 8], 26: [9, 9, 8], 27: [9, 9, 9], 28: [8, 8, 8, 8], 32: [8, 8, 8, 8]}
+    for bits, digits in want.items():
+        n = L.prs_sort_plan(bits, 1 << 20, plan)
+        assert [plan[i] for i in range(n)] == digits and sum(digits) >= bits, (bits, list(plan))
+        assert plan[4] == 8
+    assert L.prs_sort_plan(24, 1 << 23, plan) == 3 and plan[4] == 12        # large, 8-bit digits: 12 pairs per thread
+    assert L.prs_sort_plan(26, 1 << 26, plan) == 3 and plan[4] == 8         # 9-bit tiles stay at 8
+    assert L.prs_sort_plan(0, 10, plan) == 1 and L.prs_sort_plan(99, 10, plan) == 4   # clamped like prs_sort_pairs
+
+
+def test_slab_launcher_fails_loudly_without_a_gpu(tmp_path):
+    """`ParticleBot cfg --gpus 2` on a box without a CUDA device: every rank reports the error, the parent returns 1 —
+    no hang at the process-shared barrier, no CPU fallback (skipped where a GPU is present: tests/test_multigpu_gpu.py runs it)"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    exe = os.path.join(util.ROOT, "particlerobotsimulations_b200", "ParticleBot")
+    r = subprocess.run([exe, os.path.join(util.ROOT, "examples", "example.cfg"), "--gpus", "2", "--steps", "3", "--no-csv", "--quiet"],
+                       capture_output=True, text=True, cwd=str(tmp_path), timeout=120)
+    assert r.returncode == 1 and "prs_multi_run: rank" in r.stderr, (r.returncode, r.stderr[-400:])
+    r = subprocess.run([exe, os.path.join(util.ROOT, "examples", "example.cfg"), "--gpus", "2", "--video"], capture_output=True, text=True,
+                       cwd=str(tmp_path), timeout=120)
+    assert r.returncode == 2 and "--gpus N runs the fused slab engine" in r.stderr
