@@ -1099,6 +1099,7 @@ void prs_host_step_plan(const float *pos_in, const float *vel_in, const float *r
 }
 void prs_set_plan_chunks(unsigned chunks) { g_prs.plan_chunks = chunks; }
 void prs_host_step_sync(void) {
+  g_prs.plan.active = false; /* a plan whose step never reached prs_fused_step must not outlive the host-buffer step */
   if (g_prs.copy_stream) PRS_CUDA(cudaStreamSynchronize(g_prs.copy_stream));
   PRS_CUDA(cudaStreamSynchronize(g_prs.stream));
 }
