@@ -9,34 +9,4 @@ import json
 d=json.loads(open("gpurun_out/bench_scale_2x.json").read().strip().splitlines()[-1])
 print(d["n_gpus"], d["value"], d["ms_per_step"], d["config"]["exchange"], {k:round(v["us_per_step"],1) for k,v in d["stages_rank0"].items()}, d["e2e"]["value"], d.get("parity_check"), d.get("speedup_vs_one_gpu"))
 PY
-cat > /tmp/s2.cfg <<'CFG'
-nCells
-67108864
-nDead
-0
-light_x
--700
-light_y
-0
-max_time
-1e30
-seed
-5555
-sort_interval
-0.01
-init_config
-hexblock
-hexblock_nx
-8192
-hexblock_ny
-8192
-hexblock_pitch
-0.17
-hexblock_jitter
-0.01
-world_half
-896
-grid_dim
-8192
-CFG
-cd /tmp && for g in 2; do timeout 600 $GRAFT_REPO_ROOT/particlerobotsimulations_b200/ParticleBot /tmp/s2.cfg --gpus $g --steps 300 --no-csv --quiet 2>&1 | tail -2; done
+cd /tmp && for g in 2; do timeout 600 $GRAFT_REPO_ROOT/particlerobotsimulations_b200/ParticleBot $GRAFT_REPO_ROOT/examples/synthetic_s2.cfg --gpus $g --steps 300 --no-csv --quiet 2>&1 | tail -2; done

@@ -9,35 +9,5 @@ d=json.loads(open(f"gpurun_out/bench_scale_{sys.argv[1]}x.json").read().strip().
 print(d.get("stages_us_per_rank"))
 print(d["n_gpus"], d["value"], d["ms_per_step"], {k:round(v["us_per_step"],1) for k,v in d["stages_rank0"].items()}, "e2e", d["e2e"]["ms_per_step"], d["e2e"].get("cpus_bound_rank0"), d.get("parity_check",{}).get("bit_equal"), d.get("speedup_vs_one_gpu"), d["one_gpu_same_workload"]["ms_per_step"])
 PY
-cat > /tmp/s2.cfg <<'CFG'
-nCells
-67108864
-nDead
-0
-light_x
--700
-light_y
-0
-max_time
-1e30
-seed
-5555
-sort_interval
-0.01
-init_config
-hexblock
-hexblock_nx
-8192
-hexblock_ny
-8192
-hexblock_pitch
-0.17
-hexblock_jitter
-0.01
-world_half
-896
-grid_dim
-8192
-CFG
-cd /tmp && timeout 600 $GRAFT_REPO_ROOT/particlerobotsimulations_b200/ParticleBot /tmp/s2.cfg --gpus $N --steps 400 --no-csv --quiet 2>&1 | tail -3
+cd /tmp && timeout 600 $GRAFT_REPO_ROOT/particlerobotsimulations_b200/ParticleBot $GRAFT_REPO_ROOT/examples/synthetic_s2.cfg --gpus $N --steps 400 --no-csv --quiet 2>&1 | tail -3
 nvidia-smi topo -m 2>/dev/null | head -14; lscpu | grep -i "numa\|socket\|^CPU(s)" | head
